@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — rendered views/sec, forward + backward, of the splat-render path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--kind trained|init] [--workload zero123g|lgm_big]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the path's CPU implementation (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch of synthetic input: GaussianRenderer.render of all B x V views
+(forward), then backward from given upstream gradients to dL/d[B,N,14] (clamp mask included), as
+/root/reference/core/models.py:141 + main.py:102 drive it.  Workload at N = 1 ("zero123g", BASELINE.json configs[2],
+the configuration the north_star target is quoted on): 8 scenes x 26 views, 98,304 Gaussians per scene, 320^2,
+fovy 60.  At N GPUs the step has 8N scenes (weak scaling): the B*V views are partitioned across ranks, Gaussians are
+broadcast from rank 0, per-Gaussian gradients are combined with one NCCL all-reduce.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job views/s with inputs resident in HBM; `e2e` = the same metric
+with, every step, the step's inputs (Gaussians, cameras, ground-truth images and masks) copied from pinned host
+memory and the loss read back; `roofline` = the onesweep sort (dominant HBM-bound kernel group), algorithmic bytes /
+CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scenes per GPU, views per scene, Gaussians per scene, image size, fovy, BASELINE.json config)
+    "zero123g": (8, 26, 98304, 320, 60.0, "configs[2] Zero-1-to-G: 6x128^2 splatter = 98,304 Gaussians, 26 views at 320^2, batch 8"),
+    "lgm_big": (1, 8, 65536, 512, 49.1, "configs[1] LGM default: 65,536 Gaussians, 8 views at 512^2, batch 1"),
+    "tiny": (1, 1, 16384, 256, 49.1, "configs[0] tiny: 16,384 Gaussians, 1 view at 256^2"),
+}
+METRIC = "rendered views/sec fwd+bwd"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="zero123g", choices=sorted(WORKLOADS))
+    ap.add_argument("--kind", default="trained", choices=["trained", "init"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, kind, steps, warmup, budget_s=20.0):
+    """The oracle port (oracle/splat_oracle.c, OpenMP over views) on a bounded sample of the workload."""
+    import numpy as np
+    from oracle.oracle import Oracle, build
+    from lgm_b200.synthetic import make_bg, make_cameras, make_gaussians, make_upstream_grads
+    build()
+    o = Oracle("f32")
+    cores = o.num_threads()
+    B, V, N, S, fovy, _ = WORKLOADS[workload]
+    nv = max(1, min(V, cores))  # one scene, up to one view per thread
+    g = make_gaussians(1, N, kind, seed=1234).numpy()
+    cv, cvp, _ = make_cameras(1, V, fovy=fovy, seed=1234)
+    cv, cvp = cv[:, :nv].numpy(), cvp[:, :nv].numpy()
+    d_img, d_alpha, d_depth = [x[:, :nv].numpy() for x in make_upstream_grads(1, V, S, S, seed=1234)]
+    bg = make_bg().numpy()
+    t = math.tan(0.5 * math.radians(fovy))
+
+    def step():
+        o.render_step(g, cv, cvp, bg, S, S, t, t, 1.0, d_img, d_alpha, d_depth)
+
+    t0 = time.time()
+    step()  # first call also sizes the sample
+    one = time.time() - t0
+    steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+    for _ in range(max(0, min(warmup, 1))):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / steps
+    return dict(value=nv / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"1 scene x {nv} of {V} views ({workload}, {kind}-like), fwd+bwd, {steps} timed steps, "
+                       f"oracle/splat_oracle.c with OpenMP over views"), dt, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, dt, steps = cpu_reference_run(args.workload, args.kind, args.steps, args.warmup, budget_s=60.0)
+    B, V, N, S, fovy, cfgname = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {cfgname}; {args.kind}-like Gaussians; bounded sample: {cb['sample']}",
+                   "note": "the reference's rasterizer (ashawkey/diff-gaussian-rasterization) is CUDA-only and not "
+                           "available offline; this arm times the CPU oracle port of the same path on the host cores"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from lgm_b200 import default_options, ops, _lib
+    from lgm_b200.dist import ShardedGaussianRenderer
+    from lgm_b200.synthetic import make_bg, make_cameras, make_gaussians
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    _lib.lib()  # fail loudly now if the extension is missing
+
+    Bg, V, N, S, fovy, cfgname = WORKLOADS[args.workload]
+    B = Bg * world
+    opt = default_options(output_size=S, fovy=fovy)
+    renderer = ShardedGaussianRenderer(opt, device=dev)
+    # host-side (pinned) copies of the step's inputs; device-resident copies for the HBM-resident `value`
+    g_host = make_gaussians(B, N, args.kind, seed=1234).pin_memory()
+    cv, cvp, cp = make_cameras(B, V, fovy=fovy, seed=1234)
+    cv_host, cvp_host, cp_host = cv.pin_memory(), cvp.pin_memory(), cp.pin_memory()
+    bg = make_bg().to(dev)
+    n_views_total = B * V
+    per = (n_views_total + world - 1) // world
+    b0, b1 = min(n_views_total, rank * per), min(n_views_total, (rank + 1) * per)
+    n_local = b1 - b0
+    gen = torch.Generator().manual_seed(4321 + rank)
+    gt_img_host = torch.rand(n_local, 3, S, S, generator=gen).pin_memory()     # ground-truth views of this rank's block
+    gt_mask_host = (torch.rand(n_local, 1, S, S, generator=gen) > 0.5).float().pin_memory()
+    g_dev = g_host.to(dev)
+    cv_dev, cvp_dev, cp_dev = cv_host.to(dev), cvp_host.to(dev), cp_host.to(dev)
+    # upstream gradients of the loss shape 2 (x - gt) / numel (core/models.py:153), resident
+    d_img = (2.0 * (torch.rand(n_local, 3, S, S, generator=gen) - torch.rand(n_local, 3, S, S, generator=gen)) / (n_views_total * 3 * S * S)).to(dev)
+    d_alpha = (2.0 * (torch.rand(n_local, 1, S, S, generator=gen) - torch.rand(n_local, 1, S, S, generator=gen)) / (n_views_total * S * S)).to(dev)
+    src = 0 if world > 1 else None
+    info = {}
+
+    def step_resident():
+        g = g_dev.detach().requires_grad_(True)
+        out = renderer.render(g, cv_dev, cvp_dev, cp_dev, bg_color=bg, broadcast_src=src)
+        torch.autograd.backward([out["image"], out["alpha"]], [d_img, d_alpha])
+        return g.grad
+
+    def step_e2e():
+        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
+        cvd, cvpd, cpd = cv_host.to(dev, non_blocking=True), cvp_host.to(dev, non_blocking=True), cp_host.to(dev, non_blocking=True)
+        gt_i, gt_m = gt_img_host.to(dev, non_blocking=True), gt_mask_host.to(dev, non_blocking=True)
+        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src)
+        # loss of /root/reference/core/models.py:153 (MSE image + MSE alpha), normalised over the whole job
+        loss = ((out["image"] - gt_i) ** 2).sum() / (n_views_total * 3 * S * S) + ((out["alpha"] - gt_m) ** 2).sum() / (n_views_total * S * S)
+        loss.backward()
+        return float(loss.item())  # D2H read of the step's result
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        k0 = ops.launch_counter["kernels"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        launches = ops.launch_counter["kernels"] - k0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_views_total / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e, _ = timed(step_e2e, max(2, args.steps // 2), 2)
+        h2d = sum(t.numel() * t.element_size() for t in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host))
+        e2e = {"value": n_views_total / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 8,
+               "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss -> backward -> loss.item()"}
+
+    # ---- stage breakdown + roofline of the HBM-bound group, measured live with CUDA events (rank 0) ----
+    stages, roofline, extra = None, None, {}
+    if rank == 0 and not args.no_stages:
+        ops.enable_stage_timing(True)
+        for _ in range(2):
+            step_resident()
+        ops.stage_times_ms()
+        nrep = 3
+        for _ in range(nrep):
+            step_resident()
+        tms = ops.stage_times_ms()
+        ops.enable_stage_timing(False)
+        stages = {k: sum(v) / nrep for k, v in tms.items()}
+        # instance count and tile statistics of this rank's block
+        from lgm_b200.dist import shard_views
+        vm, pm, _, scene, _ = shard_views(cv_dev, cvp_dev, cp_dev, rank, world)
+        bsc = int(scene[0]); esc = int(scene[-1]) + 1
+        cfg = ops.ViewConfig(S, S, float(renderer.inner.tan_half_fov), float(renderer.inner.tan_half_fov), 1.0, keep_binning=True)
+        sc = (scene - bsc).int()
+        off = torch.zeros(esc - bsc + 1, dtype=torch.int32)
+        off[1:] = torch.cumsum(torch.bincount(sc.long(), minlength=esc - bsc), 0).int()
+        with torch.no_grad():
+            _, _, _, st = ops.forward_views(g_dev[bsc:esc], vm, pm, sc.to(dev), off.to(dev), bg, cfg)
+        Lr = st.num_rendered
+        n_tiles = ((S + 15) // 16) ** 2
+        npass = ops.sort_passes(n_local * n_tiles)
+        end_bit = 32 + max(1, (max(n_local * n_tiles, 1) - 1).bit_length())
+        # the sort alone, on the step's real (unsorted-order irrelevant for timing: use the sorted keys shuffled) keys
+        Lb = _lib.lib()
+        perm = torch.randperm(Lr, device=dev)
+        keys_u = st.keys[:Lr][perm].contiguous()
+        vals_u = st.vals[:Lr][perm].contiguous()
+        k_other, v_other = torch.empty_like(keys_u), torch.empty_like(vals_u)
+        in_tmp = bool(Lb.lgm_sort_input_is_tmp(end_bit))
+        import ctypes
+        nb = ctypes.c_size_t(0)
+        _lib.check(Lb.lgm_sort_workspace_bytes(Lr, end_bit, nb), "ws")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        sort_ms = []
+        for it in range(5):
+            kin, vin = keys_u.clone(), vals_u.clone()
+            ko, vo, kt, vt = (k_other, v_other, kin, vin) if in_tmp else (kin, vin, k_other, v_other)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(Lb.lgm_sort_pairs(torch.cuda.current_stream().cuda_stream, _lib.ptr(ko), _lib.ptr(vo), _lib.ptr(kt),
+                                         _lib.ptr(vt), Lr, end_bit, _lib.ptr(ws), nb.value), "sort")
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                sort_ms.append(a.elapsed_time(b))
+        t_sort = sum(sort_ms) / len(sort_ms)
+        peak, peak_src = load_peaks()
+        sort_bytes = (npass * 24 + 8) * Lr
+        ach = sort_bytes / (t_sort * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": f"onesweep radix sort (histogram + {npass} passes, u64 key + u32 value)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
+                    "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
+        # SURVEY §8d group accounting: preprocess + emit + sort + ranges
+        P_ = N
+        grp_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
+        t_grp = stages.get("geom", 0.0) + stages.get("bin", 0.0)
+        lens = (st.ranges[:, 1] - st.ranges[:, 0]).long()
+        pair_evals = int(lens.sum()) * 256
+        extra = {
+            "instances_per_step_rank0": Lr, "instances_per_view": Lr / max(n_local, 1),
+            "roofline_preprocess_sort": {"bound": "hbm", "achieved": grp_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
+                                         "peak": peak, "unit": "GB/s", "frac": (grp_bytes / (t_grp * 1e-3) / 1e9) / peak if t_grp > 0 else None,
+                                         "algorithmic_bytes": int(grp_bytes), "ms": t_grp},
+            "composite": {"pair_evals_upper_bound": pair_evals,
+                          "fwd_gpairs_per_s": pair_evals / (stages.get("composite_fwd", float("nan")) * 1e-3) / 1e9,
+                          "bwd_gpairs_per_s": pair_evals / (stages.get("composite_bwd", float("nan")) * 1e-3) / 1e9,
+                          "max_tile_len": int(lens.max()), "mean_tile_len": float(lens.float().mean())},
+        }
+        del st
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_reference_run(args.workload, args.kind, 3, 0, budget_s=15.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfgname}; per GPU {Bg} scenes x {V} views = {Bg * V} views/step, "
+                                   f"{args.kind}-like Gaussians (SURVEY.md 8d), step = {B} scenes view-sharded over {world} GPU(s)",
+                       "global_views": n_views_total, "gaussians_per_scene": N, "image": f"{S}x{S}",
+                       "parallelism": f"view-sharded x{world}" + (", broadcast + NCCL all-reduce of [B,N,14] grads" if world > 1 else ""),
+                       "l2": "per-step working set (>= 2 GB of geometry, instances and images) >> 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "stages_ms": stages,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,138 @@
+/*
+ * lgm_b200.h — C-ABI of the sm_100a Gaussian-splat render path (liblgm_b200.so).
+ *
+ * Drop-in boundary for the device side of LGM's renderer: these entry points are what a binding of
+ * `diff_gaussian_rasterization._C` would call in place of the external rasterizer's pybind exports
+ *   rasterize_gaussians            (called from /root/reference/core/gs.py:76-85 via GaussianRasterizer.forward)
+ *   rasterize_gaussians_backward   (autograd backward of the same call, driven by /root/reference/main.py:102)
+ *   mark_visible                   (GaussianRasterizer.markVisible; API surface, not used by LGM)
+ * but batched: one call renders ALL B x V views of a step (the Python double loop of /root/reference/core/gs.py:42-93)
+ * and one call back-propagates them, accumulating per-Gaussian gradients over the views of a scene.
+ *
+ * Conventions
+ *  - plain pointers and sizes; every pointer is DEVICE memory on the current device unless it says "host";
+ *    fp32, contiguous.  The caller owns all memory; the library never allocates, frees or keeps pointers.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises.
+ *  - returns 0 on success, a negative lgm_status for an invalid argument, a positive cudaError_t for a CUDA
+ *    failure; lgm_last_error_string() describes the last non-zero return of the calling thread.
+ *    No C++ exception crosses the ABI.
+ *  - gaussians [n_scenes, P, 14]: 0:3 position, 3 opacity, 4:7 scale, 7:11 rotation (w,x,y,z; used as given),
+ *    11:14 rgb  — the channel split of /root/reference/core/gs.py:45-49.
+ *  - view_mats / proj_mats [n_views, 16]: cam_view / cam_view_proj of /root/reference/core/provider_lvis.py:207-208
+ *    flattened row-major (the kernels read m[i + 4k] as row i of the transform, as the external rasterizer does).
+ *  - bg [3]: background colour, DEVICE memory (the reference passes a CUDA tensor, /root/reference/core/gs.py:20,63),
+ *    read by the kernels so that no host copy / synchronisation is needed.
+ *  - view_scene [n_views] int32: scene index of every view; views of one scene must be contiguous.
+ *    scene_view_offsets [n_scenes + 1] int32: first view of every scene (exclusive prefix of views per scene).
+ */
+#ifndef LGM_B200_H
+#define LGM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum lgm_status {
+    LGM_OK = 0,
+    LGM_ERR_NULL_POINTER = -1,
+    LGM_ERR_BAD_SHAPE = -2,
+    LGM_ERR_WORKSPACE_TOO_SMALL = -3,
+    LGM_ERR_TOO_MANY_INSTANCES = -4, /* L >= 2^30 in one call: split the views into chunks */
+    LGM_ERR_BAD_VALUE = -5
+};
+
+/* What GaussianRasterizationSettings carries (/root/reference/core/gs.py:58-71), for a batch of views. */
+typedef struct lgm_render_params {
+    int32_t n_scenes;      /* B */
+    int32_t n_gaussians;   /* P, per scene */
+    int32_t n_views;       /* all views of this call */
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+} lgm_render_params;
+
+#define LGM_GRAD_ROW 12 /* floats per (view, Gaussian) gradient row: mean2D 2, conic 3, opacity 1, rgb 3, depth 1, pad 2 */
+
+int lgm_abi_version(void);
+const char* lgm_last_error_string(void);
+
+/* Number of 16x16 tiles of one view. */
+int lgm_tiles_per_view(int32_t image_height, int32_t image_width);
+/* Number of per-(view, 256-Gaussian block) partial sums forward_geom writes: n_views * ceil(P / 256). */
+int64_t lgm_num_block_sums(int32_t n_gaussians, int32_t n_views);
+/* Scratch bytes forward_bin needs for L instances (alternate key/value buffers, histograms, look-back state). */
+int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes);
+
+/* K1 preprocess + instance-offset scan.  Replaces preprocessCUDA + InclusiveSum (+ its blocking D2H: here the
+ * total stays on the device in total_instances[0], read back once per step by the host wrapper).
+ * Outputs, each [n_views * P]: depth f32, radii i32 (0 = culled), xy float2, conic_opacity float4;
+ * tiles_touched u32 is optional (NULL to skip).  block_offsets [lgm_num_block_sums] u32 (exclusive scan),
+ * block_sums same size (scratch).  total_instances: 1 x u64.                                              */
+int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                     const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                     float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                     uint64_t* total_instances);
+
+/* K2 emit + K3 onesweep sort + K4 ranges.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
+ * n_instances = the value forward_geom left in total_instances.  keys_sorted u64[L] (view*tiles+tile << 32 |
+ * depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges uint2[n_views * tiles] = [start,end).   */
+int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
+                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
+                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes);
+
+/* K5 compositing.  Replaces renderCUDA fwd.  image [n_views,3,H,W] (not clamped), alpha / depth_img [n_views,H,W],
+ * n_contrib u32 [n_views,H,W].                                                                              */
+int lgm_forward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
+                          const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
+                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, float* image,
+                          float* alpha, float* depth_img, uint32_t* n_contrib);
+
+/* forward_bin followed by forward_composite (SURVEY.md §8b level 3, entry 3). */
+int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
+                           const int32_t* view_scene, const int32_t* radii, const float* xy,
+                           const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
+                           int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
+                           void* workspace, size_t workspace_bytes, const float* bg, float* image, float* alpha,
+                           float* depth_img, uint32_t* n_contrib);
+
+/* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
+ * grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on return it holds the
+ * per-view screen-space gradients (dL/dmean2D in [0:2] is what means2D.grad receives upstream).
+ * dL_dgaussians [n_scenes, P, 14]: per-Gaussian gradients summed over the views of each scene; overwritten when
+ * accumulate == 0, added to when accumulate != 0 (view chunks of one step).                                  */
+int lgm_backward(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                 const float* proj_mats, const int32_t* view_scene, const int32_t* scene_view_offsets,
+                 const int32_t* radii, const float* xy, const float* conic_opacity, const float* depth,
+                 const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, const float* alpha,
+                 const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth, float* grad_rows,
+                 float* dL_dgaussians, int32_t accumulate);
+
+/* The two halves of lgm_backward, exposed for the parity tests. */
+int lgm_backward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
+                           const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
+                           const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, const float* alpha,
+                           const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha,
+                           const float* dL_ddepth, float* grad_rows);
+int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                      const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
+                      const float* grad_rows, float* dL_dgaussians, int32_t accumulate);
+
+/* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
+int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
+
+/* The sort on its own (parity / benchmark hook): sorts n pairs on key bits [0, end_bit).  The unsorted input
+ * must be in (keys_tmp, vals_tmp) when lgm_sort_input_is_tmp(end_bit) != 0, else in (keys_out, vals_out);
+ * the result is always in (keys_out, vals_out).                                                             */
+int lgm_sort_input_is_tmp(int32_t end_bit);
+int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes);
+int lgm_sort_pairs(void* stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                   int64_t n, int32_t end_bit, void* workspace, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGM_B200_H */

@@ -1,0 +1,67 @@
+"""Builds lgm_b200/liblgm_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m lgm_b200.build            # incremental
+    python -m lgm_b200.build --force --verbose
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "liblgm_b200.so")
+SOURCES = ["preprocess.cu", "binning.cu", "radix_sort.cu", "composite.cu", "api.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("CUDA_HOME", "") + "/bin/nvcc", "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.exists(c) or c == "nvcc"):
+            return c
+    return "nvcc"
+
+
+def _deps():
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(HERE, "..", "include", "lgm_b200.h"))
+    return hdrs
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_mtime = max(os.path.getmtime(h) for h in _deps())
+    logs = {}
+
+    def compile_one(src):
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        if not force and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_mtime):
+            return o, False
+        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        logs[src] = r.stderr
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return o, True
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in res]
+    if force or any(ch for _, ch in res) or not os.path.exists(OUT):
+        r = subprocess.run([nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        for k, v in logs.items():
+            print(f"==== {k}\n{v}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,288 @@
+// api.cu — the C-ABI of include/lgm_b200.h: argument validation, workspace carving, launch sequencing.
+// No device memory is allocated here and nothing synchronises; no exception leaves these functions.
+#include "../../include/lgm_b200.h"
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* what)
+{
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+#define LGM_CUDA(call, where)                               \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return fail_cuda(e__, where); \
+    } while (0)
+#define LGM_NOTNULL(p)                                                         \
+    do {                                                                       \
+        if ((p) == nullptr) return fail(LGM_ERR_NULL_POINTER, "null pointer: " #p); \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int make_params(const lgm_render_params* in, lgm::RenderParams& p)
+{
+    if (!in) return fail(LGM_ERR_NULL_POINTER, "null pointer: prm");
+    if (in->n_scenes < 0 || in->n_gaussians < 0 || in->n_views < 0 || in->image_height <= 0 || in->image_width <= 0)
+        return fail(LGM_ERR_BAD_SHAPE, "negative size or empty image in lgm_render_params");
+    if (!(in->tanfovx > 0.f) || !(in->tanfovy > 0.f)) return fail(LGM_ERR_BAD_VALUE, "tanfovx / tanfovy must be > 0");
+    if ((int64_t)in->n_views * in->n_gaussians >= (int64_t)1 << 32)
+        return fail(LGM_ERR_BAD_SHAPE, "n_views * n_gaussians must be < 2^32 per call: split the views into chunks");
+    p.n_scenes = in->n_scenes;
+    p.P = in->n_gaussians;
+    p.n_views = in->n_views;
+    p.H = in->image_height;
+    p.W = in->image_width;
+    p.gx = (p.W + 15) / 16;
+    p.gy = (p.H + 15) / 16;
+    p.n_tiles = p.gx * p.gy;
+    if ((int64_t)p.n_views * p.n_tiles >= (int64_t)1 << 31)
+        return fail(LGM_ERR_BAD_SHAPE, "n_views * tiles must be < 2^31 per call: split the views into chunks");
+    p.tanx = in->tanfovx;
+    p.tany = in->tanfovy;
+    p.fx = (float)p.W / (2.0f * p.tanx);  // A.0 focal lengths
+    p.fy = (float)p.H / (2.0f * p.tany);
+    p.mod = in->scale_modifier;
+    return LGM_OK;
+}
+
+int bits_for(uint64_t n_minus_1)
+{
+    int b = 0;
+    while (n_minus_1) { b++; n_minus_1 >>= 1; }
+    return b;
+}
+// key bits that carry information: 32 depth bits + bits of the largest global tile id
+int key_end_bit(const lgm::RenderParams& p)
+{
+    const uint64_t gtiles = (uint64_t)p.n_views * (uint64_t)p.n_tiles;
+    return 32 + (gtiles > 1 ? bits_for(gtiles - 1) : 1);
+}
+
+struct BinWorkspace {
+    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, total;
+};
+BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
+{
+    BinWorkspace w;
+    size_t off = 0;
+    w.keys_tmp = off; off = align_up(off + (size_t)L * 8, 256);
+    w.vals_tmp = off; off = align_up(off + (size_t)L * 4, 256);
+    w.sort_scratch = off;
+    w.sort_scratch_bytes = lgm::sort_scratch_bytes(L, key_end_bit(p));
+    off = align_up(off + w.sort_scratch_bytes, 256);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgm_abi_version(void) { return 1; }
+const char* lgm_last_error_string(void) { return g_err; }
+
+int lgm_tiles_per_view(int32_t H, int32_t W) { return ((W + 15) / 16) * ((H + 15) / 16); }
+int64_t lgm_num_block_sums(int32_t P, int32_t n_views) { return (int64_t)n_views * ((P + lgm::kBlock - 1) / lgm::kBlock); }
+
+int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    LGM_NOTNULL(bytes);
+    if (n_instances < 0) return fail(LGM_ERR_BAD_SHAPE, "n_instances < 0");
+    if (n_instances >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "n_instances >= 2^30: split the views into chunks");
+    *bytes = bin_layout(p, (uint32_t)n_instances).total;
+    return LGM_OK;
+}
+
+int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                     const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                     float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                     uint64_t* total_instances)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    LGM_NOTNULL(total_instances);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.P == 0 || p.n_views == 0) {
+        LGM_CUDA(cudaMemsetAsync(total_instances, 0, sizeof(uint64_t), s), "forward_geom: memset total");
+        return LGM_OK;
+    }
+    LGM_NOTNULL(gaussians); LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(view_scene);
+    LGM_NOTNULL(depth); LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity);
+    LGM_NOTNULL(block_sums); LGM_NOTNULL(block_offsets);
+    LGM_CUDA(lgm::launch_preprocess_fwd(s, p, gaussians, view_mats, proj_mats, view_scene, depth, radii,
+                                        reinterpret_cast<float2*>(xy), reinterpret_cast<float4*>(conic_opacity),
+                                        tiles_touched, block_sums),
+             "forward_geom: preprocess");
+    const int64_t nsum = lgm_num_block_sums(p.P, p.n_views);
+    LGM_CUDA(lgm::launch_scan_block_sums(s, block_sums, (uint32_t)nsum, block_offsets,
+                                         reinterpret_cast<unsigned long long*>(total_instances)),
+             "forward_geom: scan");
+    return LGM_OK;
+}
+
+int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
+                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
+                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_instances < 0) return fail(LGM_ERR_BAD_SHAPE, "n_instances < 0");
+    if (n_instances >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "n_instances >= 2^30: split the views into chunks");
+    const size_t n_ranges = (size_t)p.n_views * p.n_tiles;
+    if (n_ranges) {
+        LGM_NOTNULL(ranges);
+        LGM_CUDA(cudaMemsetAsync(ranges, 0, n_ranges * sizeof(uint2), s), "forward_bin: memset ranges");
+    }
+    if (n_instances == 0 || p.P == 0 || p.n_views == 0) return LGM_OK;
+    LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(depth); LGM_NOTNULL(block_offsets);
+    LGM_NOTNULL(keys_sorted); LGM_NOTNULL(vals_sorted); LGM_NOTNULL(workspace);
+    const uint32_t L = (uint32_t)n_instances;
+    const BinWorkspace w = bin_layout(p, L);
+    if (workspace_bytes < w.total) return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "forward_bin: workspace too small (see lgm_bin_workspace_bytes)");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    uint64_t* keys_tmp = reinterpret_cast<uint64_t*>(ws + w.keys_tmp);
+    uint32_t* vals_tmp = reinterpret_cast<uint32_t*>(ws + w.vals_tmp);
+    const int end_bit = key_end_bit(p);
+    const bool in_tmp = lgm::sort_input_is_tmp(end_bit);
+    LGM_CUDA(lgm::launch_emit(s, p, radii, reinterpret_cast<const float2*>(xy), depth, block_offsets,
+                              in_tmp ? keys_tmp : keys_sorted, in_tmp ? vals_tmp : vals_sorted),
+             "forward_bin: emit");
+    LGM_CUDA(lgm::launch_onesweep_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, L, end_bit, ws + w.sort_scratch,
+                                       w.sort_scratch_bytes),
+             "forward_bin: sort");
+    LGM_CUDA(lgm::launch_tile_ranges(s, keys_sorted, L, reinterpret_cast<uint2*>(ranges)), "forward_bin: ranges");
+    return LGM_OK;
+}
+
+int lgm_forward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
+                          const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
+                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, float* image,
+                          float* alpha, float* depth_img, uint32_t* n_contrib)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    if (p.n_views == 0) return LGM_OK;
+    LGM_NOTNULL(view_scene); LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(image); LGM_NOTNULL(alpha); LGM_NOTNULL(depth_img);
+    LGM_NOTNULL(n_contrib);
+    if (p.P > 0) { LGM_NOTNULL(gaussians); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth); }
+    LGM_CUDA(lgm::launch_composite_fwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),
+                                       reinterpret_cast<const float4*>(conic_opacity), depth, vals_sorted,
+                                       reinterpret_cast<const uint2*>(ranges), bg, image, alpha, depth_img, n_contrib),
+             "forward_composite");
+    return LGM_OK;
+}
+
+int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
+                           const int32_t* view_scene, const int32_t* radii, const float* xy,
+                           const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
+                           int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
+                           void* workspace, size_t workspace_bytes, const float* bg, float* image, float* alpha,
+                           float* depth_img, uint32_t* n_contrib)
+{
+    if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, keys_sorted, vals_sorted, ranges,
+                                 workspace, workspace_bytes))
+        return rc;
+    return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg, image,
+                                 alpha, depth_img, n_contrib);
+}
+
+int lgm_backward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
+                           const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
+                           const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, const float* alpha,
+                           const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha,
+                           const float* dL_ddepth, float* grad_rows)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    if (p.n_views == 0 || p.P == 0) return LGM_OK;
+    LGM_NOTNULL(gaussians); LGM_NOTNULL(view_scene); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth);
+    LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(alpha); LGM_NOTNULL(n_contrib); LGM_NOTNULL(dL_dimage); LGM_NOTNULL(dL_dalpha);
+    LGM_NOTNULL(dL_ddepth); LGM_NOTNULL(grad_rows);
+    LGM_CUDA(lgm::launch_composite_bwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),
+                                       reinterpret_cast<const float4*>(conic_opacity), depth, vals_sorted,
+                                       reinterpret_cast<const uint2*>(ranges), bg, alpha, n_contrib, dL_dimage, dL_dalpha,
+                                       dL_ddepth, grad_rows),
+             "backward_composite");
+    return LGM_OK;
+}
+
+int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                      const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
+                      const float* grad_rows, float* dL_dgaussians, int32_t accumulate)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    if (p.n_scenes == 0 || p.P == 0) return LGM_OK;
+    LGM_NOTNULL(gaussians); LGM_NOTNULL(scene_view_offsets); LGM_NOTNULL(dL_dgaussians);
+    if (p.n_views > 0) { LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(radii); LGM_NOTNULL(grad_rows); }
+    LGM_CUDA(lgm::launch_preprocess_bwd((cudaStream_t)stream, p, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
+                                        grad_rows, dL_dgaussians, accumulate),
+             "backward_geom");
+    return LGM_OK;
+}
+
+int lgm_backward(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                 const float* proj_mats, const int32_t* view_scene, const int32_t* scene_view_offsets,
+                 const int32_t* radii, const float* xy, const float* conic_opacity, const float* depth,
+                 const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, const float* alpha,
+                 const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth,
+                 float* grad_rows, float* dL_dgaussians, int32_t accumulate)
+{
+    if (int rc = lgm_backward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges,
+                                        bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth, grad_rows))
+        return rc;
+    return lgm_backward_geom(stream, prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii, grad_rows,
+                             dL_dgaussians, accumulate);
+}
+
+int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible)
+{
+    if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");
+    if (n_points == 0) return LGM_OK;
+    LGM_NOTNULL(means); LGM_NOTNULL(view_mat); LGM_NOTNULL(visible);
+    LGM_CUDA(lgm::launch_mark_visible((cudaStream_t)stream, n_points, means, view_mat, visible), "mark_visible");
+    return LGM_OK;
+}
+
+int lgm_sort_input_is_tmp(int32_t end_bit) { return lgm::sort_input_is_tmp(end_bit) ? 1 : 0; }
+
+int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes)
+{
+    LGM_NOTNULL(bytes);
+    if (n < 0 || n >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "sort: n must be in [0, 2^30)");
+    if (end_bit < 1 || end_bit > 64) return fail(LGM_ERR_BAD_VALUE, "sort: end_bit must be in [1, 64]");
+    *bytes = lgm::sort_scratch_bytes((uint32_t)n, end_bit);
+    return LGM_OK;
+}
+
+int lgm_sort_pairs(void* stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                   int64_t n, int32_t end_bit, void* workspace, size_t workspace_bytes)
+{
+    if (n < 0 || n >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "sort: n must be in [0, 2^30)");
+    if (end_bit < 1 || end_bit > 64) return fail(LGM_ERR_BAD_VALUE, "sort: end_bit must be in [1, 64]");
+    if (n == 0) return LGM_OK;
+    LGM_NOTNULL(keys_out); LGM_NOTNULL(vals_out); LGM_NOTNULL(keys_tmp); LGM_NOTNULL(vals_tmp); LGM_NOTNULL(workspace);
+    if (workspace_bytes < lgm::sort_scratch_bytes((uint32_t)n, end_bit))
+        return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "sort: workspace too small (see lgm_sort_workspace_bytes)");
+    LGM_CUDA(lgm::launch_onesweep_sort((cudaStream_t)stream, keys_out, vals_out, keys_tmp, vals_tmp, (uint32_t)n, end_bit,
+                                       workspace, workspace_bytes),
+             "sort_pairs");
+    return LGM_OK;
+}
+
+}  // extern "C"

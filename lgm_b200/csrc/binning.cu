@@ -1,0 +1,131 @@
+// binning.cu — instance offsets (scan), K2 emit of (view|tile|depth) keys, K4 per-tile range identification.
+// Replaces cub::DeviceScan::InclusiveSum + the blocking 4-byte D2H, duplicateWithKeys and identifyTileRanges of the
+// external rasterizer, for all views of a step at once.
+//
+// Key layout (64 bit):  [63:32] global tile id = view * n_tiles + tile_y * grid_x + tile_x,  [31:0] float bits of the
+// view-space depth.  Per view, key - (view * n_tiles << 32) is exactly the upstream key (tile << 32 | depth bits).
+// Value (32 bit): view * P + Gaussian index (the row of the per-(view,Gaussian) geometry arrays).
+#include "common.cuh"
+#include "splat_math.cuh"
+
+namespace lgm {
+
+// Exclusive scan of the per-(view, Gaussian-block) tile counts.  n is small (n_views * ceil(P/256), e.g. 80 k at
+// 208 views x 98,304 Gaussians), so one 1024-thread block scans it: each thread sums a contiguous chunk, the 1024
+// partials are scanned with shuffles, and a second sweep writes the offsets.  The grand total (= number of
+// instances L) is left on the device and read back ONCE per step by the host wrapper.
+__global__ void __launch_bounds__(1024)
+scan_block_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                       unsigned long long* __restrict__ total)
+{
+    __shared__ unsigned long long s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t chunk = (n + 1023u) / 1024u;
+    const uint32_t b = min(n, t * chunk), e = min(n, b + chunk);
+    unsigned long long s = 0;
+    for (uint32_t i = b; i < e; i++) s += in[i];
+    unsigned long long incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        s_warp[lane] = wi - w;  // exclusive warp base
+        if (lane == 31) total[0] = wi;
+    }
+    __syncthreads();
+    unsigned long long run = s_warp[warp] + incl - s;
+    for (uint32_t i = b; i < e; i++) {
+        out[i] = (uint32_t)run;  // offsets fit 32 bit: the host wrapper bounds L per call below 2^31
+        run += in[i];
+    }
+}
+
+cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n, uint32_t* block_offsets,
+                                   unsigned long long* total)
+{
+    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, n, block_offsets, total);
+    return cudaGetLastError();
+}
+
+// K2.  One thread per (view, Gaussian); its first output slot = block offset + in-block exclusive scan of the tile
+// counts (recomputed from xy / radius with the same pinned tile_rect as preprocess), then rows of its rect in
+// row-major order — the emit order the stable sort's tie-break relies on (ascending Gaussian index per tile).
+__global__ void __launch_bounds__(kBlock)
+emit_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+            const float* __restrict__ depth, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ keys,
+            uint32_t* __restrict__ vals)
+{
+    __shared__ uint32_t s_warp[8];
+    const int view = blockIdx.y;
+    const int idx = blockIdx.x * kBlock + threadIdx.x;
+    const size_t gi = (size_t)view * prm.P + idx;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t area = 0;
+    if (idx < prm.P) {
+        const int r = radii[gi];
+        if (r > 0) {
+            const float2 p = xy[gi];
+            tile_rect(p.x, p.y, r, prm.gx, prm.gy, x0, y0, x1, y1);
+            area = (uint32_t)((x1 - x0) * (y1 - y0));
+        }
+    }
+    const uint32_t excl = block_excl_scan_256(area, s_warp, nullptr);
+    if (area == 0) return;
+    size_t off = (size_t)block_offsets[(size_t)view * gridDim.x + blockIdx.x] + excl;
+    const uint32_t dbits = __float_as_uint(depth[gi]);
+    const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    const uint32_t val = (uint32_t)gi;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            keys[off] = ((uint64_t)(tile_base + (uint32_t)(y * prm.gx + x)) << 32) | dbits;
+            vals[off] = val;
+            off++;
+        }
+}
+
+cudaError_t launch_emit(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                        const float* depth, const uint32_t* block_offsets, uint64_t* keys, uint32_t* vals)
+{
+    if (prm.P == 0 || prm.n_views == 0) return cudaSuccess;
+    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
+    emit_kernel<<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, block_offsets, keys, vals);
+    return cudaGetLastError();
+}
+
+// K4.  ranges[global tile] = [start, end) into the sorted instance list; ranges must be zero-filled first
+// (empty tiles stay (0,0)), as upstream's cudaMemset + identifyTileRanges.
+__global__ void __launch_bounds__(kBlock)
+tile_ranges_kernel(const uint64_t* __restrict__ keys, uint32_t L, uint2* __restrict__ ranges)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= L) return;
+    const uint32_t cur = (uint32_t)(keys[i] >> 32);
+    if (i == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (cur != prev) {
+            ranges[prev].y = i;
+            ranges[cur].x = i;
+        }
+    }
+    if (i == L - 1) ranges[cur].y = L;
+}
+
+cudaError_t launch_tile_ranges(cudaStream_t stream, const uint64_t* keys, uint32_t L, uint2* ranges)
+{
+    if (L == 0) return cudaSuccess;
+    tile_ranges_kernel<<<(L + kBlock - 1) / kBlock, kBlock, 0, stream>>>(keys, L, ranges);
+    return cudaGetLastError();
+}
+
+}  // namespace lgm

@@ -1,0 +1,90 @@
+// common.cuh — shared declarations of the sm_100a splat-render library (internal; the public C-ABI is include/lgm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lgm {
+
+struct RenderParams {
+    int n_scenes;   // B
+    int P;          // Gaussians per scene
+    int n_views;    // views rendered by this call (all scenes)
+    int H, W;
+    int gx, gy, n_tiles;  // tile grid per view
+    float tanx, tany, fx, fy, mod;
+};
+
+// Per-(view, Gaussian) gradient row written by the backward compositing kernel and consumed by the preprocess
+// backward: [0:2] dL/dmean2D (NDC-scaled), [2:5] dL/dconic (xx, xy, yy), [5] dL/dopacity, [6:9] dL/dcolour,
+// [9] dL/ddepth, [10:12] padding (keeps rows 16-byte aligned for vector atomics / loads).
+constexpr int kGradRow = 12;
+
+constexpr int kBlock = 256;  // threads per block of the per-Gaussian kernels and of a 16x16 tile
+
+// ---- launchers (each enqueues on `stream`, returns the launch status, never synchronises) ----
+cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const float* view_mats, const float* proj_mats, const int32_t* view_scene,
+                                  float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
+                                  uint32_t* tiles_touched /*nullable*/, uint32_t* block_sums);
+cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, const float* view_mat, uint8_t* visible);
+cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
+                                  const int32_t* radii, const float* grad_rows, float* dL_dgaussians, int accumulate);
+
+cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n, uint32_t* block_offsets,
+                                   unsigned long long* total);
+cudaError_t launch_emit(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                        const float* depth, const uint32_t* block_offsets, uint64_t* keys, uint32_t* vals);
+cudaError_t launch_tile_ranges(cudaStream_t stream, const uint64_t* keys, uint32_t L, uint2* ranges);
+
+// onesweep radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  The sorted result lands in
+// keys_out / vals_out; keys_tmp / vals_tmp are the alternate buffers; `in` says where the unsorted data is
+// (sort_input_is_tmp(end_bit) tells the caller which of the two to fill).
+int sort_num_passes(int end_bit);
+bool sort_input_is_tmp(int end_bit);
+size_t sort_scratch_bytes(uint32_t n, int end_bit);
+cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp,
+                                 uint32_t* vals_tmp, uint32_t n, int end_bit, void* scratch, size_t scratch_bytes);
+
+cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                 const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                 const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                 float* image, float* alpha, float* depth_img, uint32_t* n_contrib);
+cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                 const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                 const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                 const float* alpha, const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha,
+                                 const float* dL_ddepth, float* grad_rows);
+
+// ---- small device helpers ----
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// exclusive scan of one value per thread over a 256-thread block; `total` (optional) receives the block sum.
+// s_warp must hold 8 uint32.  Contains two __syncthreads.
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        tot += c;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return wbase + incl - v;
+}
+
+}  // namespace lgm

@@ -1,0 +1,318 @@
+// composite.cu — K5 front-to-back alpha / depth / colour compositing per 16x16 tile, and K6 its backward
+// (back-to-front walk, warp-reduced gradients, shared-memory accumulation per staged Gaussian, vector atomics).
+// Replaces renderCUDA fwd/bwd of the external rasterizer; every view of the step
+// is rendered by ONE launch (grid = views x tiles).
+//
+// Per-pair arithmetic that decides skip / stop (power, alpha, test_T) and the forward accumulators are pinned
+// (splat_math.cuh), so forward and backward take identical decisions and the forward matches the oracle up to expf.
+// Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / atomics in the backward).
+#include "common.cuh"
+#include "splat_math.cuh"
+
+namespace lgm {
+namespace {
+
+// A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store).
+__device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
+    py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+}
+
+__global__ void __launch_bounds__(kBlock, 4)
+composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
+                     const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                     const float* __restrict__ depth, const uint32_t* __restrict__ vals,
+                     const uint2* __restrict__ ranges, const float* __restrict__ bg, float* __restrict__ image,
+                     float* __restrict__ alpha_img, float* __restrict__ depth_img, uint32_t* __restrict__ n_contrib)
+{
+    __shared__ float2 s_xy[kBlock];
+    __shared__ float4 s_co[kBlock];
+    __shared__ float4 s_rgbd[kBlock];
+
+    const uint32_t gt = blockIdx.x;
+    const int view = gt / prm.n_tiles;
+    const int tile = gt - view * prm.n_tiles;
+    const int tile_y = tile / prm.gx, tile_x = tile - tile_y * prm.gx;
+    const int scene = view_scene[view];
+    int px, py;
+    pixel_of_thread(tile_x, tile_y, px, py);
+    const bool inside = px < prm.W && py < prm.H;
+    const float pfx = (float)px, pfy = (float)py;
+
+    const uint2 range = ranges[gt];
+    const int todo = (int)(range.y - range.x);
+    const int rounds = (todo + kBlock - 1) / kBlock;
+    const uint32_t view_base = (uint32_t)view * (uint32_t)prm.P;
+    const float* scene_g = gaussians + (size_t)scene * prm.P * 14;
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Wt = 0.f, D = 0.f;
+    uint32_t contributor = 0, last = 0;
+    bool done = !inside;
+
+    for (int r = 0; r < rounds; r++) {
+        if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffers
+        const int k = r * kBlock + threadIdx.x;
+        if (k < todo) {
+            const uint32_t g = vals[range.x + k];
+            s_xy[threadIdx.x] = xy[g];
+            s_co[threadIdx.x] = conic_opacity[g];
+            const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
+            s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
+        }
+        __syncthreads();
+        const int nb = min(kBlock, todo - r * kBlock);
+        for (int j = 0; !done && j < nb; j++) {
+            contributor++;
+            const float2 p = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
+            const float power = pair_power(co.x, co.y, co.z, dx, dy);
+            if (power > 0.0f) continue;
+            const float a = fminf(kAlphaMax, LGM_MUL(co.w, expf(power)));
+            if (a < kAlphaMin) continue;
+            const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
+            if (test_T < kTEps) {
+                done = true;
+                continue;
+            }
+            const float4 cd = s_rgbd[j];
+            C0 = LGM_FMA(LGM_MUL(cd.x, a), T, C0);
+            C1 = LGM_FMA(LGM_MUL(cd.y, a), T, C1);
+            C2 = LGM_FMA(LGM_MUL(cd.z, a), T, C2);
+            Wt = LGM_FMA(a, T, Wt);
+            D = LGM_FMA(LGM_MUL(cd.w, a), T, D);
+            T = test_T;
+            last = contributor;
+        }
+    }
+    if (inside) {
+        const size_t hw = (size_t)prm.H * prm.W;
+        const size_t pix = (size_t)py * prm.W + px;
+        n_contrib[(size_t)view * hw + pix] = last;
+        float* img = image + (size_t)view * 3 * hw + pix;
+        img[0] = LGM_FMA(T, __ldg(bg), C0);
+        img[hw] = LGM_FMA(T, __ldg(bg + 1), C1);
+        img[2 * hw] = LGM_FMA(T, __ldg(bg + 2), C2);
+        alpha_img[(size_t)view * hw + pix] = Wt;
+        depth_img[(size_t)view * hw + pix] = D;
+    }
+}
+
+// Sum 10 per-lane values over the warp with 14 shuffles (recursive halving: at each of the first three steps a lane
+// keeps half of its values and hands the other half to its partner).  On return lane L holds
+//   A  = sum over lanes of a[4*b4 + 2*b3 + b2]   (b4,b3,b2 = bits 4,3,2 of L; all four lanes of a quad agree)
+//   Bv = sum over lanes of b[b4]
+__device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float (&b)[2], int lane, float& A, float& Bv)
+{
+    const unsigned full = 0xffffffffu;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float k0 = h16 ? a[4] : a[0], k1 = h16 ? a[5] : a[1], k2 = h16 ? a[6] : a[2], k3 = h16 ? a[7] : a[3];
+    const float s0 = h16 ? a[0] : a[4], s1 = h16 ? a[1] : a[5], s2 = h16 ? a[2] : a[6], s3 = h16 ? a[3] : a[7];
+    float bk = h16 ? b[1] : b[0];
+    const float bs = h16 ? b[0] : b[1];
+    k0 += __shfl_xor_sync(full, s0, 16);
+    k1 += __shfl_xor_sync(full, s1, 16);
+    k2 += __shfl_xor_sync(full, s2, 16);
+    k3 += __shfl_xor_sync(full, s3, 16);
+    bk += __shfl_xor_sync(full, bs, 16);
+    float m0 = h8 ? k2 : k0, m1 = h8 ? k3 : k1;
+    const float t0 = h8 ? k0 : k2, t1 = h8 ? k1 : k3;
+    m0 += __shfl_xor_sync(full, t0, 8);
+    m1 += __shfl_xor_sync(full, t1, 8);
+    bk += __shfl_xor_sync(full, bk, 8);
+    A = h4 ? m1 : m0;
+    const float u = h4 ? m0 : m1;
+    A += __shfl_xor_sync(full, u, 4);
+    bk += __shfl_xor_sync(full, bk, 4);
+    A += __shfl_xor_sync(full, A, 2);
+    bk += __shfl_xor_sync(full, bk, 2);
+    A += __shfl_xor_sync(full, A, 1);
+    bk += __shfl_xor_sync(full, bk, 1);
+    Bv = bk;
+}
+
+__global__ void __launch_bounds__(kBlock)
+composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
+                     const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                     const float* __restrict__ depth, const uint32_t* __restrict__ vals,
+                     const uint2* __restrict__ ranges, const float* __restrict__ bg,
+                     const float* __restrict__ alpha_img, const uint32_t* __restrict__ n_contrib,
+                     const float* __restrict__ dL_dimage,
+                     const float* __restrict__ dL_dalpha_img, const float* __restrict__ dL_ddepth_img,
+                     float* __restrict__ grad_rows)
+{
+    __shared__ float2 s_xy[kBlock];
+    __shared__ float4 s_co[kBlock];
+    __shared__ float4 s_rgbd[kBlock];
+    __shared__ uint32_t s_g[kBlock];
+    __shared__ __align__(16) float s_acc[kBlock * kGradRow];
+    __shared__ uint32_t s_max[kBlock / 32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gt = blockIdx.x;
+    const int view = gt / prm.n_tiles;
+    const int tile = gt - view * prm.n_tiles;
+    const int tile_y = tile / prm.gx, tile_x = tile - tile_y * prm.gx;
+    const int scene = view_scene[view];
+    int px, py;
+    pixel_of_thread(tile_x, tile_y, px, py);
+    const bool inside = px < prm.W && py < prm.H;
+    const float pfx = (float)px, pfy = (float)py;
+    const size_t hw = (size_t)prm.H * prm.W;
+    const size_t pix = (size_t)py * prm.W + px;
+
+    const uint2 range = ranges[gt];
+    const uint32_t view_base = (uint32_t)view * (uint32_t)prm.P;
+    const float* scene_g = gaussians + (size_t)scene * prm.P * 14;
+
+    uint32_t last_contributor = 0;
+    float T_final = 0.f, dC0 = 0.f, dC1 = 0.f, dC2 = 0.f, dD = 0.f, dA = 0.f;
+    if (inside) {
+        last_contributor = n_contrib[(size_t)view * hw + pix];
+        T_final = 1.0f - alpha_img[(size_t)view * hw + pix];
+        const float* dimg = dL_dimage + (size_t)view * 3 * hw + pix;
+        dC0 = dimg[0];
+        dC1 = dimg[hw];
+        dC2 = dimg[2 * hw];
+        dD = dL_ddepth_img[(size_t)view * hw + pix];
+        dA = dL_dalpha_img[(size_t)view * hw + pix];
+    }
+    const float bg_dot = __ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2;
+
+    // Only list positions below the largest n_contrib of the tile can contribute.
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) s_max[warp] = wmax;
+#pragma unroll
+    for (int k = 0; k < kGradRow; k++) s_acc[threadIdx.x * kGradRow + k] = 0.f;
+    __syncthreads();
+    uint32_t bmax = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) bmax = max(bmax, s_max[w]);
+    const int todo = (int)min(range.y - range.x, bmax);
+    const int rounds = (todo + kBlock - 1) / kBlock;
+
+    float T = T_final;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
+    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_d = 0.f;
+    const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
+
+    for (int r = 0; r < rounds; r++) {
+        __syncthreads();  // staging buffers and s_acc rows are free again
+        const int k = r * kBlock + threadIdx.x;
+        if (k < todo) {
+            const uint32_t g = vals[range.x + (uint32_t)(todo - 1 - k)];
+            s_g[threadIdx.x] = g;
+            s_xy[threadIdx.x] = xy[g];
+            s_co[threadIdx.x] = conic_opacity[g];
+            const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
+            s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
+        }
+        __syncthreads();
+        const int nb = min(kBlock, todo - r * kBlock);
+        for (int j = 0; j < nb; j++) {
+            const uint32_t pos = (uint32_t)(todo - 1 - (r * kBlock + j));  // 0-based list position
+            if (pos >= wmax) continue;                                    // warp-uniform
+            bool valid = pos < last_contributor;
+            const float2 p = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
+            const float power = pair_power(co.x, co.y, co.z, dx, dy);
+            valid = valid && !(power > 0.0f);
+            const float G = expf(power);
+            const float a = fminf(kAlphaMax, LGM_MUL(co.w, G));
+            valid = valid && !(a < kAlphaMin);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vb[2] = {0.f, 0.f};
+            if (valid) {
+                const float4 cd = s_rgbd[j];
+                T = T / (1.f - a);
+                const float w = a * T;
+                float dL_da = 0.f;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                lc0 = cd.x; lc1 = cd.y; lc2 = cd.z;
+                dL_da += (cd.x - acc0) * dC0;
+                dL_da += (cd.y - acc1) * dC1;
+                dL_da += (cd.z - acc2) * dC2;
+                accD = last_alpha * last_d + (1.f - last_alpha) * accD;
+                last_d = cd.w;
+                dL_da += (cd.w - accD) * dD;
+                accA = last_alpha + (1.f - last_alpha) * accA;
+                dL_da += (1.f - accA) * dA;
+                dL_da *= T;
+                last_alpha = a;
+                dL_da += (-T_final / (1.f - a)) * bg_dot;
+                const float dL_dG = co.w * dL_da;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                const float dG_ddely = -gdy * co.z - gdx * co.y;
+                va[0] = dL_dG * dG_ddelx * ddelx_dx;
+                va[1] = dL_dG * dG_ddely * ddely_dy;
+                va[2] = -0.5f * gdx * dx * dL_dG;
+                va[3] = -0.5f * gdx * dy * dL_dG;
+                va[4] = -0.5f * gdy * dy * dL_dG;
+                va[5] = G * dL_da;
+                va[6] = w * dC0;
+                va[7] = w * dC1;
+                vb[0] = w * dC2;
+                vb[1] = w * dD;
+            }
+            float A, Bv;
+            warp_reduce_10(va, vb, lane, A, Bv);
+            float* row = s_acc + j * kGradRow;
+            if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), A);
+            if ((lane & 15) == 1) atomicAdd(row + 8 + (lane >> 4), Bv);
+        }
+        __syncthreads();
+        // flush: one thread per staged Gaussian, three 16-byte vector reductions into its gradient row
+        if ((int)threadIdx.x < nb) {
+            float4* row = reinterpret_cast<float4*>(s_acc + threadIdx.x * kGradRow);
+            const float4 q0 = row[0], q1 = row[1], q2 = row[2];
+            const bool nz = (q0.x != 0.f) | (q0.y != 0.f) | (q0.z != 0.f) | (q0.w != 0.f) | (q1.x != 0.f) | (q1.y != 0.f) |
+                            (q1.z != 0.f) | (q1.w != 0.f) | (q2.x != 0.f) | (q2.y != 0.f);
+            if (nz) {
+                float4* dst = reinterpret_cast<float4*>(grad_rows + (size_t)s_g[threadIdx.x] * kGradRow);
+                atomicAdd(dst, q0);
+                atomicAdd(dst + 1, q1);
+                atomicAdd(dst + 2, q2);
+                row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                row[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                 const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                 const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                 float* image, float* alpha, float* depth_img, uint32_t* n_contrib)
+{
+    const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
+    if (blocks == 0) return cudaSuccess;
+    composite_fwd_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
+                                                                  ranges, bg, image, alpha, depth_img, n_contrib);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                 const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                 const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                 const float* alpha, const uint32_t* n_contrib, const float* dL_dimage,
+                                 const float* dL_dalpha, const float* dL_ddepth, float* grad_rows)
+{
+    const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
+    if (blocks == 0) return cudaSuccess;
+    composite_bwd_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
+                                                                  ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth,
+                                                                  grad_rows);
+    return cudaGetLastError();
+}
+
+}  // namespace lgm

@@ -1,0 +1,178 @@
+// preprocess.cu — K1 (3D->2D projection, covariance, EWA conic, radius, tile rect), markVisible, and K7 (preprocess
+// backward chain rule to means / scales / rotations).  Replaces preprocessCUDA fwd/bwd + computeCov2DCUDA of the
+// external rasterizer, batched over all views of a step in one launch.
+//
+// HBM roofline: K1 writes 36 B per (view, Gaussian) (depth 4, radius 4, xy 8, conic+opacity 16, tile-count
+// block sums amortised) and reads the 56-B AoS Gaussian row once per view through L2 (rows of a scene are shared by
+// all its views); K7 reads 4 + 48 B per (view, Gaussian) and writes 56 B per Gaussian.
+#include "common.cuh"
+#include "splat_math.cuh"
+
+namespace lgm {
+
+// Stage n (<=256) consecutive 14-float Gaussian rows into shared memory with 16-byte vector loads when aligned.
+__device__ __forceinline__ void stage_rows(float* s_g, const float* __restrict__ src, int n)
+{
+    const int nfl = n * 14;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const int nv = nfl >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(s_g);
+        for (int i = threadIdx.x; i < nv; i += kBlock) d4[i] = __ldg(s4 + i);
+        for (int i = (nv << 2) + threadIdx.x; i < nfl; i += kBlock) s_g[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < nfl; i += kBlock) s_g[i] = __ldg(src + i);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
+                      const float* __restrict__ proj_mats, const int32_t* __restrict__ view_scene,
+                      float* __restrict__ depth, int32_t* __restrict__ radii, float2* __restrict__ xy,
+                      float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched,
+                      uint32_t* __restrict__ block_sums)
+{
+    __shared__ __align__(16) float s_g[kBlock * 14];
+    __shared__ float s_mv[16], s_mp[16];
+    __shared__ uint32_t s_warp[8];
+    const int view = blockIdx.y;
+    const int scene = view_scene[view];
+    const int base = blockIdx.x * kBlock;
+    const int n = min(kBlock, prm.P - base);
+    stage_rows(s_g, gaussians + ((size_t)scene * prm.P + base) * 14, n);
+    if (threadIdx.x < 16) s_mv[threadIdx.x] = view_mats[view * 16 + threadIdx.x];
+    else if (threadIdx.x < 32) s_mp[threadIdx.x - 16] = proj_mats[view * 16 + threadIdx.x - 16];
+    __syncthreads();
+
+    uint32_t tiles = 0;
+    if ((int)threadIdx.x < n) {
+        const float* g = s_g + threadIdx.x * 14;
+        const Geom o = preprocess_point(g, g + 4, g + 7, prm.mod, s_mv, s_mp, prm.W, prm.H, prm.tanx, prm.tany, prm.fx,
+                                        prm.fy, prm.gx, prm.gy);
+        const size_t gi = (size_t)view * prm.P + base + threadIdx.x;
+        depth[gi] = o.depth;
+        radii[gi] = o.radius;
+        xy[gi] = make_float2(o.px, o.py);
+        conic_opacity[gi] = make_float4(o.cx, o.cy, o.cz, o.radius > 0 ? g[3] : 0.f);
+        if (tiles_touched) tiles_touched[gi] = o.tiles;
+        tiles = o.tiles;
+    }
+    // block sum of tiles_touched -> one partial per (view, Gaussian block); scanned by scan_block_sums_kernel
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t s = tiles;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_warp[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_warp[w];
+        block_sums[(size_t)view * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const float* view_mats, const float* proj_mats, const int32_t* view_scene,
+                                  float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
+                                  uint32_t* tiles_touched, uint32_t* block_sums)
+{
+    if (prm.P == 0 || prm.n_views == 0) return cudaSuccess;
+    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
+    preprocess_fwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, view_scene, depth, radii, xy,
+                                                       conic_opacity, tiles_touched, block_sums);
+    return cudaGetLastError();
+}
+
+// ---- markVisible (upstream checkFrustum; not called by LGM, kept for API completeness) ----
+__global__ void __launch_bounds__(kBlock)
+mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ mv, uint8_t* __restrict__ visible)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= P) return;
+    float m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = __ldg(mv + k);
+    const float z = affine_row(m, 2, means[3 * i], means[3 * i + 1], means[3 * i + 2]);
+    visible[i] = !(z <= kNearCull);
+}
+
+cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, const float* view_mat, uint8_t* visible)
+{
+    if (P == 0) return cudaSuccess;
+    mark_visible_kernel<<<(P + kBlock - 1) / kBlock, kBlock, 0, stream>>>(P, means, view_mat, visible);
+    return cudaGetLastError();
+}
+
+// ---- K7: preprocess backward.  One thread per Gaussian loops over the views of its scene and accumulates in
+// registers, so the sum over views needs no atomics and is deterministic. ----
+__global__ void __launch_bounds__(kBlock)
+preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
+                      const float* __restrict__ proj_mats, const int32_t* __restrict__ scene_view_offsets,
+                      const int32_t* __restrict__ radii, const float* __restrict__ grad_rows,
+                      float* __restrict__ dL_dgaussians, int accumulate)
+{
+    __shared__ __align__(16) float s_g[kBlock * 14];
+    __shared__ float s_m[32];
+    const int scene = blockIdx.y;
+    const int base = blockIdx.x * kBlock;
+    const int n = min(kBlock, prm.P - base);
+    const float* src = gaussians + ((size_t)scene * prm.P + base) * 14;
+    stage_rows(s_g, src, n);
+    __syncthreads();
+    float g[14];
+    float d[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) d[k] = 0.f;
+    const bool active = (int)threadIdx.x < n;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 14; k++) g[k] = s_g[threadIdx.x * 14 + k];
+    }
+    const int v0 = scene_view_offsets[scene], v1 = scene_view_offsets[scene + 1];
+    for (int v = v0; v < v1; v++) {
+        __syncthreads();
+        if (threadIdx.x < 16) s_m[threadIdx.x] = view_mats[v * 16 + threadIdx.x];
+        else if (threadIdx.x < 32) s_m[threadIdx.x] = proj_mats[v * 16 + threadIdx.x - 16];
+        __syncthreads();
+        if (!active) continue;
+        const size_t gi = (size_t)v * prm.P + base + threadIdx.x;
+        if (!(radii[gi] > 0)) continue;
+        const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
+        const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
+        // r0 = (m2d.x, m2d.y, conic.xx, conic.xy)  r1 = (conic.yy, opacity, col.r, col.g)  r2 = (col.b, depth, -, -)
+        preprocess_point_bwd(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, r0.x, r0.y, r0.z,
+                             r0.w, r1.x, r2.y, d, d + 4, d + 7);
+        d[3] += r1.y;
+        d[11] += r1.z;
+        d[12] += r1.w;
+        d[13] += r2.x;
+    }
+    // transpose through shared memory for coalesced stores of the 14-float rows
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 14; k++) s_g[threadIdx.x * 14 + k] = d[k];
+    }
+    __syncthreads();
+    float* dst = dL_dgaussians + ((size_t)scene * prm.P + base) * 14;
+    const int nfl = n * 14;
+    if (accumulate) {
+        for (int i = threadIdx.x; i < nfl; i += kBlock) dst[i] += s_g[i];
+    } else {
+        for (int i = threadIdx.x; i < nfl; i += kBlock) dst[i] = s_g[i];
+    }
+}
+
+cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
+                                  const int32_t* radii, const float* grad_rows, float* dL_dgaussians, int accumulate)
+{
+    if (prm.P == 0 || prm.n_scenes == 0) return cudaSuccess;
+    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_scenes);
+    preprocess_bwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
+                                                       grad_rows, dL_dgaussians, accumulate);
+    return cudaGetLastError();
+}
+
+}  // namespace lgm

@@ -1,0 +1,270 @@
+"""Host-side driver of the CUDA splat-render path: tensor allocation, the single per-step readback of the instance
+count, and the autograd bridge.  PyTorch here is plumbing (device memory, streams, autograd); all arithmetic runs in
+lgm_b200/csrc through the C-ABI of include/lgm_b200.h.  No CPU / PyTorch fallback exists.
+
+Replaces, batched over every view of a step, what `_RasterizeGaussians.forward/backward` and
+`RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA` do per view in the external rasterizer
+(SURVEY.md §3 call stack A, §8a rows a4-a13), as driven from /root/reference/core/gs.py:42-93.
+"""
+import dataclasses
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+MAX_INSTANCES = (1 << 30) - 1       # look-back counters of the sort are 30 bit
+MAX_PAIRS_PER_CALL = 1 << 28        # (view, Gaussian) pairs per launch group: ~22 GB of state at 84 B / pair
+
+# launch accounting for bench.py's "gpu_launches" (kernels this library enqueues; memsets not counted)
+launch_counter = {"kernels": 0}
+
+# Optional per-stage CUDA-event timing (bench.py's stage breakdown; off in normal use).  When enabled, every stage
+# call is bracketed by events on the launching stream; read with stage_times_ms() after a synchronize.
+_stage_events = None
+
+
+def enable_stage_timing(on=True):
+    global _stage_events
+    _stage_events = {} if on else None
+
+
+def _timed(name, fn):
+    if _stage_events is None:
+        return fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = fn()
+    b.record()
+    _stage_events.setdefault(name, []).append((a, b))
+    return r
+
+
+def stage_times_ms(reset=True):
+    """{stage: [ms per call]} for the calls recorded since the last reset (synchronises)."""
+    torch.cuda.synchronize()
+    out = {k: [a.elapsed_time(b) for a, b in v] for k, v in (_stage_events or {}).items()}
+    if reset and _stage_events is not None:
+        _stage_events.clear()
+    return out
+
+
+@dataclasses.dataclass(frozen=True)
+class ViewConfig:
+    """Per-call constants (GaussianRasterizationSettings minus the per-view matrices)."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    scale_modifier: float = 1.0
+    keep_binning: bool = False  # keep sorted keys / tiles_touched (parity tests)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda_f32(t, name, shape_tail=None):
+    if not t.is_cuda:
+        raise _lib.LgmError(f"{name} must be a CUDA tensor (lgm_b200 has no CPU path)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.LgmError(f"{name} must be contiguous float32")
+    if shape_tail is not None and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise _lib.LgmError(f"{name} must have trailing shape {shape_tail}, got {tuple(t.shape)}")
+
+
+class ForwardState:
+    """Everything the backward needs (the analogue of upstream's geomBuffer / binningBuffer / imgBuffer)."""
+    __slots__ = ("cfg", "n_scenes", "P", "n_views", "view_scene", "scene_view_offsets", "depth", "radii", "xy",
+                 "conic_opacity", "vals", "ranges", "n_contrib", "num_rendered", "keys", "tiles_touched")
+
+
+def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg: ViewConfig):
+    """All views in one set of launches.  Returns (image [VW,3,H,W], alpha [VW,1,H,W], depth [VW,1,H,W], state)."""
+    L = _lib.lib()
+    _check_cuda_f32(gaussians, "gaussians", (14,))
+    _check_cuda_f32(view_mats, "view_mats", (16,))
+    _check_cuda_f32(proj_mats, "proj_mats", (16,))
+    _check_cuda_f32(bg, "bg", (3,))
+    dev = gaussians.device
+    B, P = gaussians.shape[0], gaussians.shape[1]
+    VW = view_mats.shape[0]
+    H, W = cfg.image_height, cfg.image_width
+    prm = _lib.make_params(B, P, VW, H, W, cfg.tanfovx, cfg.tanfovy, cfg.scale_modifier)
+    n_tiles = L.lgm_tiles_per_view(H, W)
+    st = ForwardState()
+    st.cfg, st.n_scenes, st.P, st.n_views = cfg, B, P, VW
+    st.view_scene, st.scene_view_offsets = view_scene, scene_view_offsets
+    npair = VW * P
+    st.depth = torch.empty(npair, dtype=torch.float32, device=dev)
+    st.radii = torch.empty(npair, dtype=torch.int32, device=dev)
+    st.xy = torch.empty(npair, 2, dtype=torch.float32, device=dev)
+    st.conic_opacity = torch.empty(npair, 4, dtype=torch.float32, device=dev)
+    st.tiles_touched = torch.empty(npair, dtype=torch.int32, device=dev) if cfg.keep_binning else None
+    nsum = int(L.lgm_num_block_sums(P, VW))
+    block_sums = torch.empty(max(nsum, 1), dtype=torch.int32, device=dev)
+    block_offsets = torch.empty(max(nsum, 1), dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    s = _stream()
+    _timed("geom", lambda: _lib.check(L.lgm_forward_geom(
+        s, prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(view_scene), _lib.ptr(st.depth),
+        _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.tiles_touched), _lib.ptr(block_sums),
+        _lib.ptr(block_offsets), _lib.ptr(total)), "lgm_forward_geom"))
+    launch_counter["kernels"] += 2 if npair else 0
+    # The ONE host<->device synchronisation of the step (upstream: one per view): the instance count sizes the
+    # sort buffers.
+    n_inst = int(total.item())
+    st.num_rendered = n_inst
+    if n_inst > MAX_INSTANCES:
+        raise TooManyInstances(n_inst)
+    ws_bytes = _lib._sz(0)
+    _lib.check(L.lgm_bin_workspace_bytes(prm, n_inst, ws_bytes), "lgm_bin_workspace_bytes")
+    keys = torch.empty(max(n_inst, 1), dtype=torch.int64, device=dev)
+    st.vals = torch.empty(max(n_inst, 1), dtype=torch.int32, device=dev)
+    st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
+    workspace = torch.empty(max(int(ws_bytes.value), 1), dtype=torch.uint8, device=dev)
+    image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
+    alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
+    depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
+    st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
+    # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)
+    _timed("bin", lambda: _lib.check(L.lgm_forward_bin(
+        s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, _lib.ptr(keys),
+        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel()), "lgm_forward_bin"))
+    _timed("composite_fwd", lambda: _lib.check(L.lgm_forward_composite(
+        s, prm, _lib.ptr(gaussians), _lib.ptr(view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.depth),
+        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), _lib.ptr(image), _lib.ptr(alpha), _lib.ptr(depth_img),
+        _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
+    if n_inst > 0:
+        launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)  # emit, histogram, ranges + onesweep passes
+    launch_counter["kernels"] += 1 if VW else 0                     # compositing
+    st.keys = keys if cfg.keep_binning else None
+    return image, alpha, depth_img, st
+
+
+def sort_passes(n_global_tiles):
+    bits = 32 + max(1, (max(n_global_tiles, 1) - 1).bit_length())
+    return (bits + 7) // 8
+
+
+class TooManyInstances(_lib.LgmError):
+    def __init__(self, n):
+        super().__init__(f"{n} Gaussian instances in one call (limit {MAX_INSTANCES}): split the views into chunks")
+        self.n_instances = n
+
+
+def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth):
+    """Returns (dL_dgaussians [B,P,14], grad_rows [VW*P,12])."""
+    L = _lib.lib()
+    dev = gaussians.device
+    cfg = st.cfg
+    prm = _lib.make_params(st.n_scenes, st.P, st.n_views, cfg.image_height, cfg.image_width, cfg.tanfovx, cfg.tanfovy,
+                           cfg.scale_modifier)
+    grad_rows = torch.zeros(max(st.n_views * st.P, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev)
+    d_gauss = torch.empty_like(gaussians)
+    # (lgm_backward is these two calls back to back)
+    _timed("composite_bwd", lambda: _lib.check(L.lgm_backward_composite(
+        _stream(), prm, _lib.ptr(gaussians), _lib.ptr(st.view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity),
+        _lib.ptr(st.depth), _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), _lib.ptr(alpha), _lib.ptr(st.n_contrib),
+        _lib.ptr(d_image), _lib.ptr(d_alpha), _lib.ptr(d_depth), _lib.ptr(grad_rows)), "lgm_backward_composite"))
+    _timed("geom_bwd", lambda: _lib.check(L.lgm_backward_geom(
+        _stream(), prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(st.scene_view_offsets),
+        _lib.ptr(st.radii), _lib.ptr(grad_rows), _lib.ptr(d_gauss), 0), "lgm_backward_geom"))
+    launch_counter["kernels"] += 2 if st.n_views * st.P else 0
+    if st.n_views * st.P == 0:
+        d_gauss.zero_()
+    return d_gauss, grad_rows
+
+
+def _grad_or_zeros(g, like):
+    if g is None:
+        return torch.zeros_like(like)
+    return g.contiguous().float()
+
+
+class _RenderViews(torch.autograd.Function):
+    """image, alpha, depth, radii = f(gaussians [B,P,14]); gradients flow to gaussians only."""
+
+    @staticmethod
+    def forward(ctx, gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg):
+        image, alpha, depth_img, st = forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg,
+                                                    cfg)
+        ctx.st = st
+        ctx.save_for_backward(gaussians, view_mats, proj_mats, bg, alpha)
+        radii = st.radii.view(st.n_views, st.P)
+        ctx.mark_non_differentiable(radii)
+        return image, alpha, depth_img, radii
+
+    @staticmethod
+    def backward(ctx, d_image, d_alpha, d_depth, _d_radii):
+        gaussians, view_mats, proj_mats, bg, alpha = ctx.saved_tensors
+        st = ctx.st
+        d_image = _grad_or_zeros(d_image, alpha.expand(-1, 3, -1, -1))
+        d_alpha = _grad_or_zeros(d_alpha, alpha)
+        d_depth = _grad_or_zeros(d_depth, alpha)
+        d_gauss, _ = backward_views(gaussians, view_mats, proj_mats, bg, st, alpha, d_image, d_alpha, d_depth)
+        return d_gauss, None, None, None, None, None, None
+
+
+def _scene_offsets(view_scene_cpu, n_scenes):
+    counts = torch.bincount(view_scene_cpu.long(), minlength=n_scenes)
+    off = torch.zeros(n_scenes + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(counts, 0).int()
+    return off
+
+
+_view_map_cache = {}
+
+
+def _device_view_maps(local_scene, n_scenes, device):
+    """Device copies of (view_scene, scene_view_offsets), cached: the same maps recur every step."""
+    key = (local_scene.numpy().tobytes(), n_scenes, str(device))
+    hit = _view_map_cache.get(key)
+    if hit is None:
+        if len(_view_map_cache) > 256:
+            _view_map_cache.clear()
+        hit = (local_scene.to(device), _scene_offsets(local_scene, n_scenes).to(device))
+        _view_map_cache[key] = hit
+    return hit
+
+
+def render_views(gaussians, view_mats, proj_mats, view_scene_cpu, bg, cfg: ViewConfig,
+                 max_views_per_call: Optional[int] = None):
+    """Differentiable rendering of VW views of B scenes.
+
+    gaussians [B,P,14] cuda fp32; view_mats / proj_mats [VW,16]; view_scene_cpu: CPU int tensor [VW], non-decreasing
+    (views of a scene contiguous).  Splits the views into chunks when one call would exceed the library limits
+    (pairs, instances); autograd sums the chunk gradients.  Returns image, alpha, depth, radii [VW,P].
+    """
+    VW = view_mats.shape[0]
+    B, P = gaussians.shape[0], gaussians.shape[1]
+    if VW and bool((view_scene_cpu[1:] < view_scene_cpu[:-1]).any()):
+        raise _lib.LgmError("view_scene must be non-decreasing (views of one scene contiguous)")
+    chunk = VW if max_views_per_call is None else max_views_per_call
+    if P > 0:
+        chunk = min(chunk, max(1, MAX_PAIRS_PER_CALL // P))
+    chunk = max(chunk, 1)
+    outs, v0 = [], 0
+    while v0 < VW or (VW == 0 and not outs):
+        v1 = min(VW, v0 + chunk)
+        vs = view_scene_cpu[v0:v1]
+        b0 = int(vs[0]) if v1 > v0 else 0
+        b1 = int(vs[-1]) + 1 if v1 > v0 else B
+        local_scene = (vs - b0).int()
+        try:
+            scene_dev, offsets_dev = _device_view_maps(local_scene, b1 - b0, gaussians.device)
+            o = _RenderViews.apply(
+                gaussians[b0:b1] if (b0, b1) != (0, B) else gaussians, view_mats[v0:v1], proj_mats[v0:v1],
+                scene_dev, offsets_dev, bg, cfg)
+        except TooManyInstances as e:
+            if v1 - v0 <= 1:
+                raise
+            chunk = max(1, int((v1 - v0) * 0.8 * MAX_INSTANCES / e.n_instances))
+            continue
+        outs.append(o)
+        v0 = v1
+        if VW == 0:
+            break
+    if len(outs) == 1:
+        return outs[0]
+    return tuple(torch.cat([o[i] for o in outs], 0) for i in range(4))

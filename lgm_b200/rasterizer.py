@@ -1,0 +1,109 @@
+"""Drop-in for `diff_gaussian_rasterization` (the external package imported at /root/reference/core/gs.py:7-10):
+`GaussianRasterizationSettings` and `GaussianRasterizer`, same field order, argument names, return order
+(color, radii, depth, alpha) and error behaviour (SURVEY.md §8b level 1) — backed by the batched sm_100a kernels
+with n_views = 1.
+
+Not on LGM's path and not implemented yet (raise NotImplementedError, never a silent fallback):
+spherical-harmonics colours (`shs`) and `cov3D_precomp` inputs.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """One view.  Gradients in upstream's order: means3D, means2D, sh, colors_precomp, opacities, scales,
+    rotations, cov3Ds_precomp, raster_settings."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, colors_precomp, opacities, scales, rotations, raster_settings):
+        rs = raster_settings
+        dev = means3D.device
+        P = means3D.shape[0]
+        g = torch.cat([means3D.float(), opacities.float().reshape(P, 1), scales.float(), rotations.float(),
+                       colors_precomp.float()], dim=-1).reshape(1, P, 14).contiguous()
+        cfg = ops.ViewConfig(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+                             float(rs.scale_modifier))
+        vm = rs.viewmatrix.to(dev).float().reshape(1, 16).contiguous()
+        pm = rs.projmatrix.to(dev).float().reshape(1, 16).contiguous()
+        bg = rs.bg.to(dev).float().reshape(3).contiguous()
+        view_scene = torch.zeros(1, dtype=torch.int32, device=dev)
+        offsets = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+        image, alpha, depth, st = ops.forward_views(g, vm, pm, view_scene, offsets, bg, cfg)
+        ctx.st = st
+        ctx.save_for_backward(g, vm, pm, bg, alpha)
+        radii = st.radii.view(P)
+        ctx.mark_non_differentiable(radii)
+        return image[0], radii, depth[0], alpha[0]
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii, grad_depth, grad_alpha):
+        g, vm, pm, bg, alpha = ctx.saved_tensors
+        st = ctx.st
+        H, W = st.cfg.image_height, st.cfg.image_width
+        z = lambda t, c: (torch.zeros(1, c, H, W, device=g.device) if t is None else t.reshape(1, c, H, W).contiguous().float())
+        d_gauss, rows = ops.backward_views(g, vm, pm, bg, st, alpha, z(grad_color, 3), z(grad_alpha, 1), z(grad_depth, 1))
+        d = d_gauss[0]
+        P = d.shape[0]
+        d_means2D = torch.zeros(P, 3, device=g.device)
+        d_means2D[:, :2] = rows[:P, 0:2]
+        # (means3D, means2D, colors_precomp, opacities, scales, rotations, raster_settings)
+        return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], d[:, 4:7], d[:, 7:11], None
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # upstream: rasterizer.markVisible -> _C.mark_visible(positions, viewmatrix, projmatrix), under no_grad
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = positions.float().contiguous()
+            if pos.dim() != 2 or pos.shape[1] != 3:
+                raise _lib.LgmError("means3D must have dimensions (num_points, 3)")
+            vis = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
+            vm = rs.viewmatrix.to(pos.device).float().reshape(16).contiguous()
+            L = _lib.lib()
+            _lib.check(L.lgm_mark_visible(ops._stream(), pos.shape[0], _lib.ptr(pos), _lib.ptr(vm), _lib.ptr(vis)),
+                       "lgm_mark_visible")
+            return vis.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if shs is not None:
+            raise NotImplementedError("lgm_b200: spherical-harmonics colours (shs) are not on LGM's path and are not "
+                                      "implemented; pass colors_precomp")
+        if cov3D_precomp is not None:
+            raise NotImplementedError("lgm_b200: cov3D_precomp is not on LGM's path and is not implemented; "
+                                      "pass scales and rotations")
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise _lib.LgmError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise _lib.LgmError("lgm_b200 has no CPU path: tensors must be on a CUDA device")
+        return _RasterizeGaussians.apply(means3D, means2D, colors_precomp, opacities, scales, rotations,
+                                         self.raster_settings)

@@ -1,0 +1,67 @@
+"""world_size = 2 on CPU (gloo): the autograd collective of the view-sharded renderer — identity forward, one
+all-reduce(sum) of the Gaussian gradient in backward — with a stand-in differentiable 'render' (the CUDA path needs
+a GPU; its sharded run is covered by bench.py --gpus N and tests marked gpu)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lgm_b200.dist import partition_views, replicate_for_view_sharding, shard_views
+        torch.manual_seed(0)
+        B, N, V = 2, 16, 5
+        g_full = torch.randn(B, N, 14)
+        cams = torch.randn(B, V, 4, 4)
+        # rank 1 starts from garbage and receives the Gaussians by broadcast from rank 0
+        g_in = g_full.clone() if rank == 0 else torch.zeros_like(g_full)
+        g_in.requires_grad_(True)
+        g = replicate_for_view_sharding(g_in, None, broadcast_src=0)
+        assert torch.equal(g.detach(), g_full)
+        vm, _, _, scene, (b, e) = shard_views(cams, cams, torch.zeros(B, V, 3), rank, world)
+        assert (b, e) == partition_views(B * V, world, rank)
+        # stand-in per-view "render": view j of scene s -> sum(g[s] * w_j)
+        w = vm.sum(-1)
+        loss = sum((g[int(scene[j])] * w[j]).sum() for j in range(e - b))
+        loss.backward()
+        # expected: gradient of the sum over ALL views
+        w_all = cams.reshape(B * V, 16).sum(-1)
+        exp = torch.zeros_like(g_full)
+        for j in range(B * V):
+            exp[j // V] += w_all[j]
+        ok = torch.allclose(g_in.grad, exp, rtol=1e-5, atol=1e-5)
+        q.put((rank, bool(ok), (b, e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_view_sharded_gradient_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    blocks = sorted(b for _, _, b in res)
+    assert blocks == [(0, 5), (5, 10)]

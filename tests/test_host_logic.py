@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: the drop-in API's argument checks, camera conventions, view partitioning."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from lgm_b200 import GaussianRasterizationSettings, GaussianRasterizer, LgmError
+from lgm_b200.cameras import camera_matrices, orbit_camera, projection_matrix
+from lgm_b200.dist import partition_views, shard_views
+
+
+def _settings(dev="cpu"):
+    return GaussianRasterizationSettings(
+        image_height=32, image_width=32, tanfovx=0.5, tanfovy=0.5, bg=torch.ones(3, device=dev), scale_modifier=1.0,
+        viewmatrix=torch.eye(4, device=dev), projmatrix=torch.eye(4, device=dev), sh_degree=0,
+        campos=torch.zeros(3, device=dev), prefiltered=False, debug=False)
+
+
+def test_settings_field_order_matches_reference_call():
+    # /root/reference/core/gs.py:58-71 passes these keywords; upstream's NamedTuple order:
+    assert GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_import_name_shim():
+    import diff_gaussian_rasterization as d
+    assert d.GaussianRasterizer is GaussianRasterizer and d.GaussianRasterizationSettings is GaussianRasterizationSettings
+
+
+def test_argument_exclusivity_errors():
+    r = GaussianRasterizer(_settings())
+    P = 4
+    m, m2, o = torch.zeros(P, 3), torch.zeros(P, 3), torch.ones(P, 1)
+    s, q, c = torch.ones(P, 3), torch.ones(P, 4), torch.ones(P, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(m, m2, o, shs=None, colors_precomp=None, scales=s, rotations=q)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(m, m2, o, shs=torch.zeros(P, 1, 3), colors_precomp=c, scales=s, rotations=q)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m2, o, colors_precomp=c)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m2, o, colors_precomp=c, scales=s, rotations=q, cov3D_precomp=torch.zeros(P, 6))
+    with pytest.raises(NotImplementedError):
+        r(m, m2, o, shs=torch.zeros(P, 1, 3), scales=s, rotations=q)
+    with pytest.raises(NotImplementedError):
+        r(m, m2, o, colors_precomp=c, cov3D_precomp=torch.zeros(P, 6))
+    with pytest.raises(LgmError, match="num_points, 3"):
+        r(torch.zeros(P, 4), m2, o, colors_precomp=c, scales=s, rotations=q)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly — the product has no CPU path."""
+    r = GaussianRasterizer(_settings())
+    P = 4
+    with pytest.raises(LgmError, match="no CPU path"):
+        r(torch.zeros(P, 3), torch.zeros(P, 3), torch.ones(P, 1), colors_precomp=torch.ones(P, 3), scales=torch.ones(P, 3),
+          rotations=torch.ones(P, 4))
+    from lgm_b200 import ops
+    cfg = ops.ViewConfig(32, 32, 0.5, 0.5)
+    with pytest.raises(LgmError, match="CUDA tensor"):
+        ops.render_views(torch.zeros(1, 4, 14), torch.zeros(1, 16), torch.zeros(1, 16), torch.zeros(1, dtype=torch.int32),
+                         torch.ones(3), cfg)
+
+
+def test_product_never_imports_oracle():
+    import os, re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lgm_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "liboracle" not in src and "splat_oracle" not in src, f
+
+
+def test_orbit_camera_convention():
+    c2w = orbit_camera(0, 0, 1.5)
+    assert np.allclose(c2w[:3, 3], [0, 0, 1.5]) and np.allclose(c2w[:3, :3], np.eye(3), atol=1e-6)
+    c2w = orbit_camera(30, 90, 2.0)
+    assert np.allclose(c2w[:3, 3], [2 * math.cos(math.radians(30)), -1.0, 0], atol=1e-6)
+    R = c2w[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-5) and np.isclose(np.linalg.det(R), 1, atol=1e-5)
+    # origin must land in front of the camera (view z = radius) and project to the image centre
+    P = projection_matrix(49.1, 0.5, 2.5)
+    cv, cvp, cp = camera_matrices(c2w[None], P)
+    h = torch.tensor([0, 0, 0, 1.0]) @ cv[0]
+    assert torch.isclose(h[2], torch.tensor(2.0), atol=1e-5)
+    hp = torch.tensor([0, 0, 0, 1.0]) @ cvp[0]
+    assert abs(hp[0] / hp[3]) < 1e-5 and abs(hp[1] / hp[3]) < 1e-5
+    assert torch.allclose(cp[0], -torch.tensor(c2w[:3, 3]))  # /root/reference/core/provider_lvis.py:209
+
+
+def test_projection_matrix_matches_reference_formula():
+    P = projection_matrix(49.1, 0.5, 2.5)
+    t = math.tan(0.5 * math.radians(49.1))
+    assert P[0, 0] == pytest.approx(1 / t) and P[1, 1] == pytest.approx(1 / t)
+    assert P[2, 2] == pytest.approx(3.0 / 2.0) and P[3, 2] == pytest.approx(-1.25 / 2.0) and P[2, 3] == 1
+
+
+@pytest.mark.parametrize("n,world", [(208, 8), (640, 8), (26, 4), (5, 8), (0, 2), (7, 1)])
+def test_partition_views_covers_exactly(n, world):
+    blocks = [partition_views(n, world, r) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == n
+    for (b0, e0), (b1, e1) in zip(blocks[:-1], blocks[1:]):
+        assert e0 == b1 and b0 <= e0
+    assert max(e - b for b, e in blocks) == (n + world - 1) // world if n else True
+
+
+def test_shard_views_scene_indices():
+    B, V = 3, 5
+    cv = torch.arange(B * V * 16, dtype=torch.float32).reshape(B, V, 4, 4)
+    got = []
+    for r in range(4):
+        vm, pm, cp, scene, (b, e) = shard_views(cv, cv + 1, torch.zeros(B, V, 3), r, 4)
+        assert vm.shape == (e - b, 16) and torch.equal(pm, vm + 1)
+        assert torch.equal(scene, (torch.arange(b, e) // V).int())
+        assert bool((scene[1:] >= scene[:-1]).all())
+        got.append(vm)
+    assert torch.equal(torch.cat(got), cv.reshape(B * V, 16))
