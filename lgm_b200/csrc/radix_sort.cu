@@ -30,7 +30,7 @@ constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kValMask = ~kFlagMask;
 
 __global__ void __launch_bounds__(kSortThreads)
-histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, uint32_t* __restrict__ hist)
+histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int end_bit, uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < n_pass * kRadix; i += kSortThreads) s_hist[i] = 0;
@@ -44,7 +44,9 @@ histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, uint
         const bool valid = i < n;
         const uint64_t k = valid ? keys[i] : 0ull;
         for (int p = 0; p < n_pass; p++) {
-            const uint32_t d = valid ? (uint32_t)(k >> (p * kRadixBits)) & (kRadix - 1) : 0x100u + lane;
+            // the last pass may cover fewer than 8 significant bits: bits at and above end_bit are ignored
+            const uint32_t dmask = (1u << min(kRadixBits, end_bit - p * kRadixBits)) - 1u;
+            const uint32_t d = valid ? (uint32_t)(k >> (p * kRadixBits)) & dmask : 0x100u + lane;
             const uint32_t m = __match_any_sync(0xffffffffu, d);
             if (valid && lane == (__ffs(m) - 1)) atomicAdd(&s_hist[p * kRadix + d], (uint32_t)__popc(m));
         }
@@ -69,7 +71,7 @@ struct OnesweepSmem {
 __global__ void __launch_bounds__(kSortThreads, 2)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                const uint32_t* __restrict__ hist /*[256] of this pass*/, uint32_t* lookback /*[tiles][256], zeroed*/,
+                uint32_t dmask /* (1 << significant bits of this digit) - 1 */, const uint32_t* __restrict__ hist /*[256] of this pass*/, uint32_t* lookback /*[tiles][256], zeroed*/,
                 uint32_t* ticket /*zeroed*/)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,7 +85,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     const uint32_t base = tile * (uint32_t)kTileItems;
     const uint32_t n_valid = min((uint32_t)kTileItems, n - base);
 
-    // ---- load (warp-striped: item i of lane l of warp w = base + w*512 + i*32 + l); pads sort last (digit 255) ----
+    // ---- load (warp-striped: item i of lane l of warp w = base + w*512 + i*32 + l); pads (all-ones keys) have the
+    // largest digit (dmask) in every pass and, being last in load order, rank after every real key of that digit ----
     uint64_t k[kItems];
     uint32_t v[kItems];
 #pragma unroll
@@ -100,7 +103,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-        const uint32_t d = (uint32_t)(k[i] >> shift) & (kRadix - 1);
+        const uint32_t d = (uint32_t)(k[i] >> shift) & dmask;
         const uint32_t m = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(m) - 1;
         uint32_t pre = 0;
@@ -122,7 +125,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
         sm.whist[w * kRadix + t] = cnt;
         cnt += c;
     }
-    const uint32_t cnt_valid = (t == kRadix - 1) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
+    const uint32_t cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
 
     // ---- publish the aggregate as early as possible, then the CTA-local scans ----
     volatile uint32_t* lb = lookback;
@@ -171,7 +174,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     // ---- scatter into the staged tile (sorted by digit, stable) ----
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
-        const uint32_t d = (uint32_t)(k[i] >> shift) & (kRadix - 1);
+        const uint32_t d = (uint32_t)(k[i] >> shift) & dmask;
         const uint32_t pos = sm.bin_start[d] + wh[d] + rank[i];
         sm.keys[pos] = k[i];
         sm.vals[pos] = v[i];
@@ -184,7 +187,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
         const uint32_t j = i * kSortThreads + t;
         if (j < n_valid) {
             const uint64_t key = sm.keys[j];
-            const uint32_t d = (uint32_t)(key >> shift) & (kRadix - 1);
+            const uint32_t d = (uint32_t)(key >> shift) & dmask;
             const uint32_t dst = sm.goff[d] + j;
             keys_out[dst] = key;
             vals_out[dst] = sm.vals[j];
@@ -230,7 +233,7 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
     uint32_t* valt = sort_input_is_tmp(end_bit) ? vals_out : vals_tmp;
 
     const int hist_grid = (int)min((size_t)148 * 8, (size_t)(n + kSortThreads * 8 - 1) / (kSortThreads * 8));
-    histogram_kernel<<<hist_grid, kSortThreads, 0, stream>>>(kin, n, np, hist);
+    histogram_kernel<<<hist_grid, kSortThreads, 0, stream>>>(kin, n, np, end_bit, hist);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
 
@@ -242,7 +245,8 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
     }
     for (int p = 0; p < np; p++) {
         onesweep_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), stream>>>(
-            kin, vin, kalt, valt, n, p * kRadixBits, hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tickets + p);
+            kin, vin, kalt, valt, n, p * kRadixBits, (1u << (end_bit - p * kRadixBits < kRadixBits ? end_bit - p * kRadixBits : kRadixBits)) - 1u,
+            hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tickets + p);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         uint64_t* tk = kin; kin = kalt; kalt = tk;

@@ -161,14 +161,19 @@ def test_stage_by_stage_parity(oracle32, kind, B, V, N, W, H, fovy, mod):
     assert st.num_rendered == total
 
 
-def _grad_check(got, ref, what, tol=1e-3):
-    scale = np.abs(ref).max() + 1e-30
-    err = np.abs(got - ref)
-    assert err.max() <= tol * scale, f"{what}: max err {err.max() / scale:.2e} of the gradient scale"
-    big = np.abs(ref) > 1e-2 * scale
-    if big.any():
-        rel = err[big] / np.abs(ref[big])
-        assert np.quantile(rel, 0.999) <= 10 * tol, f"{what}: 99.9th pct relative error {np.quantile(rel, 0.999):.2e}"
+def _grad_check(got, ref64, what, ref32=None, tol=1e-3):
+    """<= 1e-3 relative on accumulated gradients, measured against the fp64 oracle as max error over the tensor's
+    scale and as relative L2.  Where the fp32 ALGORITHM itself (the oracle's fp32 build, same operation order as the
+    reference) is noisier than that against fp64 — saturated pixels recover T by division from T_final ~ 1e-4, which
+    amplifies one ulp of the alpha sum to ~1e-3 — the CUDA path must be within 2x of that noise instead."""
+    scale = np.abs(ref64).max() + 1e-30
+    norm = np.linalg.norm(ref64) + 1e-30
+    err, l2 = np.abs(got - ref64).max() / scale, np.linalg.norm(got - ref64) / norm
+    n_err = n_l2 = 0.0
+    if ref32 is not None:
+        n_err, n_l2 = np.abs(ref32 - ref64).max() / scale, np.linalg.norm(ref32 - ref64) / norm
+    assert err <= max(tol, 2 * n_err), f"{what}: max err {err:.2e} of the gradient scale (fp32-algorithm noise {n_err:.2e})"
+    assert l2 <= max(tol, 2 * n_l2), f"{what}: relative L2 error {l2:.2e} (fp32-algorithm noise {n_l2:.2e})"
 
 
 @pytest.mark.parametrize("kind,with_depth", [("trained", True), ("init", False)])
@@ -192,17 +197,20 @@ def test_renderer_forward_backward_vs_oracle(oracle32, oracle64, kind, with_dept
     loss.backward()
     torch.cuda.synchronize()
     t = tan_half(opt.fovy)
-    for o, tol in ((oracle32, 1e-3), (oracle64, 1e-3)):
+    refs = {}
+    for o in (oracle32, oracle64):
         fw = o.render_step(g.numpy(), cv.numpy(), cvp.numpy(), bg.numpy(), S, S, t, t)
         mask = ((fw["image"] >= 0) & (fw["image"] <= 1)).astype(np.float64)   # clamp's gradient mask, core/gs.py:87
-        ref = o.render_step(g.numpy(), cv.numpy(), cvp.numpy(), bg.numpy(), S, S, t, t, 1.0, d_img.numpy() * mask,
-                            d_alpha.numpy(), d_depth.numpy())
-        _assert_image_close("image", out["image"].detach().cpu().numpy(), np.clip(ref["image"], 0, 1), max_bad_frac=1e-4)
-        _assert_image_close("alpha", out["alpha"].detach().cpu().numpy(), ref["alpha"], max_bad_frac=1e-4)
-        dg = gd.grad.cpu().numpy()
-        for sl, nm in ((slice(0, 3), "means"), (slice(3, 4), "opacity"), (slice(4, 7), "scales"), (slice(7, 11), "rots"),
-                       (slice(11, 14), "rgb")):
-            _grad_check(dg[..., sl], ref["dgaussians"][..., sl], f"dL/d{nm} ({o.dt.__name__})", tol)
+        refs[o.dt] = o.render_step(g.numpy(), cv.numpy(), cvp.numpy(), bg.numpy(), S, S, t, t, 1.0, d_img.numpy() * mask,
+                                   d_alpha.numpy(), d_depth.numpy())
+    r32, r64 = refs[np.float32], refs[np.float64]
+    _assert_image_close("image", out["image"].detach().cpu().numpy(), np.clip(r32["image"], 0, 1))
+    _assert_image_close("alpha", out["alpha"].detach().cpu().numpy(), r32["alpha"])
+    _assert_image_close("image vs f64", out["image"].detach().cpu().numpy(), np.clip(r64["image"], 0, 1), max_bad_frac=1e-4)
+    dg = gd.grad.cpu().numpy()
+    for sl, nm in ((slice(0, 3), "means"), (slice(3, 4), "opacity"), (slice(4, 7), "scales"), (slice(7, 11), "rots"),
+                   (slice(11, 14), "rgb")):
+        _grad_check(dg[..., sl], r64["dgaussians"][..., sl], f"dL/d{nm}", r32["dgaussians"][..., sl])
 
 
 def test_level1_rasterizer_api(oracle64):
@@ -235,19 +243,24 @@ def test_level1_rasterizer_api(oracle64):
     a = (gn[:, 0:3], gn[:, 4:7], gn[:, 7:11], gn[:, 3], gn[:, 11:14], cv[0, 0].numpy(), cvp[0, 0].numpy(), bg.numpy(), S, S, t, t)
     pre, b, f = oracle64.rasterize(*a)
     ref = oracle64.rasterize_backward(*a, pre, b, f, wi, wa[0], wd[0])
-    assert (radii.cpu().numpy() != pre["radii"]).mean() < 1e-3      # fp64 arbiter: radii may differ on a rounding edge
-    _assert_image_close("color", color.detach().cpu().numpy(), f["image"], max_bad_frac=1e-4)
-    _grad_check(means3D.grad.cpu().numpy(), ref["dL_dmeans"], "means3D")
-    _grad_check(opac.grad.cpu().numpy()[:, 0], ref["dL_dopacity"], "opacities")
-    _grad_check(scales.grad.cpu().numpy(), ref["dL_dscales"], "scales")
-    _grad_check(rots.grad.cpu().numpy(), ref["dL_drots"], "rotations")
-    _grad_check(rgbs.grad.cpu().numpy(), ref["dL_dcolor"], "colors_precomp")
-    _grad_check(means2D.grad.cpu().numpy()[:, :2], ref["dL_dmean2D"], "means2D")
+    from oracle.oracle import Oracle
+    o32 = Oracle("f32")
+    pre32, b32, f32 = o32.rasterize(*a)
+    r32 = o32.rasterize_backward(*a, pre32, b32, f32, wi, wa[0], wd[0])
+    assert np.array_equal(radii.cpu().numpy(), pre32["radii"])
+    _assert_image_close("color", color.detach().cpu().numpy(), f32["image"])
+    _assert_image_close("alpha", alpha.detach().cpu().numpy(), f32["alpha"])
+    _assert_image_close("depth", depth.detach().cpu().numpy(), f32["depth"], atol=1e-5, rtol=1e-4, hard=4.0 / 255.0)
+    _grad_check(means3D.grad.cpu().numpy(), ref["dL_dmeans"], "means3D", r32["dL_dmeans"])
+    _grad_check(opac.grad.cpu().numpy()[:, 0], ref["dL_dopacity"], "opacities", r32["dL_dopacity"])
+    _grad_check(scales.grad.cpu().numpy(), ref["dL_dscales"], "scales", r32["dL_dscales"])
+    _grad_check(rots.grad.cpu().numpy(), ref["dL_drots"], "rotations", r32["dL_drots"])
+    _grad_check(rgbs.grad.cpu().numpy(), ref["dL_dcolor"], "colors_precomp", r32["dL_dcolor"])
+    _grad_check(means2D.grad.cpu().numpy()[:, :2], ref["dL_dmean2D"], "means2D", r32["dL_dmean2D"])
     assert float(means2D.grad[:, 2].abs().max()) == 0.0
     # markVisible
     vis = rast.markVisible(means3D.detach())
-    from oracle.oracle import Oracle
-    assert np.array_equal(vis.cpu().numpy(), Oracle("f32").mark_visible(gn[:, 0:3], cv[0, 0].numpy()))
+    assert np.array_equal(vis.cpu().numpy(), o32.mark_visible(gn[:, 0:3], cv[0, 0].numpy()))
 
 
 def test_edge_cases():
@@ -265,7 +278,7 @@ def test_edge_cases():
     g[:, :, 0:3] = g[:, :, 0:3] * 0.01 + 50.0
     gd = g.to(DEV).requires_grad_(True)
     out = r.render(gd, cv, cvp, cp, bg_color=bg)
-    assert float(out["alpha"].abs().max()) == 0.0
+    assert float(out["alpha"].detach().abs().max()) == 0.0
     out["image"].sum().backward()
     assert float(gd.grad.abs().max()) == 0.0
     # one huge opaque Gaussian: saturates, alpha <= 1
