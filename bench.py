@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--sort-sweep", action="store_true", help="also time every onesweep launch shape (LGM_SORT_VARIANT)")
     return ap.parse_args()
 
 
@@ -291,31 +292,49 @@ def run_native(args):
         Lr = st.num_rendered
         n_tiles = ((S + 15) // 16) ** 2
         npass = ops.sort_passes(n_local * n_tiles)
-        end_bit = 32 + max(1, (max(n_local * n_tiles, 1) - 1).bit_length())
-        # the sort alone, on the step's real (unsorted-order irrelevant for timing: use the sorted keys shuffled) keys
+        end_bit = ops.sort_end_bit(n_local * n_tiles)
+        # the sort alone, on the step's real keys in EMIT order (ascending view*P+idx, tiles row-major within a
+        # Gaussian = a stable sort of the sorted pairs by value), compressed-key mode as in the renderer
         Lb = _lib.lib()
-        perm = torch.randperm(Lr, device=dev)
+        perm = torch.sort(st.vals[:Lr].long() & 0xFFFFFFFF, stable=True).indices
         keys_u = st.keys[:Lr][perm].contiguous()
         vals_u = st.vals[:Lr][perm].contiguous()
+        del perm
         k_other, v_other = torch.empty_like(keys_u), torch.empty_like(vals_u)
         in_tmp = bool(Lb.lgm_sort_input_is_tmp(end_bit))
         import ctypes
-        nb = ctypes.c_size_t(0)
-        _lib.check(Lb.lgm_sort_workspace_bytes(Lr, end_bit, nb), "ws")
-        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-        sort_ms = []
-        for it in range(5):
-            kin, vin = keys_u.clone(), vals_u.clone()
-            ko, vo, kt, vt = (k_other, v_other, kin, vin) if in_tmp else (kin, vin, k_other, v_other)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _lib.check(Lb.lgm_sort_pairs(torch.cuda.current_stream().cuda_stream, _lib.ptr(ko), _lib.ptr(vo), _lib.ptr(kt),
-                                         _lib.ptr(vt), Lr, end_bit, _lib.ptr(ws), nb.value), "sort")
-            b.record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                sort_ms.append(a.elapsed_time(b))
-        t_sort = sum(sort_ms) / len(sort_ms)
+
+        def time_sort():
+            nb = ctypes.c_size_t(0)
+            _lib.check(Lb.lgm_sort_workspace_bytes(Lr, end_bit, nb), "ws")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            out = []
+            for it in range(5):
+                kin, vin = keys_u.clone(), vals_u.clone()
+                ko, vo, kt, vt = (k_other, v_other, kin, vin) if in_tmp else (kin, vin, k_other, v_other)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(Lb.lgm_sort_pairs(torch.cuda.current_stream().cuda_stream, _lib.ptr(ko), _lib.ptr(vo), _lib.ptr(kt),
+                                             _lib.ptr(vt), Lr, end_bit, 1, _lib.ptr(ws), nb.value), "sort")
+                b.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    out.append(a.elapsed_time(b))
+            assert bool((ko[1:] >= ko[:-1]).all()), "standalone sort produced unsorted keys"
+            return sum(out) / len(out)
+
+        t_sort = time_sort()
+        sort_variants = None
+        if args.sort_sweep:
+            sort_variants = {}
+            keep = os.environ.get("LGM_SORT_VARIANT")
+            for vi in range(6):
+                os.environ["LGM_SORT_VARIANT"] = str(vi)
+                sort_variants[str(vi)] = time_sort()
+            if keep is None:
+                del os.environ["LGM_SORT_VARIANT"]
+            else:
+                os.environ["LGM_SORT_VARIANT"] = keep
         peak, peak_src = load_peaks()
         sort_bytes = (npass * 24 + 8) * Lr
         ach = sort_bytes / (t_sort * 1e-3) / 1e9
@@ -330,7 +349,7 @@ def run_native(args):
         lens = (st.ranges[:, 1] - st.ranges[:, 0]).long()
         pair_evals = int(lens.sum()) * 256
         extra = {
-            "instances_per_step_rank0": Lr, "instances_per_view": Lr / max(n_local, 1),
+            "instances_per_step_rank0": Lr, "instances_per_view": Lr / max(n_local, 1), "sort_variants_ms": sort_variants,
             "roofline_preprocess_sort": {"bound": "hbm", "achieved": grp_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
                                          "peak": peak, "unit": "GB/s", "frac": (grp_bytes / (t_grp * 1e-3) / 1e9) / peak if t_grp > 0 else None,
                                          "algorithmic_bytes": int(grp_bytes), "ms": t_grp},

@@ -124,13 +124,15 @@ int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* g
 /* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
-/* The sort on its own (parity / benchmark hook): sorts n pairs on key bits [0, end_bit).  The unsorted input
- * must be in (keys_tmp, vals_tmp) when lgm_sort_input_is_tmp(end_bit) != 0, else in (keys_out, vals_out);
- * the result is always in (keys_out, vals_out).                                                             */
+/* The sort on its own (parity / benchmark hook): sorts n pairs, stably, on key bits [0, end_bit).  The unsorted
+ * input must be in (keys_tmp, vals_tmp) when lgm_sort_input_is_tmp(end_bit) != 0, else in (keys_out, vals_out);
+ * the result is always in (keys_out, vals_out).  compress != 0: every key has bit 31 clear (a positive float in
+ * the low word) and the sort runs on the 63-bit value key[30:0] | key[63:32] << 31 — end_bit counts THOSE bits —
+ * which is the renderer's configuration (same order as the full key, one pass fewer at 208 views x 400 tiles). */
 int lgm_sort_input_is_tmp(int32_t end_bit);
 int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes);
 int lgm_sort_pairs(void* stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                   int64_t n, int32_t end_bit, void* workspace, size_t workspace_bytes);
+                   int64_t n, int32_t end_bit, int32_t compress, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus
 }

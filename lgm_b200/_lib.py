@@ -40,7 +40,7 @@ _SIGNATURES = {
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "lgm_sort_input_is_tmp": (ctypes.c_int, [_i32]),
     "lgm_sort_workspace_bytes": (ctypes.c_int, [_i64, _i32, ctypes.POINTER(_sz)]),
-    "lgm_sort_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _sz]),
+    "lgm_sort_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -63,11 +63,12 @@ int bits_for(uint64_t n_minus_1)
     while (n_minus_1) { b++; n_minus_1 >>= 1; }
     return b;
 }
-// key bits that carry information: 32 depth bits + bits of the largest global tile id
+// sort bits of the compressed key (radix_sort.cu): 31 depth bits (the sign bit of a depth > 0.2 is always 0) + the
+// bits of the largest global tile id
 int key_end_bit(const lgm::RenderParams& p)
 {
     const uint64_t gtiles = (uint64_t)p.n_views * (uint64_t)p.n_tiles;
-    return 32 + (gtiles > 1 ? bits_for(gtiles - 1) : 1);
+    return 31 + (gtiles > 1 ? bits_for(gtiles - 1) : 1);
 }
 
 struct BinWorkspace {
@@ -162,7 +163,7 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     LGM_CUDA(lgm::launch_emit(s, p, radii, reinterpret_cast<const float2*>(xy), depth, block_offsets,
                               in_tmp ? keys_tmp : keys_sorted, in_tmp ? vals_tmp : vals_sorted),
              "forward_bin: emit");
-    LGM_CUDA(lgm::launch_onesweep_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, L, end_bit, ws + w.sort_scratch,
+    LGM_CUDA(lgm::launch_onesweep_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, L, end_bit, /*compress=*/1, ws + w.sort_scratch,
                                        w.sort_scratch_bytes),
              "forward_bin: sort");
     LGM_CUDA(lgm::launch_tile_ranges(s, keys_sorted, L, reinterpret_cast<uint2*>(ranges)), "forward_bin: ranges");
@@ -271,16 +272,17 @@ int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes)
 }
 
 int lgm_sort_pairs(void* stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                   int64_t n, int32_t end_bit, void* workspace, size_t workspace_bytes)
+                   int64_t n, int32_t end_bit, int32_t compress, void* workspace, size_t workspace_bytes)
 {
     if (n < 0 || n >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "sort: n must be in [0, 2^30)");
     if (end_bit < 1 || end_bit > 64) return fail(LGM_ERR_BAD_VALUE, "sort: end_bit must be in [1, 64]");
+    if (compress && end_bit > 63) return fail(LGM_ERR_BAD_VALUE, "sort: compressed keys have at most 63 bits");
     if (n == 0) return LGM_OK;
     LGM_NOTNULL(keys_out); LGM_NOTNULL(vals_out); LGM_NOTNULL(keys_tmp); LGM_NOTNULL(vals_tmp); LGM_NOTNULL(workspace);
     if (workspace_bytes < lgm::sort_scratch_bytes((uint32_t)n, end_bit))
         return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "sort: workspace too small (see lgm_sort_workspace_bytes)");
     LGM_CUDA(lgm::launch_onesweep_sort((cudaStream_t)stream, keys_out, vals_out, keys_tmp, vals_tmp, (uint32_t)n, end_bit,
-                                       workspace, workspace_bytes),
+                                       compress ? 1 : 0, workspace, workspace_bytes),
              "sort_pairs");
     return LGM_OK;
 }

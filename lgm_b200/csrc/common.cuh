@@ -44,7 +44,8 @@ int sort_num_passes(int end_bit);
 bool sort_input_is_tmp(int end_bit);
 size_t sort_scratch_bytes(uint32_t n, int end_bit);
 cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp,
-                                 uint32_t* vals_tmp, uint32_t n, int end_bit, void* scratch, size_t scratch_bytes);
+                                 uint32_t* vals_tmp, uint32_t n, int end_bit, int compress, void* scratch,
+                                 size_t scratch_bytes);
 
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,

@@ -3,14 +3,21 @@
 // Replaces renderCUDA fwd/bwd of the external rasterizer; every view of the step
 // is rendered by ONE launch (grid = views x tiles).
 //
-// Per-pair arithmetic that decides skip / stop (power, alpha, test_T) and the forward accumulators are pinned
-// (splat_math.cuh), so forward and backward take identical decisions and the forward matches the oracle up to expf.
+// Work skipping that cannot change a result: while a batch of Gaussians is staged in shared memory, the staging
+// thread also derives a conservative screen-space box outside of which alpha = min(0.99, o * exp(power)) is
+// certainly < 1/255 (the reference's skip threshold).  Each warp owns an 8x4 pixel patch; one ballot per 32 staged
+// Gaussians selects those whose box meets the patch, and only these are evaluated — with the reference's exact,
+// pinned per-pair arithmetic (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
+//
 // Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / atomics in the backward).
 #include "common.cuh"
 #include "splat_math.cuh"
 
 namespace lgm {
 namespace {
+
+constexpr float kBoxScale = 1.002f;  // safety margins of the alpha >= 1/255 box (fp32 rounding of power / expf / logf)
+constexpr float kBoxPad = 0.02f;     // pixels
 
 // A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store).
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
@@ -20,6 +27,28 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
     py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
 }
 
+// Half extents (hx, hy) of the axis-aligned box around the Gaussian's centre that contains every point with
+// o * exp(power) >= 1/255, i.e. 0.5 * d^T Q d <= tau = ln(255 o), Q = [[cx, cy], [cy, cz]]:
+//   |dx| <= sqrt(2 tau cz / det Q),  |dy| <= sqrt(2 tau cx / det Q).
+// 255 o <= 1: never visible (negative extents fail every test).  Q not positive definite (or NaN): the region is
+// unbounded, keep the pair everywhere (huge extents).
+__device__ __forceinline__ float2 alpha_box(const float4 co)
+{
+    const float k = 255.0f * co.w;
+    if (k <= 1.0f) return make_float2(-1.0f, -1.0f);
+    const float det = co.x * co.z - co.y * co.y;
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return make_float2(1e30f, 1e30f);
+    const float t2 = 2.0f * __logf(k) * kBoxScale + 1e-3f;
+    const float inv = 1.0f / det;
+    return make_float2(sqrtf(t2 * co.z * inv) * kBoxScale + kBoxPad, sqrtf(t2 * co.x * inv) * kBoxScale + kBoxPad);
+}
+
+// patch = (X0, X1, Y0, Y1) pixel-centre bounds of the warp; NaNs compare false -> "hit"
+__device__ __forceinline__ bool box_hits_patch(const float4 p /*px,py,hx,hy*/, float X0, float X1, float Y0, float Y1)
+{
+    return !(p.x + p.z < X0) && !(p.x - p.z > X1) && !(p.y + p.w < Y0) && !(p.y - p.w > Y1);
+}
+
 __global__ void __launch_bounds__(kBlock, 4)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -27,10 +56,11 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const uint2* __restrict__ ranges, const float* __restrict__ bg, float* __restrict__ image,
                      float* __restrict__ alpha_img, float* __restrict__ depth_img, uint32_t* __restrict__ n_contrib)
 {
-    __shared__ float2 s_xy[kBlock];
-    __shared__ float4 s_co[kBlock];
-    __shared__ float4 s_rgbd[kBlock];
+    __shared__ float4 s_pos[kBlock];   // px, py, hx, hy
+    __shared__ float4 s_co[kBlock];    // conic xx, xy, yy, opacity
+    __shared__ float4 s_rgbd[kBlock];  // r, g, b, depth
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gt = blockIdx.x;
     const int view = gt / prm.n_tiles;
     const int tile = gt - view * prm.n_tiles;
@@ -40,6 +70,8 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     pixel_of_thread(tile_x, tile_y, px, py);
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
+    const float X0 = (float)(tile_x * kTile + (warp & 1) * 8), X1 = X0 + 7.0f;
+    const float Y0 = (float)(tile_y * kTile + (warp >> 1) * 4), Y1 = Y0 + 3.0f;
 
     const uint2 range = ranges[gt];
     const int todo = (int)(range.y - range.x);
@@ -48,7 +80,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const float* scene_g = gaussians + (size_t)scene * prm.P * 14;
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Wt = 0.f, D = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
     bool done = !inside;
 
     for (int r = 0; r < rounds; r++) {
@@ -56,35 +88,47 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         const int k = r * kBlock + threadIdx.x;
         if (k < todo) {
             const uint32_t g = vals[range.x + k];
-            s_xy[threadIdx.x] = xy[g];
-            s_co[threadIdx.x] = conic_opacity[g];
+            const float2 p = xy[g];
+            const float4 co = conic_opacity[g];
+            const float2 h = alpha_box(co);
+            s_pos[threadIdx.x] = make_float4(p.x, p.y, h.x, h.y);
+            s_co[threadIdx.x] = co;
             const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
             s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
         }
         __syncthreads();
         const int nb = min(kBlock, todo - r * kBlock);
-        for (int j = 0; !done && j < nb; j++) {
-            contributor++;
-            const float2 p = s_xy[j];
-            const float4 co = s_co[j];
-            const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
-            const float power = pair_power(co.x, co.y, co.z, dx, dy);
-            if (power > 0.0f) continue;
-            const float a = fminf(kAlphaMax, LGM_MUL(co.w, expf(power)));
-            if (a < kAlphaMin) continue;
-            const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
-            if (test_T < kTEps) {
-                done = true;
-                continue;
+        for (int base = 0; base < nb; base += 32) {
+            if (__all_sync(0xffffffffu, done)) break;  // every pixel of the patch is saturated (or outside)
+            const int jl = base + lane;
+            bool hit = false;
+            if (jl < nb) hit = box_hits_patch(s_pos[jl], X0, X1, Y0, Y1);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = base + __ffs(m) - 1;
+                m &= m - 1;
+                if (done) continue;
+                const float4 p = s_pos[j];
+                const float4 co = s_co[j];
+                const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
+                const float power = pair_power(co.x, co.y, co.z, dx, dy);
+                if (power > 0.0f) continue;
+                const float a = fminf(kAlphaMax, LGM_MUL(co.w, expf(power)));
+                if (a < kAlphaMin) continue;
+                const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
+                if (test_T < kTEps) {
+                    done = true;
+                    continue;
+                }
+                const float4 cd = s_rgbd[j];
+                C0 = LGM_FMA(LGM_MUL(cd.x, a), T, C0);
+                C1 = LGM_FMA(LGM_MUL(cd.y, a), T, C1);
+                C2 = LGM_FMA(LGM_MUL(cd.z, a), T, C2);
+                Wt = LGM_FMA(a, T, Wt);
+                D = LGM_FMA(LGM_MUL(cd.w, a), T, D);
+                T = test_T;
+                last = (uint32_t)(r * kBlock + j + 1);  // 1-based position in the tile's list (A.4 "contributor")
             }
-            const float4 cd = s_rgbd[j];
-            C0 = LGM_FMA(LGM_MUL(cd.x, a), T, C0);
-            C1 = LGM_FMA(LGM_MUL(cd.y, a), T, C1);
-            C2 = LGM_FMA(LGM_MUL(cd.z, a), T, C2);
-            Wt = LGM_FMA(a, T, Wt);
-            D = LGM_FMA(LGM_MUL(cd.w, a), T, D);
-            T = test_T;
-            last = contributor;
         }
     }
     if (inside) {
@@ -133,17 +177,16 @@ __device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float 
     Bv = bk;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                      const float* __restrict__ depth, const uint32_t* __restrict__ vals,
                      const uint2* __restrict__ ranges, const float* __restrict__ bg,
                      const float* __restrict__ alpha_img, const uint32_t* __restrict__ n_contrib,
-                     const float* __restrict__ dL_dimage,
-                     const float* __restrict__ dL_dalpha_img, const float* __restrict__ dL_ddepth_img,
-                     float* __restrict__ grad_rows)
+                     const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
+                     const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
 {
-    __shared__ float2 s_xy[kBlock];
+    __shared__ float4 s_pos[kBlock];
     __shared__ float4 s_co[kBlock];
     __shared__ float4 s_rgbd[kBlock];
     __shared__ uint32_t s_g[kBlock];
@@ -160,6 +203,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     pixel_of_thread(tile_x, tile_y, px, py);
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
+    const float X0 = (float)(tile_x * kTile + (warp & 1) * 8), X1 = X0 + 7.0f;
+    const float Y0 = (float)(tile_y * kTile + (warp >> 1) * 4), Y1 = Y0 + 3.0f;
     const size_t hw = (size_t)prm.H * prm.W;
     const size_t pix = (size_t)py * prm.W + px;
 
@@ -181,7 +226,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     }
     const float bg_dot = __ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2;
 
-    // Only list positions below the largest n_contrib of the tile can contribute.
+    // Only list positions below the largest n_contrib of the tile (of the warp's patch) can contribute.
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) s_max[warp] = wmax;
 #pragma unroll
@@ -202,70 +247,81 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         __syncthreads();  // staging buffers and s_acc rows are free again
         const int k = r * kBlock + threadIdx.x;
         if (k < todo) {
-            const uint32_t g = vals[range.x + (uint32_t)(todo - 1 - k)];
+            const uint32_t g = vals[range.x + (uint32_t)(todo - 1 - k)];  // slot t holds list position todo-1-k
             s_g[threadIdx.x] = g;
-            s_xy[threadIdx.x] = xy[g];
-            s_co[threadIdx.x] = conic_opacity[g];
+            const float2 p = xy[g];
+            const float4 co = conic_opacity[g];
+            const float2 h = alpha_box(co);
+            s_pos[threadIdx.x] = make_float4(p.x, p.y, h.x, h.y);
+            s_co[threadIdx.x] = co;
             const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
             s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
         }
         __syncthreads();
         const int nb = min(kBlock, todo - r * kBlock);
-        for (int j = 0; j < nb; j++) {
-            const uint32_t pos = (uint32_t)(todo - 1 - (r * kBlock + j));  // 0-based list position
-            if (pos >= wmax) continue;                                    // warp-uniform
-            bool valid = pos < last_contributor;
-            const float2 p = s_xy[j];
-            const float4 co = s_co[j];
-            const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
-            const float power = pair_power(co.x, co.y, co.z, dx, dy);
-            valid = valid && !(power > 0.0f);
-            const float G = expf(power);
-            const float a = fminf(kAlphaMax, LGM_MUL(co.w, G));
-            valid = valid && !(a < kAlphaMin);
-            if (!__any_sync(0xffffffffu, valid)) continue;
+        for (int base = 0; base < nb; base += 32) {
+            const int jl = base + lane;
+            bool hit = false;
+            // list position of slot jl is todo-1-(r*256+jl); positions >= wmax were never reached by this patch
+            if (jl < nb && (uint32_t)(todo - 1 - (r * kBlock + jl)) < wmax) hit = box_hits_patch(s_pos[jl], X0, X1, Y0, Y1);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = base + __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t pos = (uint32_t)(todo - 1 - (r * kBlock + j));
+                bool valid = pos < last_contributor;
+                const float4 p = s_pos[j];
+                const float4 co = s_co[j];
+                const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
+                const float power = pair_power(co.x, co.y, co.z, dx, dy);
+                valid = valid && !(power > 0.0f);
+                const float G = expf(power);
+                const float a = fminf(kAlphaMax, LGM_MUL(co.w, G));
+                valid = valid && !(a < kAlphaMin);
+                if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vb[2] = {0.f, 0.f};
-            if (valid) {
-                const float4 cd = s_rgbd[j];
-                T = T / (1.f - a);
-                const float w = a * T;
-                float dL_da = 0.f;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                lc0 = cd.x; lc1 = cd.y; lc2 = cd.z;
-                dL_da += (cd.x - acc0) * dC0;
-                dL_da += (cd.y - acc1) * dC1;
-                dL_da += (cd.z - acc2) * dC2;
-                accD = last_alpha * last_d + (1.f - last_alpha) * accD;
-                last_d = cd.w;
-                dL_da += (cd.w - accD) * dD;
-                accA = last_alpha + (1.f - last_alpha) * accA;
-                dL_da += (1.f - accA) * dA;
-                dL_da *= T;
-                last_alpha = a;
-                dL_da += (-T_final / (1.f - a)) * bg_dot;
-                const float dL_dG = co.w * dL_da;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                const float dG_ddely = -gdy * co.z - gdx * co.y;
-                va[0] = dL_dG * dG_ddelx * ddelx_dx;
-                va[1] = dL_dG * dG_ddely * ddely_dy;
-                va[2] = -0.5f * gdx * dx * dL_dG;
-                va[3] = -0.5f * gdx * dy * dL_dG;
-                va[4] = -0.5f * gdy * dy * dL_dG;
-                va[5] = G * dL_da;
-                va[6] = w * dC0;
-                va[7] = w * dC1;
-                vb[0] = w * dC2;
-                vb[1] = w * dD;
+                float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vb[2] = {0.f, 0.f};
+                if (valid) {
+                    const float4 cd = s_rgbd[j];
+                    T = T / (1.f - a);
+                    const float w = a * T;
+                    float dL_da = 0.f;
+                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                    lc0 = cd.x; lc1 = cd.y; lc2 = cd.z;
+                    dL_da += (cd.x - acc0) * dC0;
+                    dL_da += (cd.y - acc1) * dC1;
+                    dL_da += (cd.z - acc2) * dC2;
+                    accD = last_alpha * last_d + (1.f - last_alpha) * accD;
+                    last_d = cd.w;
+                    dL_da += (cd.w - accD) * dD;
+                    accA = last_alpha + (1.f - last_alpha) * accA;
+                    dL_da += (1.f - accA) * dA;
+                    dL_da *= T;
+                    last_alpha = a;
+                    dL_da += (-T_final / (1.f - a)) * bg_dot;
+                    const float dL_dG = co.w * dL_da;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                    const float dG_ddely = -gdy * co.z - gdx * co.y;
+                    va[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    va[1] = dL_dG * dG_ddely * ddely_dy;
+                    va[2] = -0.5f * gdx * dx * dL_dG;
+                    va[3] = -0.5f * gdx * dy * dL_dG;
+                    va[4] = -0.5f * gdy * dy * dL_dG;
+                    va[5] = G * dL_da;
+                    va[6] = w * dC0;
+                    va[7] = w * dC1;
+                    vb[0] = w * dC2;
+                    vb[1] = w * dD;
+                }
+                float A, Bv;
+                warp_reduce_10(va, vb, lane, A, Bv);
+                float* row = s_acc + j * kGradRow;
+                if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), A);
+                if ((lane & 15) == 1) atomicAdd(row + 8 + (lane >> 4), Bv);
             }
-            float A, Bv;
-            warp_reduce_10(va, vb, lane, A, Bv);
-            float* row = s_acc + j * kGradRow;
-            if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), A);
-            if ((lane & 15) == 1) atomicAdd(row + 8 + (lane >> 4), Bv);
         }
         __syncthreads();
         // flush: one thread per staged Gaussian, three 16-byte vector reductions into its gradient row

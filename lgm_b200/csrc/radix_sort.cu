@@ -4,106 +4,138 @@
 //
 // Structure (Adinets & Merrill "Onesweep", restated from the published algorithm, written from scratch):
 //   1. one histogram kernel reads the keys once and builds the digit histograms of every pass;
-//   2. per pass one kernel: a tile of 4096 pairs per CTA, dynamic tile ids (atomic ticket) so a CTA only ever waits
+//   2. per pass one kernel: a tile of pairs per CTA, dynamic tile ids (atomic ticket) so a CTA only ever waits
 //      on CTAs that started before it; in-CTA ranking with warp match.any multisplit (stable), chained-scan
 //      decoupled look-back across tiles per digit (flag+count packed in one 32-bit word, so no fences), staging
 //      through shared memory so that global writes are contiguous per digit run.
 // HBM traffic per pass = 12 B read + 12 B write per pair (+ 8 B per pair once for the histogram): the
 // B_sort = n_pass*24*L + 8*L of SURVEY.md §8d.  No tensor cores: integer/byte work, HBM-bound.
+//
+// "Compressed" keys: the renderer's keys carry a float depth > 0 in bits [0,32), so bit 31 is always 0.  With
+// compress = 1 the digits are taken from ck = key[30:0] | key[63:32] << 31 (computed on the fly; the stored key is
+// untouched), which saves a whole pass whenever 31 + tile bits <= 8 k < 32 + tile bits (e.g. 208 views x 400 tiles:
+// 48 bits -> 6 passes instead of 7).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace lgm {
 namespace {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItems = 16;                           // pairs per thread
-constexpr int kTileItems = kSortThreads * kItems;    // 4096 pairs per CTA
-constexpr int kWarpItems = kItems * 32;
 constexpr int kMaxPasses = 8;
+constexpr int kHistThreads = 256;
+constexpr int kHistItems = 8;
 
 constexpr uint32_t kFlagAgg = 1u << 30;   // tile aggregate available
 constexpr uint32_t kFlagInc = 2u << 30;   // inclusive prefix available
 constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kValMask = ~kFlagMask;
 
-__global__ void __launch_bounds__(kSortThreads)
-histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int end_bit, uint32_t* __restrict__ hist)
+__device__ __forceinline__ uint64_t sort_bits(uint64_t k, int compress)
+{
+    return compress ? ((k & 0x7fffffffull) | ((k >> 32) << 31)) : k;
+}
+
+// Digit histograms of all passes in one read of the keys.  Keys arrive in emit order, so the upper digits
+// (view, tile row, depth exponent) are usually identical across a warp: a warp-uniform digit costs two REDUX and one
+// shared-memory atomic; otherwise every lane adds 1 (distinct digits -> distinct banks, few conflicts).
+__global__ void __launch_bounds__(kHistThreads)
+histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int end_bit, int compress,
+                 uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
-    for (int i = threadIdx.x; i < n_pass * kRadix; i += kSortThreads) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < n_pass * kRadix; i += kHistThreads) s_hist[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // whole warps iterate together (match.any needs converged lanes); invalid lanes use an impossible marker
-    const uint32_t stride = gridDim.x * kSortThreads;
-    const uint32_t n_round = (n + stride - 1) / stride;
-    for (uint32_t r = 0; r < n_round; r++) {
-        const uint32_t i = r * stride + blockIdx.x * kSortThreads + threadIdx.x;
-        const bool valid = i < n;
-        const uint64_t k = valid ? keys[i] : 0ull;
-        for (int p = 0; p < n_pass; p++) {
-            // the last pass may cover fewer than 8 significant bits: bits at and above end_bit are ignored
-            const uint32_t dmask = (1u << min(kRadixBits, end_bit - p * kRadixBits)) - 1u;
-            const uint32_t d = valid ? (uint32_t)(k >> (p * kRadixBits)) & dmask : 0x100u + lane;
-            const uint32_t m = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == (__ffs(m) - 1)) atomicAdd(&s_hist[p * kRadix + d], (uint32_t)__popc(m));
+    const uint32_t chunk = kHistThreads * kHistItems;
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        uint64_t k[kHistItems];
+        bool ok[kHistItems];
+#pragma unroll
+        for (int j = 0; j < kHistItems; j++) {
+            const uint32_t i = c * chunk + j * kHistThreads + threadIdx.x;
+            ok[j] = i < n;
+            k[j] = ok[j] ? sort_bits(keys[i], compress) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < kHistItems; j++) {
+            const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, ok[j]));
+            if (nvalid == 0) continue;  // warp-uniform
+            for (int p = 0; p < n_pass; p++) {
+                // the last pass may cover fewer than 8 significant bits: bits at and above end_bit are ignored
+                const uint32_t dmask = (1u << min(kRadixBits, end_bit - p * kRadixBits)) - 1u;
+                const uint32_t d = (uint32_t)(k[j] >> (p * kRadixBits)) & dmask;
+                const uint32_t dmin = __reduce_min_sync(0xffffffffu, ok[j] ? d : 0xffffffffu);
+                const uint32_t dmax = __reduce_max_sync(0xffffffffu, ok[j] ? d : 0u);
+                if (dmin == dmax) {
+                    if (lane == 0) atomicAdd(&s_hist[p * kRadix + dmin], nvalid);
+                } else if (ok[j]) {
+                    atomicAdd(&s_hist[p * kRadix + d], 1u);
+                }
+            }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pass * kRadix; i += kSortThreads) {
+    for (int i = threadIdx.x; i < n_pass * kRadix; i += kHistThreads) {
         const uint32_t c = s_hist[i];
         if (c) atomicAdd(&hist[i], c);
     }
 }
 
+template <int THREADS, int ITEMS>
 struct OnesweepSmem {
+    static constexpr int kTileItems = THREADS * ITEMS;
+    static constexpr int kWarps = THREADS / 32;
     uint64_t keys[kTileItems];
     uint32_t vals[kTileItems];
-    uint32_t whist[kSortWarps * kRadix];  // per-warp digit counts, then per-warp exclusive offsets
-    uint32_t bin_start[kRadix];           // first slot of each digit inside the CTA's staged tile
-    uint32_t goff[kRadix];                // global destination of slot j of digit d = goff[d] + j   (mod 2^32)
-    uint32_t warp_tot[kSortWarps];
+    uint32_t whist[kWarps * kRadix];  // per-warp digit counts, then per-warp exclusive offsets
+    uint32_t bin_start[kRadix];       // first slot of each digit inside the CTA's staged tile
+    uint32_t goff[kRadix];            // global destination of slot j of digit d = goff[d] + j   (mod 2^32)
+    uint32_t warp_tot[8], warp_hist_tot[8];
     uint32_t tile;
 };
 
-__global__ void __launch_bounds__(kSortThreads, 2)
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                uint32_t dmask /* (1 << significant bits of this digit) - 1 */, const uint32_t* __restrict__ hist /*[256] of this pass*/, uint32_t* lookback /*[tiles][256], zeroed*/,
+                uint32_t dmask /* (1 << significant bits of this digit) - 1 */, int compress,
+                const uint32_t* __restrict__ hist /*[256] of this pass*/, uint32_t* lookback /*[tiles][256], zeroed*/,
                 uint32_t* ticket /*zeroed*/)
 {
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    constexpr int kTileItems = Smem::kTileItems;
+    constexpr int kWarps = Smem::kWarps;
+    constexpr int kWarpItems = ITEMS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
     if (t == 0) sm.tile = atomicAdd(ticket, 1u);
-    for (int i = t; i < kSortWarps * kRadix; i += kSortThreads) sm.whist[i] = 0;
+    for (int i = t; i < kWarps * kRadix; i += THREADS) sm.whist[i] = 0;
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint32_t base = tile * (uint32_t)kTileItems;
     const uint32_t n_valid = min((uint32_t)kTileItems, n - base);
 
-    // ---- load (warp-striped: item i of lane l of warp w = base + w*512 + i*32 + l); pads (all-ones keys) have the
-    // largest digit (dmask) in every pass and, being last in load order, rank after every real key of that digit ----
-    uint64_t k[kItems];
-    uint32_t v[kItems];
+    // ---- load (warp-striped: item i of lane l of warp w = base + w*ITEMS*32 + i*32 + l); pads (all-ones keys) have
+    // the largest digit (dmask) in every pass and, being last in load order, rank after every real key of that digit
+    uint64_t k[ITEMS];
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t loc = warp * kWarpItems + i * 32 + lane;
-        const bool ok = loc < n_valid;
-        k[i] = ok ? keys_in[base + loc] : ~0ull;
-        v[i] = ok ? vals_in[base + loc] : 0u;
+        k[i] = loc < n_valid ? keys_in[base + loc] : ~0ull;
     }
 
     // ---- rank inside the warp: stable in (item, lane) order ----
-    uint32_t rank[kItems];
+    uint32_t rank[ITEMS];
     uint32_t* wh = sm.whist + warp * kRadix;
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t d = (uint32_t)(k[i] >> shift) & dmask;
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
         const uint32_t m = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(m) - 1;
         uint32_t pre = 0;
@@ -117,64 +149,71 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     }
     __syncthreads();
 
-    // ---- thread d: exclusive prefix of digit d over the warps; CTA count of digit d ----
-    uint32_t cnt = 0;
+    // ---- threads 0..255: exclusive prefix of digit t over the warps; CTA count; look-back; offsets ----
+    if (t < kRadix) {
+        uint32_t cnt = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) {
-        const uint32_t c = sm.whist[w * kRadix + t];
-        sm.whist[w * kRadix + t] = cnt;
-        cnt += c;
-    }
-    const uint32_t cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
+        for (int w = 0; w < kWarps; w++) {
+            const uint32_t c = sm.whist[w * kRadix + t];
+            sm.whist[w * kRadix + t] = cnt;
+            cnt += c;
+        }
+        const uint32_t cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
+        // publish the aggregate as early as possible
+        volatile uint32_t* lb = lookback;
+        if (tile != 0) lb[(size_t)tile * kRadix + t] = kFlagAgg | cnt_valid;
 
-    // ---- publish the aggregate as early as possible, then the CTA-local scans ----
-    volatile uint32_t* lb = lookback;
-    if (tile != 0) lb[(size_t)tile * kRadix + t] = kFlagAgg | cnt_valid;
-
-    // exclusive scan over digits of (a) the CTA counts -> bin_start, (b) the global histogram -> global bin base
-    const uint32_t h = hist[t];
-    const uint32_t incl_c = warp_incl_scan(cnt, lane);
-    const uint32_t incl_h = warp_incl_scan(h, lane);
-    if (lane == 31) {
-        sm.warp_tot[warp] = incl_c;
-        sm.goff[warp] = incl_h;  // temporary use of goff[0..7] as warp totals of the histogram scan
-    }
-    __syncthreads();
-    uint32_t base_c = 0, base_h = 0;
+        // exclusive scan over digits of (a) the CTA counts -> bin_start, (b) the global histogram -> global bin base
+        const uint32_t h = hist[t];
+        const uint32_t incl_c = warp_incl_scan(cnt, lane);
+        const uint32_t incl_h = warp_incl_scan(h, lane);
+        if (lane == 31) {
+            sm.warp_tot[warp] = incl_c;
+            sm.warp_hist_tot[warp] = incl_h;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the first 8 warps only
+        uint32_t base_c = 0, base_h = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) {
-        if (w < warp) {
-            base_c += sm.warp_tot[w];
-            base_h += sm.goff[w];
+        for (int w = 0; w < kRadix / 32; w++) {
+            if (w < warp) {
+                base_c += sm.warp_tot[w];
+                base_h += sm.warp_hist_tot[w];
+            }
         }
-    }
-    const uint32_t bin_start = base_c + incl_c - cnt;
-    const uint32_t bin_global = base_h + incl_h - h;
-    __syncthreads();  // everyone has read goff[0..7] before it is overwritten below
-    sm.bin_start[t] = bin_start;
+        const uint32_t bin_start = base_c + incl_c - cnt;
+        const uint32_t bin_global = base_h + incl_h - h;
+        sm.bin_start[t] = bin_start;
 
-    // ---- decoupled look-back for digit t ----
-    uint32_t excl_prev = 0;
-    if (tile == 0) {
-        lb[t] = kFlagInc | cnt_valid;
-    } else {
-        int p = (int)tile - 1;
-        while (true) {
-            const uint32_t w = lb[(size_t)p * kRadix + t];
-            if ((w & kFlagMask) == 0) continue;  // predecessor has not published yet (it started before us)
-            excl_prev += w & kValMask;
-            if (w & kFlagInc) break;
-            p--;
+        // decoupled look-back for digit t
+        uint32_t excl_prev = 0;
+        if (tile == 0) {
+            lb[t] = kFlagInc | cnt_valid;
+        } else {
+            int p = (int)tile - 1;
+            while (true) {
+                const uint32_t w = lb[(size_t)p * kRadix + t];
+                if ((w & kFlagMask) == 0) continue;  // predecessor has not published yet (it started before us)
+                excl_prev += w & kValMask;
+                if (w & kFlagInc) break;
+                p--;
+            }
+            lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
         }
-        lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
+        sm.goff[t] = bin_global + excl_prev - bin_start;
     }
-    sm.goff[t] = bin_global + excl_prev - bin_start;
+    // values are loaded only now: their registers are not live during ranking / look-back
+    uint32_t v[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t loc = warp * kWarpItems + i * 32 + lane;
+        v[i] = loc < n_valid ? vals_in[base + loc] : 0u;
+    }
     __syncthreads();
 
     // ---- scatter into the staged tile (sorted by digit, stable) ----
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t d = (uint32_t)(k[i] >> shift) & dmask;
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
         const uint32_t pos = sm.bin_start[d] + wh[d] + rank[i];
         sm.keys[pos] = k[i];
         sm.vals[pos] = v[i];
@@ -183,16 +222,51 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
 
     // ---- write out: slot j -> goff[digit] + j ; consecutive slots of a digit are consecutive in global memory ----
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-        const uint32_t j = i * kSortThreads + t;
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t j = i * THREADS + t;
         if (j < n_valid) {
             const uint64_t key = sm.keys[j];
-            const uint32_t d = (uint32_t)(key >> shift) & dmask;
+            const uint32_t d = (uint32_t)(sort_bits(key, compress) >> shift) & dmask;
             const uint32_t dst = sm.goff[d] + j;
             keys_out[dst] = key;
             vals_out[dst] = sm.vals[j];
         }
     }
+}
+
+struct Variant {
+    int threads, items, min_blocks;
+};
+// Tunable launch shapes (LGM_SORT_VARIANT selects; default chosen from B200 measurements)
+constexpr Variant kVariants[] = {{256, 16, 2}, {512, 8, 2}, {256, 8, 4}, {384, 12, 2}, {512, 4, 3}, {1024, 4, 1}};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kDefaultVariant = 1;
+
+int variant_index()
+{
+    const char* e = getenv("LGM_SORT_VARIANT");
+    if (e) {
+        const int v = atoi(e);
+        if (v >= 0 && v < kNumVariants) return v;
+    }
+    return kDefaultVariant;
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+cudaError_t launch_pass(cudaStream_t stream, uint32_t tiles, const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
+                        uint32_t* vout, uint32_t n, int shift, uint32_t dmask, int compress, const uint32_t* hist,
+                        uint32_t* lookback, uint32_t* ticket)
+{
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<tiles, THREADS, sizeof(Smem), stream>>>(kin, vin, kout, vout, n, shift, dmask, compress, hist, lookback, ticket);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -202,24 +276,26 @@ int sort_num_passes(int end_bit) { return (end_bit + kRadixBits - 1) / kRadixBit
 bool sort_input_is_tmp(int end_bit) { return (sort_num_passes(end_bit) & 1) != 0; }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static uint32_t tile_items() { const Variant v = kVariants[variant_index()]; return (uint32_t)(v.threads * v.items); }
 
 size_t sort_scratch_bytes(uint32_t n, int end_bit)
 {
     const int np = sort_num_passes(end_bit);
-    const size_t tiles = (n + kTileItems - 1) / kTileItems;
+    const size_t tiles = (n + tile_items() - 1) / tile_items();
     // [hist: np*256 u32][tickets: np u32 (padded)][lookback: np * tiles * 256 u32]
     return align_up((size_t)np * kRadix * 4, 256) + 256 + (size_t)np * tiles * kRadix * 4;
 }
 
 cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp,
-                                 uint32_t* vals_tmp, uint32_t n, int end_bit, void* scratch, size_t scratch_bytes)
+                                 uint32_t* vals_tmp, uint32_t n, int end_bit, int compress, void* scratch,
+                                 size_t scratch_bytes)
 {
     const int np = sort_num_passes(end_bit);
     if (np > kMaxPasses || np < 1) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
     const size_t need = sort_scratch_bytes(n, end_bit);
     if (scratch_bytes < need) return cudaErrorInvalidValue;
-    const uint32_t tiles = (n + kTileItems - 1) / kTileItems;
+    const uint32_t tiles = (n + tile_items() - 1) / tile_items();
     unsigned char* sp = static_cast<unsigned char*>(scratch);
     uint32_t* hist = reinterpret_cast<uint32_t*>(sp);
     uint32_t* tickets = reinterpret_cast<uint32_t*>(sp + align_up((size_t)np * kRadix * 4, 256));
@@ -227,29 +303,36 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
     cudaError_t err = cudaMemsetAsync(scratch, 0, need, stream);
     if (err != cudaSuccess) return err;
 
-    uint64_t* kin = sort_input_is_tmp(end_bit) ? keys_tmp : keys_out;
-    uint32_t* vin = sort_input_is_tmp(end_bit) ? vals_tmp : vals_out;
-    uint64_t* kalt = sort_input_is_tmp(end_bit) ? keys_out : keys_tmp;
-    uint32_t* valt = sort_input_is_tmp(end_bit) ? vals_out : vals_tmp;
+    const bool in_tmp = sort_input_is_tmp(end_bit);
+    uint64_t* kin = in_tmp ? keys_tmp : keys_out;
+    uint32_t* vin = in_tmp ? vals_tmp : vals_out;
+    uint64_t* kalt = in_tmp ? keys_out : keys_tmp;
+    uint32_t* valt = in_tmp ? vals_out : vals_tmp;
 
-    const int hist_grid = (int)min((size_t)148 * 8, (size_t)(n + kSortThreads * 8 - 1) / (kSortThreads * 8));
-    histogram_kernel<<<hist_grid, kSortThreads, 0, stream>>>(kin, n, np, end_bit, hist);
+    const uint32_t chunk = kHistThreads * kHistItems;
+    const int hist_grid = (int)min((size_t)148 * 8, (size_t)(n + chunk - 1) / chunk);
+    histogram_kernel<<<hist_grid, kHistThreads, 0, stream>>>(kin, n, np, end_bit, compress, hist);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        err = cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem));
-        if (err != cudaSuccess) return err;
-        attr_set = true;
-    }
+    const int vi = variant_index();
     for (int p = 0; p < np; p++) {
-        onesweep_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), stream>>>(
-            kin, vin, kalt, valt, n, p * kRadixBits, (1u << (end_bit - p * kRadixBits < kRadixBits ? end_bit - p * kRadixBits : kRadixBits)) - 1u,
-            hist + p * kRadix, lookback + (size_t)p * tiles * kRadix, tickets + p);
-        err = cudaGetLastError();
+        const int shift = p * kRadixBits;
+        const int sig = end_bit - shift < kRadixBits ? end_bit - shift : kRadixBits;
+        const uint32_t dmask = (1u << sig) - 1u;
+        const uint32_t* h = hist + p * kRadix;
+        uint32_t* lb = lookback + (size_t)p * tiles * kRadix;
+        uint32_t* tk = tickets + p;
+        switch (vi) {
+            case 0: err = launch_pass<256, 16, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            case 1: err = launch_pass<512, 8, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            case 2: err = launch_pass<256, 8, 4>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            case 3: err = launch_pass<384, 12, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            case 4: err = launch_pass<512, 4, 3>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            default: err = launch_pass<1024, 4, 1>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+        }
         if (err != cudaSuccess) return err;
-        uint64_t* tk = kin; kin = kalt; kalt = tk;
+        uint64_t* tk2 = kin; kin = kalt; kalt = tk2;
         uint32_t* tv = vin; vin = valt; valt = tv;
     }
     return cudaSuccess;

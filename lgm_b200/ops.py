@@ -143,8 +143,12 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
 
 
 def sort_passes(n_global_tiles):
-    bits = 32 + max(1, (max(n_global_tiles, 1) - 1).bit_length())
-    return (bits + 7) // 8
+    return (sort_end_bit(n_global_tiles) + 7) // 8
+
+
+def sort_end_bit(n_global_tiles):
+    """Sort bits of the renderer's compressed key: 31 depth bits + global-tile bits (api.cu key_end_bit)."""
+    return 31 + max(1, (max(n_global_tiles, 1) - 1).bit_length())
 
 
 class TooManyInstances(_lib.LgmError):

@@ -63,6 +63,7 @@ def test_size_queries_and_errors(lib):
     assert lib.lgm_mark_visible(None, 5, None, None, None) == -1
     assert lib.lgm_mark_visible(None, -1, None, None, None) == -2
     assert lib.lgm_mark_visible(None, 0, None, None, None) == 0
-    assert lib.lgm_sort_pairs(None, None, None, None, None, 5, 40, None, 0) == -1
+    assert lib.lgm_sort_pairs(None, None, None, None, None, 5, 40, 0, None, 0) == -1
+    assert lib.lgm_sort_pairs(None, None, None, None, None, 5, 64, 1, None, 0) == -5
     assert lib.lgm_forward_geom(None, ok, *([None] * 12)) == -1
     assert lib.lgm_backward_composite(None, ok, *([None] * 14)) == -1

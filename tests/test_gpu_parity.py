@@ -314,8 +314,10 @@ def _np_sort_reference(keys, end_bit):
 
 @pytest.mark.parametrize("n", [1, 31, 4095, 4096, 4097, 100_003, 3_000_001])
 @pytest.mark.parametrize("end_bit,dist", [(8, "uniform"), (41, "uniform"), (49, "tiles"), (64, "uniform"), (49, "equal"),
-                                          (48, "fewdistinct")])
+                                          (48, "fewdistinct"), (-48, "tiles"), (-45, "tiles")])
 def test_onesweep_sort_pairs(n, end_bit, dist):
+    compress = 1 if end_bit < 0 else 0   # negative: the renderer's compressed-key mode on |end_bit| bits
+    end_bit = abs(end_bit)
     from lgm_b200 import _lib
     L = _lib.lib()
     rng = np.random.RandomState(n % 1000 + end_bit)
@@ -327,7 +329,11 @@ def test_onesweep_sort_pairs(n, end_bit, dist):
         keys = np.full(n, 0x0001234512345678, np.uint64)
     else:
         keys = rng.randint(0, 5, n).astype(np.uint64) << np.uint64(40)
-    order = _np_sort_reference(keys, end_bit)
+    if compress:
+        ck = (keys & np.uint64(0x7fffffff)) | ((keys >> np.uint64(32)) << np.uint64(31))
+        order = _np_sort_reference(ck, end_bit)
+    else:
+        order = _np_sort_reference(keys, end_bit)
     in_tmp = bool(L.lgm_sort_input_is_tmp(end_bit))
     kin = torch.from_numpy(keys.view(np.int64)).to(DEV)
     vin = torch.arange(n, dtype=torch.int32, device=DEV)
@@ -337,7 +343,7 @@ def test_onesweep_sort_pairs(n, end_bit, dist):
     _lib.check(L.lgm_sort_workspace_bytes(n, end_bit, nb), "ws")
     ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
     _lib.check(L.lgm_sort_pairs(torch.cuda.current_stream().cuda_stream, _lib.ptr(k_out), _lib.ptr(v_out), _lib.ptr(k_tmp),
-                                _lib.ptr(v_tmp), n, end_bit, _lib.ptr(ws), nb.value), "lgm_sort_pairs")
+                                _lib.ptr(v_tmp), n, end_bit, compress, _lib.ptr(ws), nb.value), "lgm_sort_pairs")
     torch.cuda.synchronize()
     assert np.array_equal(v_out.cpu().numpy().view(np.uint32), order.astype(np.uint32)), "order differs from a stable sort"
     assert np.array_equal(k_out.cpu().numpy().view(np.uint64), keys[order])
