@@ -4,10 +4,11 @@
 // is rendered by ONE launch (grid = views x tiles).
 //
 // Work skipping that cannot change a result: while a batch of Gaussians is staged in shared memory, the staging
-// thread also derives a conservative screen-space box outside of which alpha = min(0.99, o * exp(power)) is
-// certainly < 1/255 (the reference's skip threshold).  Each warp owns an 8x4 pixel patch; one ballot per 32 staged
-// Gaussians selects those whose box meets the patch, and only these are evaluated — with the reference's exact,
-// pinned per-pair arithmetic (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
+// thread also derives a conservative bound t2 such that alpha = min(0.99, o * exp(power)) >= 1/255 (the reference's
+// skip threshold) is only possible where the conic's quadratic form is <= t2.  Each warp owns an 8x4 pixel patch;
+// per 32 staged Gaussians the lanes test one Gaussian each (exact ellipse-vs-rectangle minimum), a ballot selects
+// those that can reach the patch, and only these are evaluated — with the reference's exact, pinned per-pair
+// arithmetic (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
 //
 // Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / atomics in the backward).
 #include "common.cuh"
@@ -16,8 +17,8 @@
 namespace lgm {
 namespace {
 
-constexpr float kBoxScale = 1.002f;  // safety margins of the alpha >= 1/255 box (fp32 rounding of power / expf / logf)
-constexpr float kBoxPad = 0.02f;     // pixels
+constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
+constexpr float kCullPad = 2e-3f;
 
 // A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store).
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
@@ -27,26 +28,36 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
     py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
 }
 
-// Half extents (hx, hy) of the axis-aligned box around the Gaussian's centre that contains every point with
-// o * exp(power) >= 1/255, i.e. 0.5 * d^T Q d <= tau = ln(255 o), Q = [[cx, cy], [cy, cz]]:
-//   |dx| <= sqrt(2 tau cz / det Q),  |dy| <= sqrt(2 tau cx / det Q).
-// 255 o <= 1: never visible (negative extents fail every test).  Q not positive definite (or NaN): the region is
-// unbounded, keep the pair everywhere (huge extents).
-__device__ __forceinline__ float2 alpha_box(const float4 co)
+// Staged Gaussian: p0 = (px, py, cx, cy), p1 = (cz, opacity, t2, -).
+// alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. q(d) = cx dx^2 + 2 cy dx dy + cz dy^2
+// <= 2 ln(255 o).  t2 is that bound with safety margins; t2 < 0: never visible (255 o <= 1); t2 = +inf: the conic is
+// not positive definite (or NaN) — the visible region is unbounded, keep the pair everywhere.
+__device__ __forceinline__ float cull_bound(const float4 co)
 {
     const float k = 255.0f * co.w;
-    if (k <= 1.0f) return make_float2(-1.0f, -1.0f);
+    if (k <= 1.0f) return -1.0f;
     const float det = co.x * co.z - co.y * co.y;
-    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return make_float2(1e30f, 1e30f);
-    const float t2 = 2.0f * __logf(k) * kBoxScale + 1e-3f;
-    const float inv = 1.0f / det;
-    return make_float2(sqrtf(t2 * co.z * inv) * kBoxScale + kBoxPad, sqrtf(t2 * co.x * inv) * kBoxScale + kBoxPad);
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return __int_as_float(0x7f800000);
+    return 2.0f * __logf(k) * kCullScale + kCullPad;
 }
 
-// patch = (X0, X1, Y0, Y1) pixel-centre bounds of the warp; NaNs compare false -> "hit"
-__device__ __forceinline__ bool box_hits_patch(const float4 p /*px,py,hx,hy*/, float X0, float X1, float Y0, float Y1)
+// Does the ellipse q(d) <= t2 around the Gaussian centre reach the warp's patch?  Exact minimum of the convex
+// quadratic over the rectangle d in [ax,bx] x [ay,by] (d = centre - pixel): zero if the centre is inside, otherwise
+// attained on a face that looks at the centre.  Conservative: the margins in t2 dominate the rounding here.
+__device__ __forceinline__ bool ellipse_hits_patch(const float4 p0, const float4 p1, float X0, float X1, float Y0, float Y1)
 {
-    return !(p.x + p.z < X0) && !(p.x - p.z > X1) && !(p.y + p.w < Y0) && !(p.y - p.w > Y1);
+    const float t2 = p1.z;
+    if (t2 < 0.0f) return false;
+    const float cx = p0.z, cy = p0.w, cz = p1.x;
+    const float ax = p0.x - X1, bx = p0.x - X0, ay = p0.y - Y1, by = p0.y - Y0;  // d ranges over [ax,bx] x [ay,by]
+    const float dxc = fminf(fmaxf(0.0f, ax), bx), dyc = fminf(fmaxf(0.0f, ay), by);
+    // face x = dxc: best y is -cy dxc / cz clamped;  face y = dyc: best x is -cy dyc / cx clamped
+    const float y1 = fminf(fmaxf(__fdividef(-cy * dxc, cz), ay), by);
+    const float x2 = fminf(fmaxf(__fdividef(-cy * dyc, cx), ax), bx);
+    const float q1 = cx * dxc * dxc + 2.0f * cy * dxc * y1 + cz * y1 * y1;
+    const float q2 = cx * x2 * x2 + 2.0f * cy * x2 * dyc + cz * dyc * dyc;
+    const float q = (dxc == 0.0f && dyc == 0.0f) ? 0.0f : fminf(dxc != 0.0f ? q1 : q2, dyc != 0.0f ? q2 : q1);
+    return !(q > t2);  // NaN -> hit
 }
 
 __global__ void __launch_bounds__(kBlock, 4)
@@ -56,8 +67,8 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const uint2* __restrict__ ranges, const float* __restrict__ bg, float* __restrict__ image,
                      float* __restrict__ alpha_img, float* __restrict__ depth_img, uint32_t* __restrict__ n_contrib)
 {
-    __shared__ float4 s_pos[kBlock];   // px, py, hx, hy
-    __shared__ float4 s_co[kBlock];    // conic xx, xy, yy, opacity
+    __shared__ float4 s_p0[kBlock];    // px, py, conic xx, conic xy
+    __shared__ float4 s_p1[kBlock];    // conic yy, opacity, cull bound t2, -
     __shared__ float4 s_rgbd[kBlock];  // r, g, b, depth
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -90,9 +101,8 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
             const uint32_t g = vals[range.x + k];
             const float2 p = xy[g];
             const float4 co = conic_opacity[g];
-            const float2 h = alpha_box(co);
-            s_pos[threadIdx.x] = make_float4(p.x, p.y, h.x, h.y);
-            s_co[threadIdx.x] = co;
+            s_p0[threadIdx.x] = make_float4(p.x, p.y, co.x, co.y);
+            s_p1[threadIdx.x] = make_float4(co.z, co.w, cull_bound(co), 0.0f);
             const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
             s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
         }
@@ -102,18 +112,18 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
             if (__all_sync(0xffffffffu, done)) break;  // every pixel of the patch is saturated (or outside)
             const int jl = base + lane;
             bool hit = false;
-            if (jl < nb) hit = box_hits_patch(s_pos[jl], X0, X1, Y0, Y1);
+            if (jl < nb) hit = ellipse_hits_patch(s_p0[jl], s_p1[jl], X0, X1, Y0, Y1);
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
                 if (done) continue;
-                const float4 p = s_pos[j];
-                const float4 co = s_co[j];
-                const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
-                const float power = pair_power(co.x, co.y, co.z, dx, dy);
+                const float4 p0 = s_p0[j];
+                const float4 p1 = s_p1[j];
+                const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
+                const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);
                 if (power > 0.0f) continue;
-                const float a = fminf(kAlphaMax, LGM_MUL(co.w, expf(power)));
+                const float a = fminf(kAlphaMax, LGM_MUL(p1.y, expf(power)));
                 if (a < kAlphaMin) continue;
                 const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
                 if (test_T < kTEps) {
@@ -186,8 +196,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
 {
-    __shared__ float4 s_pos[kBlock];
-    __shared__ float4 s_co[kBlock];
+    __shared__ float4 s_p0[kBlock];
+    __shared__ float4 s_p1[kBlock];
     __shared__ float4 s_rgbd[kBlock];
     __shared__ uint32_t s_g[kBlock];
     __shared__ __align__(16) float s_acc[kBlock * kGradRow];
@@ -251,9 +261,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
             s_g[threadIdx.x] = g;
             const float2 p = xy[g];
             const float4 co = conic_opacity[g];
-            const float2 h = alpha_box(co);
-            s_pos[threadIdx.x] = make_float4(p.x, p.y, h.x, h.y);
-            s_co[threadIdx.x] = co;
+            s_p0[threadIdx.x] = make_float4(p.x, p.y, co.x, co.y);
+            s_p1[threadIdx.x] = make_float4(co.z, co.w, cull_bound(co), 0.0f);
             const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
             s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
         }
@@ -263,16 +272,18 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
             const int jl = base + lane;
             bool hit = false;
             // list position of slot jl is todo-1-(r*256+jl); positions >= wmax were never reached by this patch
-            if (jl < nb && (uint32_t)(todo - 1 - (r * kBlock + jl)) < wmax) hit = box_hits_patch(s_pos[jl], X0, X1, Y0, Y1);
+            if (jl < nb && (uint32_t)(todo - 1 - (r * kBlock + jl)) < wmax)
+                hit = ellipse_hits_patch(s_p0[jl], s_p1[jl], X0, X1, Y0, Y1);
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t pos = (uint32_t)(todo - 1 - (r * kBlock + j));
                 bool valid = pos < last_contributor;
-                const float4 p = s_pos[j];
-                const float4 co = s_co[j];
-                const float dx = LGM_SUB(p.x, pfx), dy = LGM_SUB(p.y, pfy);
+                const float4 p0 = s_p0[j];
+                const float4 p1 = s_p1[j];
+                const float4 co = make_float4(p0.z, p0.w, p1.x, p1.y);
+                const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
                 const float power = pair_power(co.x, co.y, co.z, dx, dy);
                 valid = valid && !(power > 0.0f);
                 const float G = expf(power);

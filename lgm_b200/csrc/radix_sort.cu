@@ -97,7 +97,23 @@ struct OnesweepSmem {
     uint32_t tile;
 };
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+// lanes of the warp holding the same digit as this lane.  MATCH = the match.any instruction; otherwise one ballot per
+// digit bit (8 VOTEs + logic: more instructions, but no dependence on the long-latency MATCH unit).
+template <bool MATCH>
+__device__ __forceinline__ uint32_t peers_with_same_digit(uint32_t d)
+{
+    if (MATCH) return __match_any_sync(0xffffffffu, d);
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; b++) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
@@ -136,7 +152,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const uint32_t m = peers_with_same_digit<MATCH>(d);
         const int leader = __ffs(m) - 1;
         uint32_t pre = 0;
         if (lane == leader) {
@@ -236,9 +252,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
 
 struct Variant {
     int threads, items, min_blocks;
+    bool match;
 };
 // Tunable launch shapes (LGM_SORT_VARIANT selects; default chosen from B200 measurements)
-constexpr Variant kVariants[] = {{256, 16, 2}, {512, 8, 2}, {256, 8, 4}, {384, 12, 2}, {512, 4, 3}, {1024, 4, 1}};
+constexpr Variant kVariants[] = {{256, 16, 2, true}, {512, 8, 2, true},  {256, 8, 4, true},
+                                 {256, 16, 2, false}, {512, 8, 2, false}, {256, 8, 4, false}};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 1;
 
@@ -252,13 +270,13 @@ int variant_index()
     return kDefaultVariant;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH>
 cudaError_t launch_pass(cudaStream_t stream, uint32_t tiles, const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
                         uint32_t* vout, uint32_t n, int shift, uint32_t dmask, int compress, const uint32_t* hist,
                         uint32_t* lookback, uint32_t* ticket)
 {
     using Smem = OnesweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, MATCH>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
@@ -323,14 +341,16 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
         const uint32_t* h = hist + p * kRadix;
         uint32_t* lb = lookback + (size_t)p * tiles * kRadix;
         uint32_t* tk = tickets + p;
+#define LGM_PASS(T, I, B, M) launch_pass<T, I, B, M>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk)
         switch (vi) {
-            case 0: err = launch_pass<256, 16, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
-            case 1: err = launch_pass<512, 8, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
-            case 2: err = launch_pass<256, 8, 4>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
-            case 3: err = launch_pass<384, 12, 2>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
-            case 4: err = launch_pass<512, 4, 3>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
-            default: err = launch_pass<1024, 4, 1>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk); break;
+            case 0: err = LGM_PASS(256, 16, 2, true); break;
+            case 1: err = LGM_PASS(512, 8, 2, true); break;
+            case 2: err = LGM_PASS(256, 8, 4, true); break;
+            case 3: err = LGM_PASS(256, 16, 2, false); break;
+            case 4: err = LGM_PASS(512, 8, 2, false); break;
+            default: err = LGM_PASS(256, 8, 4, false); break;
         }
+#undef LGM_PASS
         if (err != cudaSuccess) return err;
         uint64_t* tk2 = kin; kin = kalt; kalt = tk2;
         uint32_t* tv = vin; vin = valt; valt = tv;
