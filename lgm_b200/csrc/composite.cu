@@ -1,24 +1,36 @@
 // composite.cu — K5 front-to-back alpha / depth / colour compositing per 16x16 tile, and K6 its backward
-// (back-to-front walk, warp-reduced gradients, shared-memory accumulation per staged Gaussian, vector atomics).
+// (back-to-front walk, warp-reduced gradients, vector-free fp32 reductions straight into the gradient rows).
 // Replaces renderCUDA fwd/bwd of the external rasterizer; every view of the step
 // is rendered by ONE launch (grid = views x tiles).
 //
-// Work skipping that cannot change a result: while a batch of Gaussians is staged in shared memory, the staging
-// thread also derives a conservative bound t2 such that alpha = min(0.99, o * exp(power)) >= 1/255 (the reference's
-// skip threshold) is only possible where the conic's quadratic form is <= t2.  Each warp owns an 8x4 pixel patch;
-// per 32 staged Gaussians the lanes test one Gaussian each (exact ellipse-vs-rectangle minimum), a ballot selects
-// those that can reach the patch, and only these are evaluated — with the reference's exact, pinned per-pair
-// arithmetic (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
+// Work skipping that cannot change a result: while Gaussians are staged in shared memory, the staging thread also
+// derives a conservative bound t2 such that alpha = min(0.99, o * exp(power)) >= 1/255 (the reference's skip
+// threshold) is only possible where the conic's quadratic form is <= t2.  Each warp owns an 8x4 pixel patch; per 32
+// staged Gaussians the lanes test one Gaussian each (exact ellipse-vs-rectangle minimum), a ballot selects those that
+// can reach the patch, and only these are evaluated — with the reference's exact, pinned per-pair arithmetic
+// (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
 //
-// Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / atomics in the backward).
+// Scheduling: after culling, the work of the 8 warps of a tile is very uneven, so block barriers are the enemy.  Up
+// to kBatch = 1024 Gaussians (48 KB of the SM's 227 KB shared memory) are staged per barrier — most tiles need exactly
+// one — and the warps then run independently to the end of the batch.
+//
+// Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / L2 reductions in the backward).
 #include "common.cuh"
 #include "splat_math.cuh"
 
 namespace lgm {
 namespace {
 
+constexpr int kBatch = 1024;          // Gaussians staged per block barrier
 constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
 constexpr float kCullPad = 2e-3f;
+
+struct __align__(16) Staged {
+    float4 p0;    // px, py, conic xx, conic xy
+    float4 p1;    // conic yy, opacity, cull bound t2, row index (view * P + idx) as bits
+    float4 rgbd;  // r, g, b, depth
+};
+static_assert(sizeof(Staged) == 48, "staged record is three 16-byte vectors");
 
 // A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store).
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
@@ -28,7 +40,6 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
     py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
 }
 
-// Staged Gaussian: p0 = (px, py, cx, cy), p1 = (cz, opacity, t2, -).
 // alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. q(d) = cx dx^2 + 2 cy dx dy + cz dy^2
 // <= 2 ln(255 o).  t2 is that bound with safety margins; t2 < 0: never visible (255 o <= 1); t2 = +inf: the conic is
 // not positive definite (or NaN) — the visible region is unbounded, keep the pair everywhere.
@@ -60,6 +71,19 @@ __device__ __forceinline__ bool ellipse_hits_patch(const float4 p0, const float4
     return !(q > t2);  // NaN -> hit
 }
 
+// Gather one instance (row g of the per-(view,Gaussian) arrays + its colour) into a staged record.
+__device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view_base, const float* __restrict__ scene_g,
+                                          const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                                          const float* __restrict__ depth)
+{
+    const float2 p = xy[g];
+    const float4 co = conic_opacity[g];
+    const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
+    dst.p0 = make_float4(p.x, p.y, co.x, co.y);
+    dst.p1 = make_float4(co.z, co.w, cull_bound(co), __uint_as_float(g));
+    dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
+}
+
 __global__ void __launch_bounds__(kBlock, 4)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -67,9 +91,8 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const uint2* __restrict__ ranges, const float* __restrict__ bg, float* __restrict__ image,
                      float* __restrict__ alpha_img, float* __restrict__ depth_img, uint32_t* __restrict__ n_contrib)
 {
-    __shared__ float4 s_p0[kBlock];    // px, py, conic xx, conic xy
-    __shared__ float4 s_p1[kBlock];    // conic yy, opacity, cull bound t2, -
-    __shared__ float4 s_rgbd[kBlock];  // r, g, b, depth
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gt = blockIdx.x;
@@ -86,7 +109,6 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
 
     const uint2 range = ranges[gt];
     const int todo = (int)(range.y - range.x);
-    const int rounds = (todo + kBlock - 1) / kBlock;
     const uint32_t view_base = (uint32_t)view * (uint32_t)prm.P;
     const float* scene_g = gaussians + (size_t)scene * prm.P * 14;
 
@@ -94,32 +116,24 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     uint32_t last = 0;
     bool done = !inside;
 
-    for (int r = 0; r < rounds; r++) {
-        if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffers
-        const int k = r * kBlock + threadIdx.x;
-        if (k < todo) {
-            const uint32_t g = vals[range.x + k];
-            const float2 p = xy[g];
-            const float4 co = conic_opacity[g];
-            s_p0[threadIdx.x] = make_float4(p.x, p.y, co.x, co.y);
-            s_p1[threadIdx.x] = make_float4(co.z, co.w, cull_bound(co), 0.0f);
-            const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
-            s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
-        }
+    for (int r0 = 0; r0 < todo; r0 += kBatch) {
+        if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffer
+        const int nb = min(kBatch, todo - r0);
+        for (int k = threadIdx.x; k < nb; k += kBlock)
+            stage_one(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth);
         __syncthreads();
-        const int nb = min(kBlock, todo - r * kBlock);
         for (int base = 0; base < nb; base += 32) {
             if (__all_sync(0xffffffffu, done)) break;  // every pixel of the patch is saturated (or outside)
             const int jl = base + lane;
             bool hit = false;
-            if (jl < nb) hit = ellipse_hits_patch(s_p0[jl], s_p1[jl], X0, X1, Y0, Y1);
+            if (jl < nb) hit = ellipse_hits_patch(s_rec[jl].p0, s_rec[jl].p1, X0, X1, Y0, Y1);
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
                 if (done) continue;
-                const float4 p0 = s_p0[j];
-                const float4 p1 = s_p1[j];
+                const float4 p0 = s_rec[j].p0;
+                const float4 p1 = s_rec[j].p1;
                 const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
                 const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);
                 if (power > 0.0f) continue;
@@ -130,14 +144,14 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     done = true;
                     continue;
                 }
-                const float4 cd = s_rgbd[j];
+                const float4 cd = s_rec[j].rgbd;
                 C0 = LGM_FMA(LGM_MUL(cd.x, a), T, C0);
                 C1 = LGM_FMA(LGM_MUL(cd.y, a), T, C1);
                 C2 = LGM_FMA(LGM_MUL(cd.z, a), T, C2);
                 Wt = LGM_FMA(a, T, Wt);
                 D = LGM_FMA(LGM_MUL(cd.w, a), T, D);
                 T = test_T;
-                last = (uint32_t)(r * kBlock + j + 1);  // 1-based position in the tile's list (A.4 "contributor")
+                last = (uint32_t)(r0 + j + 1);  // 1-based position in the tile's list (A.4 "contributor")
             }
         }
     }
@@ -196,11 +210,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
 {
-    __shared__ float4 s_p0[kBlock];
-    __shared__ float4 s_p1[kBlock];
-    __shared__ float4 s_rgbd[kBlock];
-    __shared__ uint32_t s_g[kBlock];
-    __shared__ __align__(16) float s_acc[kBlock * kGradRow];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
     __shared__ uint32_t s_max[kBlock / 32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,94 +245,88 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         dD = dL_ddepth_img[(size_t)view * hw + pix];
         dA = dL_dalpha_img[(size_t)view * hw + pix];
     }
-    const float bg_dot = __ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2;
+    const float bgT = -T_final * (__ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2);
 
     // Only list positions below the largest n_contrib of the tile (of the warp's patch) can contribute.
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) s_max[warp] = wmax;
-#pragma unroll
-    for (int k = 0; k < kGradRow; k++) s_acc[threadIdx.x * kGradRow + k] = 0.f;
     __syncthreads();
     uint32_t bmax = 0;
 #pragma unroll
     for (int w = 0; w < kBlock / 32; w++) bmax = max(bmax, s_max[w]);
     const int todo = (int)min(range.y - range.x, bmax);
-    const int rounds = (todo + kBlock - 1) / kBlock;
 
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_d = 0.f;
+    float last_alpha = 0.f, oml = 1.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_d = 0.f;  // oml = 1 - last_alpha
     const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
 
-    for (int r = 0; r < rounds; r++) {
-        __syncthreads();  // staging buffers and s_acc rows are free again
-        const int k = r * kBlock + threadIdx.x;
-        if (k < todo) {
-            const uint32_t g = vals[range.x + (uint32_t)(todo - 1 - k)];  // slot t holds list position todo-1-k
-            s_g[threadIdx.x] = g;
-            const float2 p = xy[g];
-            const float4 co = conic_opacity[g];
-            s_p0[threadIdx.x] = make_float4(p.x, p.y, co.x, co.y);
-            s_p1[threadIdx.x] = make_float4(co.z, co.w, cull_bound(co), 0.0f);
-            const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
-            s_rgbd[threadIdx.x] = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
-        }
+    for (int r0 = 0; r0 < todo; r0 += kBatch) {
+        __syncthreads();  // the staging buffer is free again
+        const int nb = min(kBatch, todo - r0);
+        // slot k holds list position todo-1-(r0+k): the walk is back to front
+        for (int k = threadIdx.x; k < nb; k += kBlock)
+            stage_one(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth);
         __syncthreads();
-        const int nb = min(kBlock, todo - r * kBlock);
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
             bool hit = false;
-            // list position of slot jl is todo-1-(r*256+jl); positions >= wmax were never reached by this patch
-            if (jl < nb && (uint32_t)(todo - 1 - (r * kBlock + jl)) < wmax)
-                hit = ellipse_hits_patch(s_p0[jl], s_p1[jl], X0, X1, Y0, Y1);
+            // positions >= wmax were never reached by this patch in the forward
+            if (jl < nb && (uint32_t)(todo - 1 - (r0 + jl)) < wmax)
+                hit = ellipse_hits_patch(s_rec[jl].p0, s_rec[jl].p1, X0, X1, Y0, Y1);
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
-                const uint32_t pos = (uint32_t)(todo - 1 - (r * kBlock + j));
-                bool valid = pos < last_contributor;
-                const float4 p0 = s_p0[j];
-                const float4 p1 = s_p1[j];
-                const float4 co = make_float4(p0.z, p0.w, p1.x, p1.y);
+                const uint32_t pos = (uint32_t)(todo - 1 - (r0 + j));
+                const float4 p0 = s_rec[j].p0;
+                const float4 p1 = s_rec[j].p1;
                 const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
-                const float power = pair_power(co.x, co.y, co.z, dx, dy);
-                valid = valid && !(power > 0.0f);
+                const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);  // the forward's pinned decisions
                 const float G = expf(power);
-                const float a = fminf(kAlphaMax, LGM_MUL(co.w, G));
-                valid = valid && !(a < kAlphaMin);
+                const float a = fminf(kAlphaMax, LGM_MUL(p1.y, G));
+                const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(a < kAlphaMin);
                 if (!__any_sync(0xffffffffu, valid)) continue;
 
-                float va[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vb[2] = {0.f, 0.f};
-                if (valid) {
-                    const float4 cd = s_rgbd[j];
-                    T = T / (1.f - a);
-                    const float w = a * T;
-                    float dL_da = 0.f;
-                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                    lc0 = cd.x; lc1 = cd.y; lc2 = cd.z;
-                    dL_da += (cd.x - acc0) * dC0;
-                    dL_da += (cd.y - acc1) * dC1;
-                    dL_da += (cd.z - acc2) * dC2;
-                    accD = last_alpha * last_d + (1.f - last_alpha) * accD;
-                    last_d = cd.w;
-                    dL_da += (cd.w - accD) * dD;
-                    accA = last_alpha + (1.f - last_alpha) * accA;
-                    dL_da += (1.f - accA) * dA;
-                    dL_da *= T;
-                    last_alpha = a;
-                    dL_da += (-T_final / (1.f - a)) * bg_dot;
-                    const float dL_dG = co.w * dL_da;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                    const float dG_ddely = -gdy * co.z - gdx * co.y;
+                float va[8], vb[2];
+                {
+                    // evaluated by every lane (no divergent region); invalid lanes contribute zeros and keep their state
+                    const float4 cd = s_rec[j].rgbd;
+                    const float rcp = __fdividef(1.0f, 1.0f - a);
+                    const float Tn = T * rcp;
+                    const float w = valid ? a * Tn : 0.0f;
+                    const float n0 = fmaf(last_alpha, lc0, oml * acc0);
+                    const float n1 = fmaf(last_alpha, lc1, oml * acc1);
+                    const float n2 = fmaf(last_alpha, lc2, oml * acc2);
+                    const float nD = fmaf(last_alpha, last_d, oml * accD);
+                    const float nA = fmaf(oml, accA, last_alpha);
+                    float dL_da = (cd.x - n0) * dC0;
+                    dL_da = fmaf(cd.y - n1, dC1, dL_da);
+                    dL_da = fmaf(cd.z - n2, dC2, dL_da);
+                    dL_da = fmaf(cd.w - nD, dD, dL_da);
+                    dL_da = fmaf(1.0f - nA, dA, dL_da);
+                    dL_da = fmaf(dL_da, Tn, bgT * rcp);
+                    dL_da = valid ? dL_da : 0.0f;
+                    if (valid) {
+                        T = Tn;
+                        acc0 = n0; acc1 = n1; acc2 = n2; accD = nD; accA = nA;
+                        lc0 = cd.x; lc1 = cd.y; lc2 = cd.z; last_d = cd.w;
+                        last_alpha = a;
+                        oml = 1.0f - a;
+                    }
+                    const float dL_dG = p1.y * dL_da;
+                    const float Gv = valid ? G : 0.0f;  // exp(power) of a skipped pair may be inf: keep 0 * inf out
+                    const float gdx = Gv * dx, gdy = Gv * dy;
+                    const float dG_ddelx = -gdx * p0.z - gdy * p0.w;
+                    const float dG_ddely = -gdy * p1.x - gdx * p0.w;
+                    const float h = -0.5f * dL_dG;
+                    const float hgx = h * gdx;
                     va[0] = dL_dG * dG_ddelx * ddelx_dx;
                     va[1] = dL_dG * dG_ddely * ddely_dy;
-                    va[2] = -0.5f * gdx * dx * dL_dG;
-                    va[3] = -0.5f * gdx * dy * dL_dG;
-                    va[4] = -0.5f * gdy * dy * dL_dG;
-                    va[5] = G * dL_da;
+                    va[2] = hgx * dx;
+                    va[3] = hgx * dy;
+                    va[4] = h * gdy * dy;
+                    va[5] = Gv * dL_da;
                     va[6] = w * dC0;
                     va[7] = w * dC1;
                     vb[0] = w * dC2;
@@ -329,26 +334,10 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 }
                 float A, Bv;
                 warp_reduce_10(va, vb, lane, A, Bv);
-                float* row = s_acc + j * kGradRow;
+                // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
+                float* row = grad_rows + (size_t)__float_as_uint(p1.w) * kGradRow;
                 if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), A);
                 if ((lane & 15) == 1) atomicAdd(row + 8 + (lane >> 4), Bv);
-            }
-        }
-        __syncthreads();
-        // flush: one thread per staged Gaussian, three 16-byte vector reductions into its gradient row
-        if ((int)threadIdx.x < nb) {
-            float4* row = reinterpret_cast<float4*>(s_acc + threadIdx.x * kGradRow);
-            const float4 q0 = row[0], q1 = row[1], q2 = row[2];
-            const bool nz = (q0.x != 0.f) | (q0.y != 0.f) | (q0.z != 0.f) | (q0.w != 0.f) | (q1.x != 0.f) | (q1.y != 0.f) |
-                            (q1.z != 0.f) | (q1.w != 0.f) | (q2.x != 0.f) | (q2.y != 0.f);
-            if (nz) {
-                float4* dst = reinterpret_cast<float4*>(grad_rows + (size_t)s_g[threadIdx.x] * kGradRow);
-                atomicAdd(dst, q0);
-                atomicAdd(dst + 1, q1);
-                atomicAdd(dst + 2, q2);
-                row[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                row[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                row[2] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
@@ -363,8 +352,15 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    composite_fwd_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                  ranges, bg, image, alpha, depth_img, n_contrib);
+    const int smem = kBatch * (int)sizeof(Staged);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    composite_fwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
+                                                                     vals, ranges, bg, image, alpha, depth_img, n_contrib);
     return cudaGetLastError();
 }
 
@@ -376,9 +372,16 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    composite_bwd_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                  ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth,
-                                                                  grad_rows);
+    const int smem = kBatch * (int)sizeof(Staged);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    composite_bwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
+                                                                     vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
+                                                                     dL_ddepth, grad_rows);
     return cudaGetLastError();
 }
 
