@@ -131,27 +131,28 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
             while (m) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
-                if (done) continue;
                 const float4 p0 = s_rec[j].p0;
                 const float4 p1 = s_rec[j].p1;
                 const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
                 const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);
-                if (power > 0.0f) continue;
                 const float a = fminf(kAlphaMax, LGM_MUL(p1.y, expf(power)));
-                if (a < kAlphaMin) continue;
                 const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
-                if (test_T < kTEps) {
-                    done = true;
-                    continue;
-                }
+                // A.4 in predicate form: skip if power > 0 or alpha < 1/255; stop (without compositing) if T would
+                // fall below 1e-4; otherwise composite.  Lanes that do not composite add exact zeros.
+                const bool cand = !done && !(power > 0.0f) && !(a < kAlphaMin);
+                const bool stop = cand && (test_T < kTEps);
+                const bool comp = cand && !stop;
+                done = done || stop;
+                if (!__any_sync(0xffffffffu, comp)) continue;
                 const float4 cd = s_rec[j].rgbd;
-                C0 = LGM_FMA(LGM_MUL(cd.x, a), T, C0);
-                C1 = LGM_FMA(LGM_MUL(cd.y, a), T, C1);
-                C2 = LGM_FMA(LGM_MUL(cd.z, a), T, C2);
-                Wt = LGM_FMA(a, T, Wt);
-                D = LGM_FMA(LGM_MUL(cd.w, a), T, D);
-                T = test_T;
-                last = (uint32_t)(r0 + j + 1);  // 1-based position in the tile's list (A.4 "contributor")
+                const float ae = comp ? a : 0.0f;
+                C0 = LGM_FMA(LGM_MUL(cd.x, ae), T, C0);
+                C1 = LGM_FMA(LGM_MUL(cd.y, ae), T, C1);
+                C2 = LGM_FMA(LGM_MUL(cd.z, ae), T, C2);
+                Wt = LGM_FMA(ae, T, Wt);
+                D = LGM_FMA(LGM_MUL(cd.w, ae), T, D);
+                T = comp ? test_T : T;
+                last = comp ? (uint32_t)(r0 + j + 1) : last;  // 1-based position in the tile's list (A.4 "contributor")
             }
         }
     }
@@ -257,8 +258,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const int todo = (int)min(range.y - range.x, bmax);
 
     float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
-    float last_alpha = 0.f, oml = 1.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_d = 0.f;  // oml = 1 - last_alpha
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;  // colour / depth / alpha behind the current Gaussian
     const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
 
     for (int r0 = 0; r0 < todo; r0 += kBatch) {
@@ -290,32 +290,29 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
 
                 float va[8], vb[2];
                 {
-                    // evaluated by every lane (no divergent region); invalid lanes contribute zeros and keep their state
+                    // Evaluated by every lane, no divergent region: a lane that does not contribute runs with
+                    // alpha = 0 and G = 0, which leaves its running state untouched and makes its ten terms exact zeros.
+                    // "Colour behind" recursions in eager form: after a contributor (a, c),  acc <- acc + a (c - acc)
+                    // ( = a c + (1 - a) acc, A.5), likewise depth and alpha; T <- T / (1 - a).
                     const float4 cd = s_rec[j].rgbd;
-                    const float rcp = __fdividef(1.0f, 1.0f - a);
-                    const float Tn = T * rcp;
-                    const float w = valid ? a * Tn : 0.0f;
-                    const float n0 = fmaf(last_alpha, lc0, oml * acc0);
-                    const float n1 = fmaf(last_alpha, lc1, oml * acc1);
-                    const float n2 = fmaf(last_alpha, lc2, oml * acc2);
-                    const float nD = fmaf(last_alpha, last_d, oml * accD);
-                    const float nA = fmaf(oml, accA, last_alpha);
-                    float dL_da = (cd.x - n0) * dC0;
-                    dL_da = fmaf(cd.y - n1, dC1, dL_da);
-                    dL_da = fmaf(cd.z - n2, dC2, dL_da);
-                    dL_da = fmaf(cd.w - nD, dD, dL_da);
-                    dL_da = fmaf(1.0f - nA, dA, dL_da);
-                    dL_da = fmaf(dL_da, Tn, bgT * rcp);
-                    dL_da = valid ? dL_da : 0.0f;
-                    if (valid) {
-                        T = Tn;
-                        acc0 = n0; acc1 = n1; acc2 = n2; accD = nD; accA = nA;
-                        lc0 = cd.x; lc1 = cd.y; lc2 = cd.z; last_d = cd.w;
-                        last_alpha = a;
-                        oml = 1.0f - a;
-                    }
+                    const float ae = valid ? a : 0.0f;
+                    const float Gv = valid ? G : 0.0f;
+                    const float rcp = __fdividef(1.0f, 1.0f - ae);
+                    T *= rcp;
+                    const float w = ae * T;
+                    const float e0 = cd.x - acc0, e1 = cd.y - acc1, e2 = cd.z - acc2, eD = cd.w - accD, eA = 1.0f - accA;
+                    float dL_da = e0 * dC0;
+                    dL_da = fmaf(e1, dC1, dL_da);
+                    dL_da = fmaf(e2, dC2, dL_da);
+                    dL_da = fmaf(eD, dD, dL_da);
+                    dL_da = fmaf(eA, dA, dL_da);
+                    dL_da = fmaf(dL_da, T, bgT * rcp);
+                    acc0 = fmaf(ae, e0, acc0);
+                    acc1 = fmaf(ae, e1, acc1);
+                    acc2 = fmaf(ae, e2, acc2);
+                    accD = fmaf(ae, eD, accD);
+                    accA = fmaf(ae, eA, accA);
                     const float dL_dG = p1.y * dL_da;
-                    const float Gv = valid ? G : 0.0f;  // exp(power) of a skipped pair may be inf: keep 0 * inf out
                     const float gdx = Gv * dx, gdy = Gv * dy;
                     const float dG_ddelx = -gdx * p0.z - gdy * p0.w;
                     const float dG_ddely = -gdy * p1.x - gdx * p0.w;
