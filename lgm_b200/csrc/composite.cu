@@ -260,6 +260,10 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;  // colour / depth / alpha behind the current Gaussian
     const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
+    // which of the ten reduced sums this lane sends to the gradient row (warp_reduce_10): lanes 0,4,..,28 hold the
+    // eight "a" sums (slots 0..7), lanes 1 and 17 the two "b" sums (slots 8, 9); other lanes send nothing
+    const bool red_is_b = (lane & 15) == 1;
+    const int red_slot = (lane & 3) == 0 ? (lane >> 2) : (red_is_b ? 8 + (lane >> 4) : -1);
 
     for (int r0 = 0; r0 < todo; r0 += kBatch) {
         __syncthreads();  // the staging buffer is free again
@@ -297,7 +301,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     const float4 cd = s_rec[j].rgbd;
                     const float ae = valid ? a : 0.0f;
                     const float Gv = valid ? G : 0.0f;
-                    const float rcp = __fdividef(1.0f, 1.0f - ae);
+                    float rcp;  // 1 / (1 - alpha), alpha <= 0.99: one MUFU.RCP (the backward is tolerance-checked)
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(1.0f - ae));
                     T *= rcp;
                     const float w = ae * T;
                     const float e0 = cd.x - acc0, e1 = cd.y - acc1, e2 = cd.z - acc2, eD = cd.w - accD, eA = 1.0f - accA;
@@ -332,9 +337,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 float A, Bv;
                 warp_reduce_10(va, vb, lane, A, Bv);
                 // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
-                float* row = grad_rows + (size_t)__float_as_uint(p1.w) * kGradRow;
-                if ((lane & 3) == 0) atomicAdd(row + (lane >> 2), A);
-                if ((lane & 15) == 1) atomicAdd(row + 8 + (lane >> 4), Bv);
+                if (red_slot >= 0)
+                    atomicAdd(grad_rows + (size_t)__float_as_uint(p1.w) * kGradRow + red_slot, red_is_b ? Bv : A);
             }
         }
     }

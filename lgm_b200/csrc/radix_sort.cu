@@ -63,16 +63,24 @@ histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int 
         for (int j = 0; j < kHistItems; j++) {
             const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, ok[j]));
             if (nvalid == 0) continue;  // warp-uniform
-            for (int p = 0; p < n_pass; p++) {
-                // the last pass may cover fewer than 8 significant bits: bits at and above end_bit are ignored
-                const uint32_t dmask = (1u << min(kRadixBits, end_bit - p * kRadixBits)) - 1u;
-                const uint32_t d = (uint32_t)(k[j] >> (p * kRadixBits)) & dmask;
-                const uint32_t dmin = __reduce_min_sync(0xffffffffu, ok[j] ? d : 0xffffffffu);
-                const uint32_t dmax = __reduce_max_sync(0xffffffffu, ok[j] ? d : 0u);
-                if (dmin == dmax) {
-                    if (lane == 0) atomicAdd(&s_hist[p * kRadix + dmin], nvalid);
+            // bits at and above end_bit are ignored (the last pass may cover fewer than 8 significant bits)
+            const uint64_t kk = end_bit < 64 ? (k[j] & ((1ull << end_bit) - 1ull)) : k[j];
+            // passes 0..2 (low mantissa bytes of the depth): digits differ across lanes, plain shared atomics
+            const int n_low = min(n_pass, 3);
+            if (ok[j])
+                for (int p = 0; p < n_low; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(kk >> (p * kRadixBits)) & 0xffu)], 1u);
+            if (n_pass > 3) {
+                // passes 3.. : one uniformity test (two REDUX each on the two 32-bit halves of the upper bits) covers them all
+                const uint64_t hi = kk >> 24;
+                const uint32_t h0 = (uint32_t)hi, h1 = (uint32_t)(hi >> 32);
+                const bool uni = __reduce_min_sync(0xffffffffu, ok[j] ? h0 : 0xffffffffu) == __reduce_max_sync(0xffffffffu, ok[j] ? h0 : 0u) &&
+                                 __reduce_min_sync(0xffffffffu, ok[j] ? h1 : 0xffffffffu) == __reduce_max_sync(0xffffffffu, ok[j] ? h1 : 0u);
+                const uint64_t hv = __shfl_sync(0xffffffffu, hi, __ffs(__ballot_sync(0xffffffffu, ok[j])) - 1);
+                if (uni) {
+                    if (lane == 0)
+                        for (int p = 3; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hv >> ((p - 3) * kRadixBits)) & 0xffu)], nvalid);
                 } else if (ok[j]) {
-                    atomicAdd(&s_hist[p * kRadix + d], 1u);
+                    for (int p = 3; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hi >> ((p - 3) * kRadixBits)) & 0xffu)], 1u);
                 }
             }
         }
