@@ -258,13 +258,181 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     }
 }
 
+// Persistent, software-pipelined form of the same pass: one CTA per resident slot loops over ticketed tiles and issues
+// the key loads of its NEXT tile before ranking the current one, so HBM reads stay in flight during ranking, look-back
+// and scatter (the one-tile-per-CTA form above keeps the memory system busy only ~1/4 of a CTA's life: measured 2.5 TB/s).
+// Dead-lock freedom is unchanged: a CTA works on its tickets in increasing order and a tile only ever waits on lower
+// tickets, each of which is held by a resident CTA that needs nothing from higher tickets.
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                           uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, uint32_t n_tiles,
+                           int shift, uint32_t dmask, int compress, const uint32_t* __restrict__ hist,
+                           uint32_t* lookback /*[tiles][256], zeroed*/, uint32_t* ticket /*zeroed*/)
+{
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    constexpr int kTileItems = Smem::kTileItems;
+    constexpr int kWarps = Smem::kWarps;
+    constexpr int kWarpItems = ITEMS * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ uint32_t s_next;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* wh = sm.whist + warp * kRadix;
+    volatile uint32_t* lb = lookback;
+
+    // global bin bases of this pass (exclusive scan of the histogram), kept in a register by threads 0..255
+    uint32_t bin_global = 0;
+    if (t == 0) sm.tile = atomicAdd(ticket, 1u);
+    if (t < kRadix) {
+        const uint32_t h = hist[t];
+        const uint32_t incl_h = warp_incl_scan(h, lane);
+        if (lane == 31) sm.warp_hist_tot[warp] = incl_h;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint32_t base_h = 0;
+#pragma unroll
+        for (int w = 0; w < kRadix / 32; w++)
+            if (w < warp) base_h += sm.warp_hist_tot[w];
+        bin_global = base_h + incl_h - h;
+    }
+    __syncthreads();
+    uint32_t tile = sm.tile;
+
+    uint64_t kn[ITEMS];  // keys of the tile this CTA will process next (in flight)
+    if (tile < n_tiles) {
+        const uint32_t base = tile * (uint32_t)kTileItems;
+        const uint32_t n_valid = min((uint32_t)kTileItems, n - base);
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t loc = warp * kWarpItems + i * 32 + lane;
+            kn[i] = loc < n_valid ? keys_in[base + loc] : ~0ull;
+        }
+    }
+
+    while (tile < n_tiles) {
+        const uint32_t base = tile * (uint32_t)kTileItems;
+        const uint32_t n_valid = min((uint32_t)kTileItems, n - base);
+        uint64_t k[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) k[i] = kn[i];
+
+        __syncthreads();  // everyone is done with the previous tile's shared state
+        uint32_t my_next = 0;
+        if (t == 0) my_next = atomicAdd(ticket, 1u);  // stays in a register: the round trip overlaps the ranking
+        for (int i = t; i < kWarps * kRadix; i += THREADS) sm.whist[i] = 0;
+        __syncthreads();
+
+        // values of this tile: needed only at the scatter
+        uint32_t v[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t loc = warp * kWarpItems + i * 32 + lane;
+            v[i] = loc < n_valid ? vals_in[base + loc] : 0u;
+        }
+
+        // ---- rank inside the warp: stable in (item, lane) order ----
+        uint32_t rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
+            const uint32_t m = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(m) - 1;
+            uint32_t pre = 0;
+            if (lane == leader) {
+                pre = wh[d];
+                wh[d] = pre + (uint32_t)__popc(m);
+            }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            rank[i] = pre + (uint32_t)__popc(m & lt_mask);
+            __syncwarp();
+        }
+        if (t == 0) s_next = my_next;
+        __syncthreads();
+
+        // ---- prefetch the next tile's keys (ticket has arrived by now) ----
+        const uint32_t next = s_next;
+        if (next < n_tiles) {
+            const uint32_t nbase = next * (uint32_t)kTileItems;
+            const uint32_t nn = min((uint32_t)kTileItems, n - nbase);
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const uint32_t loc = warp * kWarpItems + i * 32 + lane;
+                kn[i] = loc < nn ? keys_in[nbase + loc] : ~0ull;
+            }
+        }
+
+        // ---- threads 0..255: per-digit prefix over warps, CTA count, look-back, offsets ----
+        if (t < kRadix) {
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) {
+                const uint32_t c = sm.whist[w * kRadix + t];
+                sm.whist[w * kRadix + t] = cnt;
+                cnt += c;
+            }
+            const uint32_t cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
+            if (tile != 0) lb[(size_t)tile * kRadix + t] = kFlagAgg | cnt_valid;
+            const uint32_t incl_c = warp_incl_scan(cnt, lane);
+            if (lane == 31) sm.warp_tot[warp] = incl_c;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint32_t base_c = 0;
+#pragma unroll
+            for (int w = 0; w < kRadix / 32; w++)
+                if (w < warp) base_c += sm.warp_tot[w];
+            const uint32_t bin_start = base_c + incl_c - cnt;
+            sm.bin_start[t] = bin_start;
+            uint32_t excl_prev = 0;
+            if (tile == 0) {
+                lb[t] = kFlagInc | cnt_valid;
+            } else {
+                int p = (int)tile - 1;
+                while (true) {
+                    const uint32_t w = lb[(size_t)p * kRadix + t];
+                    if ((w & kFlagMask) == 0) continue;
+                    excl_prev += w & kValMask;
+                    if (w & kFlagInc) break;
+                    p--;
+                }
+                lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
+            }
+            sm.goff[t] = bin_global + excl_prev - bin_start;
+        }
+        __syncthreads();
+
+        // ---- scatter into the staged tile (sorted by digit, stable), then write out ----
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
+            const uint32_t pos = sm.bin_start[d] + wh[d] + rank[i];
+            sm.keys[pos] = k[i];
+            sm.vals[pos] = v[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const uint32_t j = i * THREADS + t;
+            if (j < n_valid) {
+                const uint64_t key = sm.keys[j];
+                const uint32_t d = (uint32_t)(sort_bits(key, compress) >> shift) & dmask;
+                const uint32_t dst = sm.goff[d] + j;
+                keys_out[dst] = key;
+                vals_out[dst] = sm.vals[j];
+            }
+        }
+        tile = next;
+    }
+}
+
 struct Variant {
     int threads, items, min_blocks;
-    bool match;
+    bool match, persistent;
 };
 // Tunable launch shapes (LGM_SORT_VARIANT selects; default chosen from B200 measurements)
-constexpr Variant kVariants[] = {{256, 16, 2, true}, {512, 8, 2, true},  {256, 8, 4, true},
-                                 {256, 16, 2, false}, {512, 8, 2, false}, {256, 8, 4, false}};
+constexpr Variant kVariants[] = {{256, 16, 2, true, false}, {512, 8, 2, true, false},  {256, 8, 4, true, false},
+                                 {256, 16, 2, false, false}, {512, 8, 2, false, false}, {256, 8, 4, false, false},
+                                 {384, 8, 2, true, true},   {512, 6, 2, true, true},   {256, 12, 3, true, true},
+                                 {384, 10, 2, true, true}};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 1;
 
@@ -292,6 +460,29 @@ cudaError_t launch_pass(cudaStream_t stream, uint32_t tiles, const uint64_t* kin
         attr_set = true;
     }
     kern<<<tiles, THREADS, sizeof(Smem), stream>>>(kin, vin, kout, vout, n, shift, dmask, compress, hist, lookback, ticket);
+    return cudaGetLastError();
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+cudaError_t launch_pass_persistent(cudaStream_t stream, uint32_t tiles, const uint64_t* kin, const uint32_t* vin,
+                                   uint64_t* kout, uint32_t* vout, uint32_t n, int shift, uint32_t dmask, int compress,
+                                   const uint32_t* hist, uint32_t* lookback, uint32_t* ticket)
+{
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    auto kern = onesweep_persistent_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    static int resident = 0;
+    if (!resident) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        resident = sms * (per_sm > 0 ? per_sm : 1);  // one CTA per resident slot: a multiple of the SM count (148)
+    }
+    const uint32_t grid = tiles < (uint32_t)resident ? tiles : (uint32_t)resident;
+    kern<<<grid, THREADS, sizeof(Smem), stream>>>(kin, vin, kout, vout, n, tiles, shift, dmask, compress, hist, lookback, ticket);
     return cudaGetLastError();
 }
 
@@ -356,7 +547,13 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
             case 2: err = LGM_PASS(256, 8, 4, true); break;
             case 3: err = LGM_PASS(256, 16, 2, false); break;
             case 4: err = LGM_PASS(512, 8, 2, false); break;
-            default: err = LGM_PASS(256, 8, 4, false); break;
+            case 5: err = LGM_PASS(256, 8, 4, false); break;
+#define LGM_PPASS(T, I, B) launch_pass_persistent<T, I, B>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk)
+            case 6: err = LGM_PPASS(384, 8, 2); break;
+            case 7: err = LGM_PPASS(512, 6, 2); break;
+            case 8: err = LGM_PPASS(256, 12, 3); break;
+            default: err = LGM_PPASS(384, 10, 2); break;
+#undef LGM_PPASS
         }
 #undef LGM_PASS
         if (err != cudaSuccess) return err;

@@ -388,3 +388,13 @@ def test_full_size_properties(cfg):
     assert bool(torch.isfinite(g1).all())
     scale = float(g1.abs().max())
     assert scale > 0 and float((g2 - 2 * g1).abs().max()) <= 1e-4 * 2 * scale
+
+
+@pytest.mark.parametrize("variant", list(range(10)))
+def test_onesweep_every_launch_shape(variant, monkeypatch):
+    """Every tunable launch shape of the sort (LGM_SORT_VARIANT: one-tile-per-CTA and persistent pipelined forms,
+    match.any and ballot ranking) sorts stably; n is not a multiple of any tile size and spans many tiles."""
+    monkeypatch.setenv("LGM_SORT_VARIANT", str(variant))
+    for n, end_bit, dist in ((1_000_003, -48, "tiles"), (4097, 64, "uniform"), (250_000, 49, "equal")):
+        test_onesweep_sort_pairs.__wrapped__(n, end_bit, dist) if hasattr(test_onesweep_sort_pairs, "__wrapped__") \
+            else test_onesweep_sort_pairs(n, end_bit, dist)
