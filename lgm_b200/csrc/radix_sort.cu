@@ -105,6 +105,33 @@ struct OnesweepSmem {
     uint32_t tile;
 };
 
+// Decoupled look-back for one digit: sum of the counts of tiles [0, tile) of digit t.  Walks back over the
+// predecessors' status words, adding aggregates until an inclusive prefix is met.  The walk is the latency chain of the
+// whole pass (hundreds of tiles are in flight and most have only their aggregate out), so kLookAhead status words are
+// fetched per round trip instead of one; a word that is not published yet is simply polled again.
+constexpr int kLookAhead = 8;
+__device__ __forceinline__ uint32_t lookback_exclusive(volatile uint32_t* lb, uint32_t tile, int t)
+{
+    uint32_t excl = 0;
+    int p = (int)tile - 1;
+    while (p >= 0) {
+        uint32_t w[kLookAhead];
+#pragma unroll
+        for (int u = 0; u < kLookAhead; u++) w[u] = (p - u >= 0) ? lb[(size_t)(p - u) * kRadix + t] : kFlagInc;
+        bool done = false;
+#pragma unroll
+        for (int u = 0; u < kLookAhead; u++) {
+            if (done) break;
+            if ((w[u] & kFlagMask) == 0) break;  // not published yet: poll again from this tile
+            excl += w[u] & kValMask;
+            p--;
+            if (w[u] & kFlagInc) done = true;
+        }
+        if (done) break;
+    }
+    return excl;
+}
+
 // lanes of the warp holding the same digit as this lane.  MATCH = the match.any instruction; otherwise one ballot per
 // digit bit (8 VOTEs + logic: more instructions, but no dependence on the long-latency MATCH unit).
 template <bool MATCH>
@@ -213,14 +240,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
         if (tile == 0) {
             lb[t] = kFlagInc | cnt_valid;
         } else {
-            int p = (int)tile - 1;
-            while (true) {
-                const uint32_t w = lb[(size_t)p * kRadix + t];
-                if ((w & kFlagMask) == 0) continue;  // predecessor has not published yet (it started before us)
-                excl_prev += w & kValMask;
-                if (w & kFlagInc) break;
-                p--;
-            }
+            excl_prev = lookback_exclusive(lb, tile, t);
             lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
         }
         sm.goff[t] = bin_global + excl_prev - bin_start;
@@ -386,14 +406,7 @@ onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, const uint32_t*
             if (tile == 0) {
                 lb[t] = kFlagInc | cnt_valid;
             } else {
-                int p = (int)tile - 1;
-                while (true) {
-                    const uint32_t w = lb[(size_t)p * kRadix + t];
-                    if ((w & kFlagMask) == 0) continue;
-                    excl_prev += w & kValMask;
-                    if (w & kFlagInc) break;
-                    p--;
-                }
+                excl_prev = lookback_exclusive(lb, tile, t);
                 lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
             }
             sm.goff[t] = bin_global + excl_prev - bin_start;
