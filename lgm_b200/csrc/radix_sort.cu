@@ -109,7 +109,7 @@ struct OnesweepSmem {
 // predecessors' status words, adding aggregates until an inclusive prefix is met.  The walk is the latency chain of the
 // whole pass (hundreds of tiles are in flight and most have only their aggregate out), so kLookAhead status words are
 // fetched per round trip instead of one; a word that is not published yet is simply polled again.
-constexpr int kLookAhead = 8;
+constexpr int kLookAhead = 16;
 __device__ __forceinline__ uint32_t lookback_exclusive(volatile uint32_t* lb, uint32_t tile, int t)
 {
     uint32_t excl = 0;
@@ -117,7 +117,10 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile uint32_t* lb, ui
     while (p >= 0) {
         uint32_t w[kLookAhead];
 #pragma unroll
-        for (int u = 0; u < kLookAhead; u++) w[u] = (p - u >= 0) ? lb[(size_t)(p - u) * kRadix + t] : kFlagInc;
+        for (int u = 0; u < kLookAhead; u++) {
+            w[u] = uint32_t(kFlagInc);  // before tile 0: an inclusive prefix of zero
+            if (p - u >= 0) w[u] = lb[(size_t)(p - u) * kRadix + t];
+        }
         bool done = false;
 #pragma unroll
         for (int u = 0; u < kLookAhead; u++) {
@@ -189,14 +192,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
         const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
         const uint32_t m = peers_with_same_digit<MATCH>(d);
         const int leader = __ffs(m) - 1;
+        // the group's leader reserves the group's slots with one shared-memory atomic (returns the digit's count over
+        // the warp's earlier items); atomics of one warp execute in program order, so the ITEMS rounds pipeline with
+        // no warp barrier between them
         uint32_t pre = 0;
-        if (lane == leader) {
-            pre = wh[d];
-            wh[d] = pre + (uint32_t)__popc(m);
-        }
+        if (lane == leader) pre = atomicAdd(&wh[d], (uint32_t)__popc(m));
         pre = __shfl_sync(0xffffffffu, pre, leader);
         rank[i] = pre + (uint32_t)__popc(m & lt_mask);
-        __syncwarp();
     }
     __syncthreads();
 
@@ -359,13 +361,9 @@ onesweep_persistent_kernel(const uint64_t* __restrict__ keys_in, const uint32_t*
             const uint32_t m = __match_any_sync(0xffffffffu, d);
             const int leader = __ffs(m) - 1;
             uint32_t pre = 0;
-            if (lane == leader) {
-                pre = wh[d];
-                wh[d] = pre + (uint32_t)__popc(m);
-            }
+            if (lane == leader) pre = atomicAdd(&wh[d], (uint32_t)__popc(m));
             pre = __shfl_sync(0xffffffffu, pre, leader);
             rank[i] = pre + (uint32_t)__popc(m & lt_mask);
-            __syncwarp();
         }
         if (t == 0) s_next = my_next;
         __syncthreads();
@@ -447,7 +445,7 @@ constexpr Variant kVariants[] = {{256, 16, 2, true, false}, {512, 8, 2, true, fa
                                  {384, 8, 2, true, true},   {512, 6, 2, true, true},   {256, 12, 3, true, true},
                                  {384, 10, 2, true, true}};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 1;
+constexpr int kDefaultVariant = 4;
 
 int variant_index()
 {
