@@ -109,28 +109,51 @@ struct OnesweepSmem {
 // predecessors' status words, adding aggregates until an inclusive prefix is met.  The walk is the latency chain of the
 // whole pass (hundreds of tiles are in flight and most have only their aggregate out), so kLookAhead status words are
 // fetched per round trip instead of one; a word that is not published yet is simply polled again.
-constexpr int kLookAhead = 16;
+constexpr int kLookAhead = 16;  // status words per round trip in the walk
+constexpr int kLookFirst = 8;   // status words of the first round trip, issued before the scatter
+template <int N>
+__device__ __forceinline__ void lookback_issue(volatile uint32_t* lb, int p, int t, uint32_t (&w)[N])
+{
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        w[u] = uint32_t(kFlagInc);  // before tile 0: an inclusive prefix of zero
+        if (p - u >= 0) w[u] = lb[(size_t)(p - u) * kRadix + t];
+    }
+}
+// consume status words of tiles p, p-1, ...: returns true when an inclusive prefix ended the walk; a word that is not
+// published yet stops the batch (that tile is polled again)
+template <int N>
+__device__ __forceinline__ bool lookback_consume(const uint32_t (&w)[N], int& p, uint32_t& excl)
+{
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        if ((w[u] & kFlagMask) == 0) return false;
+        excl += w[u] & kValMask;
+        p--;
+        if (w[u] & kFlagInc) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ uint32_t lookback_finish(volatile uint32_t* lb, uint32_t tile, int t, const uint32_t (&w0)[kLookFirst])
+{
+    uint32_t excl = 0;
+    int p = (int)tile - 1;
+    if (lookback_consume<kLookFirst>(w0, p, excl)) return excl;
+    while (p >= 0) {
+        uint32_t w[kLookAhead];
+        lookback_issue<kLookAhead>(lb, p, t, w);
+        if (lookback_consume<kLookAhead>(w, p, excl)) break;
+    }
+    return excl;
+}
 __device__ __forceinline__ uint32_t lookback_exclusive(volatile uint32_t* lb, uint32_t tile, int t)
 {
     uint32_t excl = 0;
     int p = (int)tile - 1;
     while (p >= 0) {
         uint32_t w[kLookAhead];
-#pragma unroll
-        for (int u = 0; u < kLookAhead; u++) {
-            w[u] = uint32_t(kFlagInc);  // before tile 0: an inclusive prefix of zero
-            if (p - u >= 0) w[u] = lb[(size_t)(p - u) * kRadix + t];
-        }
-        bool done = false;
-#pragma unroll
-        for (int u = 0; u < kLookAhead; u++) {
-            if (done) break;
-            if ((w[u] & kFlagMask) == 0) break;  // not published yet: poll again from this tile
-            excl += w[u] & kValMask;
-            p--;
-            if (w[u] & kFlagInc) done = true;
-        }
-        if (done) break;
+        lookback_issue<kLookAhead>(lb, p, t, w);
+        if (lookback_consume<kLookAhead>(w, p, excl)) break;
     }
     return excl;
 }
@@ -168,6 +191,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
     if (t == 0) sm.tile = atomicAdd(ticket, 1u);
+    const uint32_t h_digit = t < kRadix ? hist[t] : 0u;  // global count of digit t in this pass (needed after ranking)
     for (int i = t; i < kWarps * kRadix; i += THREADS) sm.whist[i] = 0;
     __syncthreads();
     const uint32_t tile = sm.tile;
@@ -202,7 +226,9 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     }
     __syncthreads();
 
-    // ---- threads 0..255: exclusive prefix of digit t over the warps; CTA count; look-back; offsets ----
+    // ---- threads 0..255: exclusive prefix of digit t over the warps; CTA count -> aggregate out; local bin scan ----
+    volatile uint32_t* lb = lookback;
+    uint32_t cnt_valid = 0, bin_start = 0, bin_global = 0;
     if (t < kRadix) {
         uint32_t cnt = 0;
 #pragma unroll
@@ -211,15 +237,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
             sm.whist[w * kRadix + t] = cnt;
             cnt += c;
         }
-        const uint32_t cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
+        cnt_valid = ((uint32_t)t == dmask) ? cnt - ((uint32_t)kTileItems - n_valid) : cnt;
         // publish the aggregate as early as possible
-        volatile uint32_t* lb = lookback;
         if (tile != 0) lb[(size_t)tile * kRadix + t] = kFlagAgg | cnt_valid;
 
         // exclusive scan over digits of (a) the CTA counts -> bin_start, (b) the global histogram -> global bin base
-        const uint32_t h = hist[t];
         const uint32_t incl_c = warp_incl_scan(cnt, lane);
-        const uint32_t incl_h = warp_incl_scan(h, lane);
+        const uint32_t incl_h = warp_incl_scan(h_digit, lane);
         if (lane == 31) {
             sm.warp_tot[warp] = incl_c;
             sm.warp_hist_tot[warp] = incl_h;
@@ -233,21 +257,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
                 base_h += sm.warp_hist_tot[w];
             }
         }
-        const uint32_t bin_start = base_c + incl_c - cnt;
-        const uint32_t bin_global = base_h + incl_h - h;
+        bin_start = base_c + incl_c - cnt;
+        bin_global = base_h + incl_h - h_digit;
         sm.bin_start[t] = bin_start;
-
-        // decoupled look-back for digit t
-        uint32_t excl_prev = 0;
-        if (tile == 0) {
-            lb[t] = kFlagInc | cnt_valid;
-        } else {
-            excl_prev = lookback_exclusive(lb, tile, t);
-            lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
-        }
-        sm.goff[t] = bin_global + excl_prev - bin_start;
     }
-    // values are loaded only now: their registers are not live during ranking / look-back
+    // values are loaded only now: their registers are not live during ranking
     uint32_t v[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
@@ -256,13 +270,28 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     }
     __syncthreads();
 
-    // ---- scatter into the staged tile (sorted by digit, stable) ----
+    // ---- look-back, first round trip in flight while the tile is scattered into shared memory ----
+    uint32_t w0[kLookFirst];
+    if (t < kRadix && tile != 0) lookback_issue<kLookFirst>(lb, (int)tile - 1, t, w0);
+
+    // scatter into the staged tile (sorted by digit, stable)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t d = (uint32_t)(sort_bits(k[i], compress) >> shift) & dmask;
         const uint32_t pos = sm.bin_start[d] + wh[d] + rank[i];
         sm.keys[pos] = k[i];
         sm.vals[pos] = v[i];
+    }
+
+    if (t < kRadix) {
+        uint32_t excl_prev = 0;
+        if (tile == 0) {
+            lb[t] = kFlagInc | cnt_valid;
+        } else {
+            excl_prev = lookback_finish(lb, tile, t, w0);
+            lb[(size_t)tile * kRadix + t] = kFlagInc | (excl_prev + cnt_valid);
+        }
+        sm.goff[t] = bin_global + excl_prev - bin_start;
     }
     __syncthreads();
 

@@ -34,13 +34,15 @@ for it in range(2):
     torch.cuda.synchronize()
 tile_items = 4096
 nt = min(32768, (Lr + tile_items - 1) // tile_items)
-buf = np.zeros((nt, 8), np.uint64)
+buf = np.zeros((nt, 16), np.uint64)
 L.lgm_debug_sort_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
 rc = L.lgm_debug_sort_timing(buf.ctypes.data_as(ctypes.c_void_p), nt)
 d = buf.astype(np.int64)   # stamps of the LAST pass that ran (clock64 is per SM: only differences within a tile matter)
 names = ["ticket+zero", "key load wait", "rank+sync", "prefix+lookback(t0)", "wait others+vals", "scatter", "write issue"]
-dur = np.diff(d, axis=1)[100:nt - 100]
+dur = np.diff(d[:, :8], axis=1)[100:nt - 100]
 print("tiles", nt, "rc", rc)
 for i, nme in enumerate(names):
     print(f"{nme:22s} median {np.median(dur[:, i]):8.0f}  p90 {np.percentile(dur[:, i], 90):8.0f} cycles")
+dd = d[100:nt - 100]
+print("  prefix loop + publish ", np.median(dd[:, 8] - dd[:, 3]), " hist load+scan+bar", np.median(dd[:, 9] - dd[:, 8]), " lookback+publish", np.median(dd[:, 4] - dd[:, 9]))
 print("total median", np.median(d[100:nt - 100, 7] - d[100:nt - 100, 0]))
