@@ -45,6 +45,10 @@ class Oracle:
     def num_threads(self):
         return int(self.lib.orc_num_threads())
 
+    def set_num_threads(self, n):
+        """Override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+        self.lib.orc_set_num_threads(ctypes.c_int(int(n)))
+
     def _a(self, x, shape=None):
         a = np.ascontiguousarray(np.asarray(x, dtype=self.dt))
         if shape is not None:

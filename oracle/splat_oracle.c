@@ -584,3 +584,11 @@ int orc_num_threads(void)
 #endif
 }
 int orc_real_bytes(void) { return (int)sizeof(real); }
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
