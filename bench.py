@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--sort-sweep", action="store_true", help="also time every onesweep launch shape (LGM_SORT_VARIANT)")
+    ap.add_argument("--loop-baseline", action="store_true",
+                    help="also time the reference's per-view driver loop (core/gs.py:42-93) on the same kernels")
     return ap.parse_args()
 
 
@@ -376,6 +378,39 @@ def run_native(args):
                           "max_tile_len": int(lens.max()), "mean_tile_len": float(lens.float().mean())},
         }
         del st
+
+    # ---- the reference's DRIVER shape on the same kernels: core/gs.py:42-93's Python loop over B and V with one
+    # GaussianRasterizer call (and one host readback) per view, clamp, stack, one autograd backward ----
+    if rank == 0 and world == 1 and not args.no_stages and args.loop_baseline:
+        from lgm_b200 import GaussianRasterizationSettings, GaussianRasterizer
+
+        def step_loop():
+            g = g_dev.detach().requires_grad_(True)
+            images, alphas = [], []
+            tanh = float(renderer.inner.tan_half_fov)
+            for b in range(B):
+                means3D, opacity = g[b, :, 0:3].contiguous().float(), g[b, :, 3:4].contiguous().float()
+                scales, rotations, rgbs = g[b, :, 4:7].contiguous().float(), g[b, :, 7:11].contiguous().float(), g[b, :, 11:].contiguous().float()
+                for v in range(V):
+                    rs = GaussianRasterizationSettings(
+                        image_height=S, image_width=S, tanfovx=tanh, tanfovy=tanh, bg=bg, scale_modifier=1.0,
+                        viewmatrix=cv_dev[b, v], projmatrix=cvp_dev[b, v], sh_degree=0, campos=cp_dev[b, v],
+                        prefiltered=False, debug=False)
+                    img, _radii, _depth, al = GaussianRasterizer(raster_settings=rs)(
+                        means3D=means3D, means2D=torch.zeros_like(means3D), shs=None, colors_precomp=rgbs, opacities=opacity,
+                        scales=scales, rotations=rotations, cov3D_precomp=None)
+                    images.append(img.clamp(0, 1))
+                    alphas.append(al)
+            images = torch.stack(images, dim=0).view(B * V, 3, S, S)
+            alphas = torch.stack(alphas, dim=0).view(B * V, 1, S, S)
+            torch.autograd.backward([images, alphas], [d_img, d_alpha])
+            return g.grad
+
+        ms_loop, _ = timed(step_loop, 2, 1)
+        extra["per_view_loop"] = {"value": n_views_total / (ms_loop * 1e-3), "unit": UNIT, "ms_per_step": ms_loop,
+                                  "what": "same kernels driven as /root/reference/core/gs.py:42-93 drives the external "
+                                          "rasterizer: Python loop over B x V, one GaussianRasterizer call and one host "
+                                          "readback per view, clamp, torch.stack, one backward"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -4,11 +4,11 @@
 // is rendered by ONE launch (grid = views x tiles).
 //
 // Work skipping that cannot change a result: while Gaussians are staged in shared memory, the staging thread also
-// derives a conservative bound t2 such that alpha = min(0.99, o * exp(power)) >= 1/255 (the reference's skip
-// threshold) is only possible where the conic's quadratic form is <= t2.  Each warp owns an 8x4 pixel patch; per 32
-// staged Gaussians the lanes test one Gaussian each (exact ellipse-vs-rectangle minimum), a ballot selects those that
-// can reach the patch, and only these are evaluated — with the reference's exact, pinned per-pair arithmetic
-// (splat_math.cuh).  A skipped pair is one the reference evaluates and then discards.
+// derives, ONCE per Gaussian, a conservative screen-space box outside of which alpha = min(0.99, o * exp(power)) is
+// certainly < 1/255 (the reference's skip threshold) and from it an 8-bit mask of the tile's eight 8x4-pixel patches
+// the Gaussian can reach.  Each warp owns one patch; per 32 staged Gaussians one ballot of the warp's mask bit selects
+// the Gaussians to evaluate — with the reference's exact, pinned per-pair arithmetic (splat_math.cuh).  A skipped pair
+// is one the reference evaluates and then discards.
 //
 // Scheduling: after culling, the work of the 8 warps of a tile is very uneven, so block barriers are the enemy.  Up
 // to kBatch = 1024 Gaussians (48 KB of the SM's 227 KB shared memory) are staged per barrier — most tiles need exactly
@@ -24,15 +24,17 @@ namespace {
 constexpr int kBatch = 1024;          // Gaussians staged per block barrier
 constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
 constexpr float kCullPad = 2e-3f;
+constexpr float kCullPix = 0.02f;     // pixels
 
 struct __align__(16) Staged {
     float4 p0;    // px, py, conic xx, conic xy
-    float4 p1;    // conic yy, opacity, cull bound t2, row index (view * P + idx) as bits
+    float4 p1;    // conic yy, opacity, row index (view * P + idx) as bits, 8-bit patch mask as bits
     float4 rgbd;  // r, g, b, depth
 };
 static_assert(sizeof(Staged) == 48, "staged record is three 16-byte vectors");
 
-// A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store).
+// A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store): patch w of the tile
+// is column (w & 1), row (w >> 1).
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -40,47 +42,45 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
     py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
 }
 
-// alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. q(d) = cx dx^2 + 2 cy dx dy + cz dy^2
-// <= 2 ln(255 o).  t2 is that bound with safety margins; t2 < 0: never visible (255 o <= 1); t2 = +inf: the conic is
-// not positive definite (or NaN) — the visible region is unbounded, keep the pair everywhere.
-__device__ __forceinline__ float cull_bound(const float4 co)
+// Which of the tile's eight 8x4 patches can this Gaussian reach with alpha >= 1/255 ?  (bit w = patch w)
+// alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. 0.5 d^T Q d <= tau = ln(255 o) with
+// Q = [[cx, cy], [cy, cz]]: an ellipse around the centre with axis-aligned half extents
+//   hx = sqrt(2 tau cz / det Q),  hy = sqrt(2 tau cx / det Q)          (+ safety margins for fp32 rounding).
+// Computed ONCE per staged Gaussian by its staging thread; each warp then only tests its bit.
+// 255 o <= 1: never visible (mask 0).  Q not positive definite (or NaN): the region is unbounded, all patches.
+__device__ __forceinline__ uint32_t patch_mask(float px, float py, const float4 co, float tile_x0, float tile_y0)
 {
     const float k = 255.0f * co.w;
-    if (k <= 1.0f) return -1.0f;
+    if (k <= 1.0f) return 0u;
     const float det = co.x * co.z - co.y * co.y;
-    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return __int_as_float(0x7f800000);
-    return 2.0f * __logf(k) * kCullScale + kCullPad;
-}
-
-// Does the ellipse q(d) <= t2 around the Gaussian centre reach the warp's patch?  Exact minimum of the convex
-// quadratic over the rectangle d in [ax,bx] x [ay,by] (d = centre - pixel): zero if the centre is inside, otherwise
-// attained on a face that looks at the centre.  Conservative: the margins in t2 dominate the rounding here.
-__device__ __forceinline__ bool ellipse_hits_patch(const float4 p0, const float4 p1, float X0, float X1, float Y0, float Y1)
-{
-    const float t2 = p1.z;
-    if (t2 < 0.0f) return false;
-    const float cx = p0.z, cy = p0.w, cz = p1.x;
-    const float ax = p0.x - X1, bx = p0.x - X0, ay = p0.y - Y1, by = p0.y - Y0;  // d ranges over [ax,bx] x [ay,by]
-    const float dxc = fminf(fmaxf(0.0f, ax), bx), dyc = fminf(fmaxf(0.0f, ay), by);
-    // face x = dxc: best y is -cy dxc / cz clamped;  face y = dyc: best x is -cy dyc / cx clamped
-    const float y1 = fminf(fmaxf(__fdividef(-cy * dxc, cz), ay), by);
-    const float x2 = fminf(fmaxf(__fdividef(-cy * dyc, cx), ax), bx);
-    const float q1 = cx * dxc * dxc + 2.0f * cy * dxc * y1 + cz * y1 * y1;
-    const float q2 = cx * x2 * x2 + 2.0f * cy * x2 * dyc + cz * dyc * dyc;
-    const float q = (dxc == 0.0f && dyc == 0.0f) ? 0.0f : fminf(dxc != 0.0f ? q1 : q2, dyc != 0.0f ? q2 : q1);
-    return !(q > t2);  // NaN -> hit
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return 0xffu;
+    const float t2 = 2.0f * __logf(k) * kCullScale + kCullPad;
+    const float inv = __fdividef(t2, det);
+    const float hx = sqrtf(co.z * inv) * kCullScale + kCullPix, hy = sqrtf(co.x * inv) * kCullScale + kCullPix;
+    const float lo_x = px - hx - tile_x0, hi_x = px + hx - tile_x0;  // extent relative to the tile origin
+    const float lo_y = py - hy - tile_y0, hi_y = py + hy - tile_y0;
+    // columns cover pixel centres [0,7] and [8,15]; rows [0,3], [4,7], [8,11], [12,15].  NaN compares false -> keep.
+    const uint32_t c0 = !(hi_x < 0.0f) && !(lo_x > 7.0f), c1 = !(hi_x < 8.0f) && !(lo_x > 15.0f);
+    const uint32_t cols = c0 | (c1 << 1);
+    uint32_t m = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const bool row = !(hi_y < 4.0f * r) && !(lo_y > 4.0f * r + 3.0f);
+        m |= row ? (cols << (2 * r)) : 0u;
+    }
+    return m;
 }
 
 // Gather one instance (row g of the per-(view,Gaussian) arrays + its colour) into a staged record.
 __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view_base, const float* __restrict__ scene_g,
                                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
-                                          const float* __restrict__ depth)
+                                          const float* __restrict__ depth, float tile_x0, float tile_y0)
 {
     const float2 p = xy[g];
     const float4 co = conic_opacity[g];
     const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
     dst.p0 = make_float4(p.x, p.y, co.x, co.y);
-    dst.p1 = make_float4(co.z, co.w, cull_bound(co), __uint_as_float(g));
+    dst.p1 = make_float4(co.z, co.w, __uint_as_float(g), __uint_as_float(patch_mask(p.x, p.y, co, tile_x0, tile_y0)));
     dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
 }
 
@@ -104,8 +104,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     pixel_of_thread(tile_x, tile_y, px, py);
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
-    const float X0 = (float)(tile_x * kTile + (warp & 1) * 8), X1 = X0 + 7.0f;
-    const float Y0 = (float)(tile_y * kTile + (warp >> 1) * 4), Y1 = Y0 + 3.0f;
+    const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
 
     const uint2 range = ranges[gt];
     const int todo = (int)(range.y - range.x);
@@ -120,13 +119,13 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffer
         const int nb = min(kBatch, todo - r0);
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth);
+            stage_one(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             if (__all_sync(0xffffffffu, done)) break;  // every pixel of the patch is saturated (or outside)
             const int jl = base + lane;
             bool hit = false;
-            if (jl < nb) hit = ellipse_hits_patch(s_rec[jl].p0, s_rec[jl].p1, X0, X1, Y0, Y1);
+            if (jl < nb) hit = (__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u;
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
@@ -225,8 +224,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     pixel_of_thread(tile_x, tile_y, px, py);
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
-    const float X0 = (float)(tile_x * kTile + (warp & 1) * 8), X1 = X0 + 7.0f;
-    const float Y0 = (float)(tile_y * kTile + (warp >> 1) * 4), Y1 = Y0 + 3.0f;
+    const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
     const size_t hw = (size_t)prm.H * prm.W;
     const size_t pix = (size_t)py * prm.W + px;
 
@@ -270,14 +268,14 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         const int nb = min(kBatch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth);
+            stage_one(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
+                      tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
             bool hit = false;
             // positions >= wmax were never reached by this patch in the forward
-            if (jl < nb && (uint32_t)(todo - 1 - (r0 + jl)) < wmax)
-                hit = ellipse_hits_patch(s_rec[jl].p0, s_rec[jl].p1, X0, X1, Y0, Y1);
+            if (jl < nb && (uint32_t)(todo - 1 - (r0 + jl)) < wmax) hit = (__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u;
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = base + __ffs(m) - 1;
@@ -338,7 +336,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 warp_reduce_10(va, vb, lane, A, Bv);
                 // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
                 if (red_slot >= 0)
-                    atomicAdd(grad_rows + (size_t)__float_as_uint(p1.w) * kGradRow + red_slot, red_is_b ? Bv : A);
+                    atomicAdd(grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow + red_slot, red_is_b ? Bv : A);
             }
         }
     }
