@@ -84,20 +84,23 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
                     uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes);
 
-/* K5 compositing.  Replaces renderCUDA fwd.  image [n_views,3,H,W] (not clamped), alpha / depth_img [n_views,H,W],
- * n_contrib u32 [n_views,H,W].                                                                              */
+/* K5 compositing.  Replaces renderCUDA fwd.  image [n_views,3,H,W], alpha / depth_img [n_views,H,W], n_contrib u32
+ * [n_views,H,W] (bits 0..28: number of list entries the pixel consumed, as upstream).
+ * clamp_image == 0: image as upstream writes it (not clamped).  clamp_image != 0: the caller's clamp(0,1) of
+ * /root/reference/core/gs.py:87 is fused into the store, and bits 29..31 of n_contrib flag the colour channels whose
+ * gradient that clamp blocks; lgm_backward* honours the flags, so d(clamped image) is what it must be given.    */
 int lgm_forward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
                           const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
-                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, float* image,
-                          float* alpha, float* depth_img, uint32_t* n_contrib);
+                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, int32_t clamp_image,
+                          float* image, float* alpha, float* depth_img, uint32_t* n_contrib);
 
 /* forward_bin followed by forward_composite (SURVEY.md §8b level 3, entry 3). */
 int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
                            int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
-                           void* workspace, size_t workspace_bytes, const float* bg, float* image, float* alpha,
-                           float* depth_img, uint32_t* n_contrib);
+                           void* workspace, size_t workspace_bytes, const float* bg, int32_t clamp_image, float* image,
+                           float* alpha, float* depth_img, uint32_t* n_contrib);
 
 /* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
  * grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on return it holds the

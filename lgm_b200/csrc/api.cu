@@ -172,8 +172,8 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
 
 int lgm_forward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
                           const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
-                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, float* image,
-                          float* alpha, float* depth_img, uint32_t* n_contrib)
+                          const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, int32_t clamp_image,
+                          float* image, float* alpha, float* depth_img, uint32_t* n_contrib)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
@@ -183,7 +183,8 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
     if (p.P > 0) { LGM_NOTNULL(gaussians); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth); }
     LGM_CUDA(lgm::launch_composite_fwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),
                                        reinterpret_cast<const float4*>(conic_opacity), depth, vals_sorted,
-                                       reinterpret_cast<const uint2*>(ranges), bg, image, alpha, depth_img, n_contrib),
+                                       reinterpret_cast<const uint2*>(ranges), bg, clamp_image ? 1 : 0, image, alpha, depth_img,
+                                       n_contrib),
              "forward_composite");
     return LGM_OK;
 }
@@ -192,14 +193,14 @@ int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const flo
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
                            int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
-                           void* workspace, size_t workspace_bytes, const float* bg, float* image, float* alpha,
-                           float* depth_img, uint32_t* n_contrib)
+                           void* workspace, size_t workspace_bytes, const float* bg, int32_t clamp_image, float* image,
+                           float* alpha, float* depth_img, uint32_t* n_contrib)
 {
     if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, keys_sorted, vals_sorted, ranges,
                                  workspace, workspace_bytes))
         return rc;
-    return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg, image,
-                                 alpha, depth_img, n_contrib);
+    return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg,
+                                 clamp_image, image, alpha, depth_img, n_contrib);
 }
 
 int lgm_backward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,

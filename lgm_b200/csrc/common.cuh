@@ -50,7 +50,7 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
                                  const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
-                                 float* image, float* alpha, float* depth_img, uint32_t* n_contrib);
+                                 int clamp_image, float* image, float* alpha, float* depth_img, uint32_t* n_contrib);
 cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
                                  const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,

@@ -22,6 +22,8 @@ namespace lgm {
 namespace {
 
 constexpr int kBatch = 1024;          // Gaussians staged per block barrier
+constexpr uint32_t kClampFlag0 = 1u << 29;      // n_contrib bits 29..31: colour channel 0..2 was clamped
+constexpr uint32_t kContribMask = kClampFlag0 - 1u;
 constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
 constexpr float kCullPad = 2e-3f;
 constexpr float kCullPix = 0.02f;     // pixels
@@ -88,8 +90,9 @@ __global__ void __launch_bounds__(kBlock, 4)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                      const float* __restrict__ depth, const uint32_t* __restrict__ vals,
-                     const uint2* __restrict__ ranges, const float* __restrict__ bg, float* __restrict__ image,
-                     float* __restrict__ alpha_img, float* __restrict__ depth_img, uint32_t* __restrict__ n_contrib)
+                     const uint2* __restrict__ ranges, const float* __restrict__ bg, int clamp_image,
+                     float* __restrict__ image, float* __restrict__ alpha_img, float* __restrict__ depth_img,
+                     uint32_t* __restrict__ n_contrib)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
@@ -158,11 +161,21 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     if (inside) {
         const size_t hw = (size_t)prm.H * prm.W;
         const size_t pix = (size_t)py * prm.W + px;
+        float o0 = LGM_FMA(T, __ldg(bg), C0), o1 = LGM_FMA(T, __ldg(bg + 1), C1), o2 = LGM_FMA(T, __ldg(bg + 2), C2);
+        if (clamp_image) {
+            // the renderer's clamp(0, 1) (/root/reference/core/gs.py:87) fused into the store; the channels whose
+            // gradient the clamp blocks (value outside [0,1], or NaN) are flagged in bits 29..31 of n_contrib
+            last |= (!(o0 >= 0.0f && o0 <= 1.0f) ? kClampFlag0 : 0u) | (!(o1 >= 0.0f && o1 <= 1.0f) ? kClampFlag0 << 1 : 0u) |
+                    (!(o2 >= 0.0f && o2 <= 1.0f) ? kClampFlag0 << 2 : 0u);
+            o0 = fminf(fmaxf(o0, 0.0f), 1.0f);
+            o1 = fminf(fmaxf(o1, 0.0f), 1.0f);
+            o2 = fminf(fmaxf(o2, 0.0f), 1.0f);
+        }
         n_contrib[(size_t)view * hw + pix] = last;
         float* img = image + (size_t)view * 3 * hw + pix;
-        img[0] = LGM_FMA(T, __ldg(bg), C0);
-        img[hw] = LGM_FMA(T, __ldg(bg + 1), C1);
-        img[2 * hw] = LGM_FMA(T, __ldg(bg + 2), C2);
+        img[0] = o0;
+        img[hw] = o1;
+        img[2 * hw] = o2;
         alpha_img[(size_t)view * hw + pix] = Wt;
         depth_img[(size_t)view * hw + pix] = D;
     }
@@ -235,12 +248,13 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     uint32_t last_contributor = 0;
     float T_final = 0.f, dC0 = 0.f, dC1 = 0.f, dC2 = 0.f, dD = 0.f, dA = 0.f;
     if (inside) {
-        last_contributor = n_contrib[(size_t)view * hw + pix];
+        const uint32_t nc = n_contrib[(size_t)view * hw + pix];
+        last_contributor = nc & kContribMask;
         T_final = 1.0f - alpha_img[(size_t)view * hw + pix];
         const float* dimg = dL_dimage + (size_t)view * 3 * hw + pix;
-        dC0 = dimg[0];
-        dC1 = dimg[hw];
-        dC2 = dimg[2 * hw];
+        dC0 = (nc & kClampFlag0) ? 0.0f : dimg[0];  // clamp's gradient mask (set by the forward when it clamps)
+        dC1 = (nc & (kClampFlag0 << 1)) ? 0.0f : dimg[hw];
+        dC2 = (nc & (kClampFlag0 << 2)) ? 0.0f : dimg[2 * hw];
         dD = dL_ddepth_img[(size_t)view * hw + pix];
         dA = dL_dalpha_img[(size_t)view * hw + pix];
     }
@@ -347,7 +361,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
                                  const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
-                                 float* image, float* alpha, float* depth_img, uint32_t* n_contrib)
+                                 int clamp_image, float* image, float* alpha, float* depth_img, uint32_t* n_contrib)
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
@@ -359,7 +373,7 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
         attr_set = true;
     }
     composite_fwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
-                                                                     vals, ranges, bg, image, alpha, depth_img, n_contrib);
+                                                                     vals, ranges, bg, clamp_image, image, alpha, depth_img, n_contrib);
     return cudaGetLastError();
 }
 

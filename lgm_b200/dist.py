@@ -77,6 +77,7 @@ class ShardedGaussianRenderer:
         vm, pm, _cp, scene, (b, e) = shard_views(cam_view, cam_view_proj, cam_pos, rank, world)
         S = int(self.inner.opt.output_size)
         bg = (self.inner.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
-        cfg = ops.ViewConfig(S, S, float(self.inner.tan_half_fov), float(self.inner.tan_half_fov), float(scale_modifier))
+        cfg = ops.ViewConfig(S, S, float(self.inner.tan_half_fov), float(self.inner.tan_half_fov), float(scale_modifier),
+                             clamp_image=True)  # core/gs.py:87, fused
         image, alpha, depth, _ = ops.render_views(g, vm.to(g.device), pm.to(g.device), scene, bg, cfg)
-        return {"image": image.clamp(0, 1), "alpha": alpha, "depth": depth, "views": (b, e)}
+        return {"image": image, "alpha": alpha, "depth": depth, "views": (b, e)}

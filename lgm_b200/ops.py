@@ -58,6 +58,7 @@ class ViewConfig:
     tanfovy: float
     scale_modifier: float = 1.0
     keep_binning: bool = False  # keep sorted keys / tiles_touched (parity tests)
+    clamp_image: bool = False   # fuse the renderer's clamp(0,1) (core/gs.py:87) and its gradient mask into the kernels
 
 
 def _stream():
@@ -133,8 +134,8 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel()), "lgm_forward_bin"))
     _timed("composite_fwd", lambda: _lib.check(L.lgm_forward_composite(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.depth),
-        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), _lib.ptr(image), _lib.ptr(alpha), _lib.ptr(depth_img),
-        _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
+        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), 1 if cfg.clamp_image else 0, _lib.ptr(image), _lib.ptr(alpha),
+        _lib.ptr(depth_img), _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
     if n_inst > 0:
         launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)  # emit, histogram, ranges + onesweep passes
     launch_counter["kernels"] += 1 if VW else 0                     # compositing

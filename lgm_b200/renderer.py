@@ -48,9 +48,10 @@ class GaussianRenderer:
         vm = cam_view.reshape(B * V, 16).contiguous().float()  # core/gs.py:54-55
         pm = cam_view_proj.reshape(B * V, 16).contiguous().float()
         bg = (self.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
-        cfg = ops.ViewConfig(S, S, float(self.tan_half_fov), float(self.tan_half_fov), float(scale_modifier))
+        # core/gs.py:87 clamps the image (alpha is not clamped): fused into the compositing kernels (clamp_image)
+        cfg = ops.ViewConfig(S, S, float(self.tan_half_fov), float(self.tan_half_fov), float(scale_modifier),
+                             clamp_image=True)
         image, alpha, depth, _radii = ops.render_views(g, vm, pm, self._view_scene(B, V), bg, cfg, max_views_per_call)
-        image = image.clamp(0, 1)                              # core/gs.py:87 (alpha is not clamped)
         return {
             "image": image.view(B, V, 3, S, S),   # [B, V, 3, H, W]
             "alpha": alpha.view(B, V, 1, S, S),   # [B, V, 1, H, W]

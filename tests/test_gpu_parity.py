@@ -398,3 +398,32 @@ def test_onesweep_every_launch_shape(variant, monkeypatch):
     for n, end_bit, dist in ((1_000_003, -48, "tiles"), (4097, 64, "uniform"), (250_000, 49, "equal")):
         test_onesweep_sort_pairs.__wrapped__(n, end_bit, dist) if hasattr(test_onesweep_sort_pairs, "__wrapped__") \
             else test_onesweep_sort_pairs(n, end_bit, dist)
+
+
+def test_fused_clamp_equals_torch_clamp():
+    """clamp_image (the clamp(0,1) of /root/reference/core/gs.py:87 fused into K5, its gradient mask carried to K6 in
+    n_contrib bits 29..31) == unfused kernels + torch.clamp under autograd, on colours that really leave [0,1]."""
+    from lgm_b200 import ops
+    B, V, N, S = 2, 2, 3000, 64
+    g = make_gaussians(B, N, "trained", seed=21)
+    g[:, :, 4:7] *= 5.0
+    g[:, :, 11:14] = g[:, :, 11:14] * 2.5 - 0.75          # rgb in [-0.75, 1.75]
+    cv, cvp, _ = make_cameras(B, V, seed=21)
+    t = tan_half(49.1)
+    vm, pm = cv.reshape(B * V, 16).to(DEV), cvp.reshape(B * V, 16).to(DEV)
+    scene = torch.arange(B, dtype=torch.int32).repeat_interleave(V)
+    bg = torch.tensor([0.9, 0.1, 0.5], device=DEV)
+    w = torch.randn(B * V, 3, S, S, generator=torch.Generator().manual_seed(3)).to(DEV)
+    res = []
+    for fused in (False, True):
+        gd = g.to(DEV).requires_grad_(True)
+        cfg = ops.ViewConfig(S, S, t, t, 1.0, clamp_image=fused)
+        img, al, dp, _ = ops.render_views(gd, vm, pm, scene, bg, cfg)
+        if not fused:
+            assert float(img.max()) > 1.01 and float(img.min()) < -0.01  # the scene does leave [0,1]
+            img = img.clamp(0, 1)
+        ((img * w).sum() + al.sum() + dp.sum()).backward()
+        res.append((img.detach(), gd.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    scale = float(res[0][1].abs().max())
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 2e-5 * scale  # same kernels; only the atomics' order differs
