@@ -347,7 +347,7 @@ def run_native(args):
         if args.sort_sweep:
             sort_variants = {}
             keep = os.environ.get("LGM_SORT_VARIANT")
-            for vi in range(10):
+            for vi in range(12):
                 os.environ["LGM_SORT_VARIANT"] = str(vi)
                 sort_variants[str(vi)] = time_sort()
             if keep is None:

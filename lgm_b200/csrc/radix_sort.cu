@@ -471,8 +471,8 @@ struct Variant {
 // Tunable launch shapes (LGM_SORT_VARIANT selects; default chosen from B200 measurements)
 constexpr Variant kVariants[] = {{256, 16, 2, true, false}, {512, 8, 2, true, false},  {256, 8, 4, true, false},
                                  {256, 16, 2, false, false}, {512, 8, 2, false, false}, {256, 8, 4, false, false},
-                                 {384, 8, 2, true, true},   {512, 6, 2, true, true},   {256, 12, 3, true, true},
-                                 {384, 10, 2, true, true}};
+                                 {384, 8, 2, true, true},   {384, 8, 3, false, false}, {384, 8, 3, true, false},
+                                 {256, 12, 3, false, false}, {384, 6, 4, false, false}, {1024, 4, 1, false, false}};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 4;
 
@@ -590,10 +590,12 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
             case 5: err = LGM_PASS(256, 8, 4, false); break;
 #define LGM_PPASS(T, I, B) launch_pass_persistent<T, I, B>(stream, tiles, kin, vin, kalt, valt, n, shift, dmask, compress, h, lb, tk)
             case 6: err = LGM_PPASS(384, 8, 2); break;
-            case 7: err = LGM_PPASS(512, 6, 2); break;
-            case 8: err = LGM_PPASS(256, 12, 3); break;
-            default: err = LGM_PPASS(384, 10, 2); break;
 #undef LGM_PPASS
+            case 7: err = LGM_PASS(384, 8, 3, false); break;
+            case 8: err = LGM_PASS(384, 8, 3, true); break;
+            case 9: err = LGM_PASS(256, 12, 3, false); break;
+            case 10: err = LGM_PASS(384, 6, 4, false); break;
+            default: err = LGM_PASS(1024, 4, 1, false); break;
         }
 #undef LGM_PASS
         if (err != cudaSuccess) return err;
