@@ -106,7 +106,7 @@ cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, 
 
 // ---- K7: preprocess backward.  One thread per Gaussian loops over the views of its scene and accumulates in
 // registers, so the sum over views needs no atomics and is deterministic. ----
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ scene_view_offsets,
                       const int32_t* __restrict__ radii, const float* __restrict__ grad_rows,
