@@ -15,13 +15,25 @@ def partition_views(n_items, world_size, rank):
     return b, min(n_items, b + per)
 
 
+def scene_blocks(n_scenes, views_per_scene, world_size):
+    """If the view partition gives every rank the same number of WHOLE scenes, return that number, else None.
+    (Then rank r's gradient is non-zero only in scenes [r k, (r+1) k): an all-gather of the owned blocks equals the
+    all-reduce of the zero-padded tensors at a fraction of the traffic.)"""
+    n = n_scenes * views_per_scene
+    per = (n + world_size - 1) // world_size
+    if per == 0 or per % views_per_scene or n % world_size or n_scenes % world_size:
+        return None
+    return per // views_per_scene
+
+
 class _ReplicatedInput(torch.autograd.Function):
-    """Identity in forward (optionally a broadcast from `src`); all-reduce(sum) of the gradient in backward, so the
-    collective sits in the autograd graph of `gaussians` exactly once per step."""
+    """Identity in forward (optionally a broadcast from `src`); sum of the ranks' gradients in backward, so the
+    collective sits in the autograd graph of `gaussians` exactly once per step.  The sum is an all-reduce in general;
+    when every rank owns whole scenes (`block` scenes each) it is an all-gather of the owned blocks."""
 
     @staticmethod
-    def forward(ctx, x, group, src):
-        ctx.group = group
+    def forward(ctx, x, group, src, block):
+        ctx.group, ctx.block = group, block
         if src is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
             x = x.contiguous().clone()
             dist.broadcast(x, src=src, group=group)
@@ -31,13 +43,19 @@ class _ReplicatedInput(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous()
         if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
-            g = g.clone()
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None, None
+            world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
+            if ctx.block is not None and g.shape[0] == ctx.block * world:
+                out = torch.empty_like(g)
+                dist.all_gather_into_tensor(out, g[rank * ctx.block:(rank + 1) * ctx.block].contiguous(), group=ctx.group)
+                g = out
+            else:
+                g = g.clone()
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None, None, None
 
 
-def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None):
-    return _ReplicatedInput.apply(gaussians, group, broadcast_src)
+def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None, scenes_per_rank=None):
+    return _ReplicatedInput.apply(gaussians, group, broadcast_src, scenes_per_rank)
 
 
 def shard_views(cam_view, cam_view_proj, cam_pos, rank=None, world_size=None):
@@ -62,7 +80,8 @@ class ShardedGaussianRenderer:
 
     render() returns this rank's views only: image [n_local,3,H,W], alpha, depth [n_local,1,H,W] and the (begin,end)
     block of the flattened B*V index space.  Back-propagating any loss on them yields, on EVERY rank, the gradient
-    of the sum of all ranks' losses w.r.t. `gaussians` (one all-reduce)."""
+    of the sum of all ranks' losses w.r.t. `gaussians` (one collective: all-reduce, or all-gather when every rank
+    owns whole scenes)."""
 
     def __init__(self, opt, device="cuda", group=None):
         from .renderer import GaussianRenderer
@@ -71,9 +90,10 @@ class ShardedGaussianRenderer:
 
     def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1, broadcast_src=None):
         from . import ops
-        g = replicate_for_view_sharding(gaussians.contiguous().float(), self.group, broadcast_src)
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        g = replicate_for_view_sharding(gaussians.contiguous().float(), self.group, broadcast_src,
+                                        scene_blocks(cam_view.shape[0], cam_view.shape[1], world))
         vm, pm, _cp, scene, (b, e) = shard_views(cam_view, cam_view_proj, cam_pos, rank, world)
         S = int(self.inner.opt.output_size)
         bg = (self.inner.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()

@@ -9,7 +9,7 @@ from types import SimpleNamespace
 
 import torch
 
-from . import ops
+from . import ops, ply
 
 
 def default_options(output_size=256, fovy=49.1, znear=0.5, zfar=2.5):
@@ -57,3 +57,10 @@ class GaussianRenderer:
             "alpha": alpha.view(B, V, 1, S, S),   # [B, V, 1, H, W]
             "depth": depth.view(B, V, 1, S, S),   # [B, V, 1, H, W]  (superset of the reference's dict)
         }
+
+    # on-disk format of the path's input (/root/reference/core/gs.py:101-190)
+    def save_ply(self, gaussians, path, compatible=True):
+        return ply.save_ply(gaussians, path, compatible)
+
+    def load_ply(self, path, compatible=True):
+        return ply.load_ply(path, compatible)

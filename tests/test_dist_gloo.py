@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from lgm_b200.dist import partition_views, replicate_for_view_sharding, shard_views
+        from lgm_b200.dist import partition_views, replicate_for_view_sharding, scene_blocks, shard_views
         torch.manual_seed(0)
         B, N, V = 2, 16, 5
         g_full = torch.randn(B, N, 14)
@@ -45,6 +45,12 @@ def _worker(rank, world, port, q):
         for j in range(B * V):
             exp[j // V] += w_all[j]
         ok = torch.allclose(g_in.grad, exp, rtol=1e-5, atol=1e-5)
+        # whole scenes per rank (B = 2, world = 2): the all-gather path must give the same sum
+        assert scene_blocks(B, V, world) == 1 and scene_blocks(3, V, world) is None and scene_blocks(4, 3, 2) == 2
+        g2 = g_full.clone().requires_grad_(True)
+        gg = replicate_for_view_sharding(g2, None, None, scene_blocks(B, V, world))
+        sum((gg[int(scene[j])] * w[j]).sum() for j in range(e - b)).backward()
+        ok = ok and torch.allclose(g2.grad, exp, rtol=1e-5, atol=1e-5)
         q.put((rank, bool(ok), (b, e)))
     finally:
         dist.destroy_process_group()
