@@ -17,11 +17,12 @@
 // Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / L2 reductions in the backward).
 #include "common.cuh"
 #include "splat_math.cuh"
+#include <stdlib.h>
 
 namespace lgm {
 namespace {
 
-constexpr int kBatch = 1024;          // Gaussians staged per block barrier
+constexpr int kBatch = 1024;          // Gaussians staged per block barrier (default; LGM_FWD_BATCH / LGM_BWD_BATCH override)
 constexpr uint32_t kClampFlag0 = 1u << 29;      // n_contrib bits 29..31: colour channel 0..2 was clamped
 constexpr uint32_t kContribMask = kClampFlag0 - 1u;
 constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kBlock, 4)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                      const float* __restrict__ depth, const uint32_t* __restrict__ vals,
-                     const uint2* __restrict__ ranges, const float* __restrict__ bg, int clamp_image,
+                     const uint2* __restrict__ ranges, const float* __restrict__ bg, int clamp_image, int batch,
                      float* __restrict__ image, float* __restrict__ alpha_img, float* __restrict__ depth_img,
                      uint32_t* __restrict__ n_contrib)
 {
@@ -118,9 +119,9 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     uint32_t last = 0;
     bool done = !inside;
 
-    for (int r0 = 0; r0 < todo; r0 += kBatch) {
+    for (int r0 = 0; r0 < todo; r0 += batch) {
         if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffer
-        const int nb = min(kBatch, todo - r0);
+        const int nb = min(batch, todo - r0);
         for (int k = threadIdx.x; k < nb; k += kBlock)
             stage_one(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
@@ -221,7 +222,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                      const uint2* __restrict__ ranges, const float* __restrict__ bg,
                      const float* __restrict__ alpha_img, const uint32_t* __restrict__ n_contrib,
                      const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
-                     const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
+                     const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows, int batch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
@@ -277,9 +278,9 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const bool red_is_b = (lane & 15) == 1;
     const int red_slot = (lane & 3) == 0 ? (lane >> 2) : (red_is_b ? 8 + (lane >> 4) : -1);
 
-    for (int r0 = 0; r0 < todo; r0 += kBatch) {
+    for (int r0 = 0; r0 < todo; r0 += batch) {
         __syncthreads();  // the staging buffer is free again
-        const int nb = min(kBatch, todo - r0);
+        const int nb = min(batch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
         for (int k = threadIdx.x; k < nb; k += kBlock)
             stage_one(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
@@ -356,6 +357,18 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     }
 }
 
+constexpr int kMaxBatch = 2048;
+// tuning hook: staged Gaussians per barrier (multiple of 32, 32..2048)
+int batch_from_env(const char* name)
+{
+    const char* e = getenv(name);
+    if (e) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= kMaxBatch && v % 32 == 0) return v;
+    }
+    return kBatch;
+}
+
 }  // namespace
 
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
@@ -365,15 +378,17 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int smem = kBatch * (int)sizeof(Staged);
+    const int batch = batch_from_env("LGM_FWD_BATCH");
+    const int smem = batch * (int)sizeof(Staged);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxBatch * (int)sizeof(Staged));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     composite_fwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
-                                                                     vals, ranges, bg, clamp_image, image, alpha, depth_img, n_contrib);
+                                                                     vals, ranges, bg, clamp_image, batch, image, alpha, depth_img, n_contrib);
     return cudaGetLastError();
 }
 
@@ -385,16 +400,18 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int smem = kBatch * (int)sizeof(Staged);
+    const int batch = batch_from_env("LGM_BWD_BATCH");
+    const int smem = batch * (int)sizeof(Staged);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxBatch * (int)sizeof(Staged));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     composite_bwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
                                                                      vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-                                                                     dL_ddepth, grad_rows);
+                                                                     dL_ddepth, grad_rows, batch);
     return cudaGetLastError();
 }
 
