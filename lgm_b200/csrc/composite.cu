@@ -90,7 +90,7 @@ __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view
     dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
 }
 
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, 6)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                      const float* __restrict__ depth, const uint32_t* __restrict__ vals,
@@ -218,7 +218,7 @@ __device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float 
     Bv = bk;
 }
 
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, 5)
 composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                      const float* __restrict__ depth, const uint32_t* __restrict__ vals,
