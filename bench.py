@@ -358,7 +358,11 @@ def run_native(args):
         sort_bytes = (npass * 24 + 8) * Lr
         ach = sort_bytes / (t_sort * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"onesweep radix sort (histogram + {npass} passes, u64 key + u32 value)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    # DRAM bytes from the ncu --set full capture of this workload (profiles/r01_summary.md):
+                    # 752 + 716 MB per pass and 498 MB for the histogram at L = 62.2 M -> 23.6 and 8.0 B per pair
+                    "traffic": int((npass * 23.6 + 8.0) * Lr),
+                    "traffic_source": "profiles/r01_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per pair, scaled by L)",
                     "peak_source": peak_src, "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
                     "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
         # SURVEY §8d group accounting: preprocess + emit + sort + ranges
