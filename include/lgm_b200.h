@@ -103,7 +103,8 @@ int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const flo
                            float* alpha, float* depth_img, uint32_t* n_contrib);
 
 /* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
- * grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on return it holds the
+ * dL_ddepth may be NULL (= zero gradient w.r.t. the depth image: LGM's losses never use depth; a cheaper kernel
+ * instantiation runs).  grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on return it holds the
  * per-view screen-space gradients (dL/dmean2D in [0:2] is what means2D.grad receives upstream).
  * dL_dgaussians [n_scenes, P, 14]: per-Gaussian gradients summed over the views of each scene; overwritten when
  * accumulate == 0, added to when accumulate != 0 (view chunks of one step).                                  */

@@ -214,7 +214,7 @@ int lgm_backward_composite(void* stream, const lgm_render_params* prm, const flo
     if (p.n_views == 0 || p.P == 0) return LGM_OK;
     LGM_NOTNULL(gaussians); LGM_NOTNULL(view_scene); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth);
     LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(alpha); LGM_NOTNULL(n_contrib); LGM_NOTNULL(dL_dimage); LGM_NOTNULL(dL_dalpha);
-    LGM_NOTNULL(dL_ddepth); LGM_NOTNULL(grad_rows);
+    LGM_NOTNULL(grad_rows);  // dL_ddepth may be NULL: no gradient w.r.t. the depth image
     LGM_CUDA(lgm::launch_composite_bwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),
                                        reinterpret_cast<const float4*>(conic_opacity), depth, vals_sorted,
                                        reinterpret_cast<const uint2*>(ranges), bg, alpha, n_contrib, dL_dimage, dL_dalpha,

@@ -189,19 +189,21 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
 // keeps half of its values and hands the other half to its partner).  On return lane L holds
 //   A  = sum over lanes of a[4*b4 + 2*b3 + b2]   (b4,b3,b2 = bits 4,3,2 of L; all four lanes of a quad agree)
 //   Bv = sum over lanes of b[b4]
+template <bool DEPTH>
 __device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float (&b)[2], int lane, float& A, float& Bv)
 {
     const unsigned full = 0xffffffffu;
     const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
     float k0 = h16 ? a[4] : a[0], k1 = h16 ? a[5] : a[1], k2 = h16 ? a[6] : a[2], k3 = h16 ? a[7] : a[3];
     const float s0 = h16 ? a[0] : a[4], s1 = h16 ? a[1] : a[5], s2 = h16 ? a[2] : a[6], s3 = h16 ? a[3] : a[7];
-    float bk = h16 ? b[1] : b[0];
-    const float bs = h16 ? b[0] : b[1];
+    // without a depth gradient b[1] is identically zero: every lane keeps b[0] and lane 1 ends with the full sum
+    float bk = DEPTH ? (h16 ? b[1] : b[0]) : b[0];
+    const float bs = DEPTH ? (h16 ? b[0] : b[1]) : b[0];
     k0 += __shfl_xor_sync(full, s0, 16);
     k1 += __shfl_xor_sync(full, s1, 16);
     k2 += __shfl_xor_sync(full, s2, 16);
     k3 += __shfl_xor_sync(full, s3, 16);
-    bk += __shfl_xor_sync(full, bs, 16);
+    bk += __shfl_xor_sync(full, bs, 16);  // DEPTH = false: a plain butterfly, all lanes end with sum b[0]
     float m0 = h8 ? k2 : k0, m1 = h8 ? k3 : k1;
     const float t0 = h8 ? k0 : k2, t1 = h8 ? k1 : k3;
     m0 += __shfl_xor_sync(full, t0, 8);
@@ -218,6 +220,9 @@ __device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float 
     Bv = bk;
 }
 
+// DEPTH: whether a gradient w.r.t. the depth image is given (LGM never uses the depth output, so its training step
+// runs the cheaper DEPTH = false instantiation: one value less to reduce, no depth recursion).
+template <bool DEPTH>
 __global__ void __launch_bounds__(kBlock, 5)
 composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -259,7 +264,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         dC0 = (nc & kClampFlag0) ? 0.0f : dimg[0];  // clamp's gradient mask (set by the forward when it clamps)
         dC1 = (nc & (kClampFlag0 << 1)) ? 0.0f : dimg[hw];
         dC2 = (nc & (kClampFlag0 << 2)) ? 0.0f : dimg[2 * hw];
-        dD = dL_ddepth_img[(size_t)view * hw + pix];
+        if (DEPTH) dD = dL_ddepth_img[(size_t)view * hw + pix];
         dA = dL_dalpha_img[(size_t)view * hw + pix];
     }
     const float bgT = -T_final * (__ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2);
@@ -279,7 +284,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     // which of the ten reduced sums this lane sends to the gradient row (warp_reduce_10): lanes 0,4,..,28 hold the
     // eight "a" sums (slots 0..7), lanes 1 and 17 the two "b" sums (slots 8, 9); other lanes send nothing
     const bool red_is_b = (lane & 15) == 1;
-    const int red_slot = (lane & 3) == 0 ? (lane >> 2) : (red_is_b ? 8 + (lane >> 4) : -1);
+    const int red_slot = (lane & 3) == 0 ? (lane >> 2) : ((red_is_b && (DEPTH || lane == 1)) ? 8 + (lane >> 4) : -1);
 
     for (int r0 = 0; r0 < todo; r0 += batch) {
         __syncthreads();  // the staging buffer is free again
@@ -325,13 +330,13 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     float dL_da = e0 * dC0;
                     dL_da = fmaf(e1, dC1, dL_da);
                     dL_da = fmaf(e2, dC2, dL_da);
-                    dL_da = fmaf(eD, dD, dL_da);
+                    if (DEPTH) dL_da = fmaf(eD, dD, dL_da);
                     dL_da = fmaf(eA, dA, dL_da);
                     dL_da = fmaf(dL_da, T, bgT * rcp);
                     acc0 = fmaf(ae, e0, acc0);
                     acc1 = fmaf(ae, e1, acc1);
                     acc2 = fmaf(ae, e2, acc2);
-                    accD = fmaf(ae, eD, accD);
+                    if (DEPTH) accD = fmaf(ae, eD, accD);
                     accA = fmaf(ae, eA, accA);
                     const float dL_dG = p1.y * dL_da;
                     const float gdx = Gv * dx, gdy = Gv * dy;
@@ -348,10 +353,10 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     va[6] = w * dC0;
                     va[7] = w * dC1;
                     vb[0] = w * dC2;
-                    vb[1] = w * dD;
+                    vb[1] = DEPTH ? w * dD : 0.0f;
                 }
                 float A, Bv;
-                warp_reduce_10(va, vb, lane, A, Bv);
+                warp_reduce_10<DEPTH>(va, vb, lane, A, Bv);
                 // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
                 if (red_slot >= 0)
                     atomicAdd(grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow + red_slot, red_is_b ? Bv : A);
@@ -407,14 +412,22 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
     const int smem = batch * (int)sizeof(Staged);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxBatch * (int)sizeof(Staged));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kMaxBatch * (int)sizeof(Staged));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    composite_bwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
-                                                                     vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-                                                                     dL_ddepth, grad_rows, batch);
+    if (dL_ddepth)
+        composite_bwd_kernel<true><<<(unsigned)blocks, kBlock, smem, stream>>>(
+            prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
+            dL_ddepth, grad_rows, batch);
+    else
+        composite_bwd_kernel<false><<<(unsigned)blocks, kBlock, smem, stream>>>(
+            prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
+            nullptr, grad_rows, batch);
     return cudaGetLastError();
 }
 

@@ -195,6 +195,7 @@ class _RenderViews(torch.autograd.Function):
         image, alpha, depth_img, st = forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg,
                                                     cfg)
         ctx.st = st
+        ctx.set_materialize_grads(False)  # an unused output (depth, in LGM) arrives as None, not as a zero image
         ctx.save_for_backward(gaussians, view_mats, proj_mats, bg, alpha)
         radii = st.radii.view(st.n_views, st.P)
         ctx.mark_non_differentiable(radii)
@@ -206,7 +207,7 @@ class _RenderViews(torch.autograd.Function):
         st = ctx.st
         d_image = _grad_or_zeros(d_image, alpha.expand(-1, 3, -1, -1))
         d_alpha = _grad_or_zeros(d_alpha, alpha)
-        d_depth = _grad_or_zeros(d_depth, alpha)
+        d_depth = None if d_depth is None else d_depth.contiguous().float()  # None -> NULL: no depth gradient
         d_gauss, _ = backward_views(gaussians, view_mats, proj_mats, bg, st, alpha, d_image, d_alpha, d_depth)
         return d_gauss, None, None, None, None, None, None
 

@@ -49,6 +49,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         offsets = torch.tensor([0, 1], dtype=torch.int32, device=dev)
         image, alpha, depth, st = ops.forward_views(g, vm, pm, view_scene, offsets, bg, cfg)
         ctx.st = st
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, vm, pm, bg, alpha)
         radii = st.radii.view(P)
         ctx.mark_non_differentiable(radii)
@@ -60,7 +61,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         st = ctx.st
         H, W = st.cfg.image_height, st.cfg.image_width
         z = lambda t, c: (torch.zeros(1, c, H, W, device=g.device) if t is None else t.reshape(1, c, H, W).contiguous().float())
-        d_gauss, rows = ops.backward_views(g, vm, pm, bg, st, alpha, z(grad_color, 3), z(grad_alpha, 1), z(grad_depth, 1))
+        d_gauss, rows = ops.backward_views(g, vm, pm, bg, st, alpha, z(grad_color, 3), z(grad_alpha, 1),
+                                           None if grad_depth is None else z(grad_depth, 1))
         d = d_gauss[0]
         P = d.shape[0]
         d_means2D = torch.zeros(P, 3, device=g.device)
