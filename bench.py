@@ -34,6 +34,9 @@ WORKLOADS = {
     "zero123g": (8, 26, 98304, 320, 60.0, "configs[2] Zero-1-to-G: 6x128^2 splatter = 98,304 Gaussians, 26 views at 320^2, batch 8"),
     "lgm_big": (1, 8, 65536, 512, 49.1, "configs[1] LGM default: 65,536 Gaussians, 8 views at 512^2, batch 1"),
     "tiny": (1, 1, 16384, 256, 49.1, "configs[0] tiny: 16,384 Gaussians, 1 view at 256^2"),
+    # the two multi-GPU configurations, expressed per GPU (weak scaling: x N scenes / views at N GPUs)
+    "sharded_step": (4, 20, 98304, 320, 60.0, "configs[3] view-sharded step: 32 scenes x 20 views at 320^2 over 8 GPUs = 4 scenes x 20 views per GPU"),
+    "scale_sweep": (1, 32, 1000000, 1024, 49.1, "configs[4] scale sweep: 1M Gaussians, 256 views at 1024^2 over 8 GPUs = 32 views per GPU"),
 }
 METRIC = "rendered views/sec fwd+bwd"
 UNIT = "views/s"
