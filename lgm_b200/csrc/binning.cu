@@ -60,6 +60,8 @@ cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_su
 // K2.  One thread per (view, Gaussian); its first output slot = block offset + in-block exclusive scan of the tile
 // counts (recomputed from xy / radius with the same pinned tile_rect as preprocess), then rows of its rect in
 // row-major order — the emit order the stable sort's tie-break relies on (ascending Gaussian index per tile).
+constexpr uint32_t kCoopArea = 12;  // tiles per Gaussian above which the warp emits cooperatively
+
 __global__ void __launch_bounds__(kBlock)
 emit_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
             const float* __restrict__ depth, const uint32_t* __restrict__ block_offsets, uint64_t* __restrict__ keys,
@@ -80,17 +82,40 @@ emit_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const flo
         }
     }
     const uint32_t excl = block_excl_scan_256(area, s_warp, nullptr);
-    if (area == 0) return;
-    size_t off = (size_t)block_offsets[(size_t)view * gridDim.x + blockIdx.x] + excl;
-    const uint32_t dbits = __float_as_uint(depth[gi]);
+    const uint32_t off32 = block_offsets[(size_t)view * gridDim.x + blockIdx.x] + excl;  // < 2^30 (api.cu bounds L)
+    const uint32_t dbits = area ? __float_as_uint(depth[gi]) : 0u;
     const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
     const uint32_t val = (uint32_t)gi;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            keys[off] = ((uint64_t)(tile_base + (uint32_t)(y * prm.gx + x)) << 32) | dbits;
-            vals[off] = val;
-            off++;
+    const bool big = area > kCoopArea;
+
+    // small footprints: the owning thread writes its few instances (all lanes busy, runs of adjacent threads adjoin)
+    if (area != 0 && !big) {
+        size_t off = off32;
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                keys[off] = ((uint64_t)(tile_base + (uint32_t)(y * prm.gx + x)) << 32) | dbits;
+                vals[off] = val;
+                off++;
+            }
+    }
+    // large footprints (early training, 1024^2 views: hundreds of tiles per Gaussian): the whole warp writes one
+    // Gaussian's instances, 32 consecutive slots per step — coalesced, no divergent serial loops
+    const int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t a = __shfl_sync(0xffffffffu, area, src);
+        const uint32_t o = __shfl_sync(0xffffffffu, off32, src);
+        const uint32_t sx0 = __shfl_sync(0xffffffffu, (uint32_t)x0, src), sy0 = __shfl_sync(0xffffffffu, (uint32_t)y0, src);
+        const uint32_t w = __shfl_sync(0xffffffffu, (uint32_t)(x1 - x0), src);
+        const uint32_t sd = __shfl_sync(0xffffffffu, dbits, src), sv = __shfl_sync(0xffffffffu, val, src);
+        for (uint32_t i = lane; i < a; i += 32) {  // i-th tile of the rect in row-major order: the emit order
+            const uint32_t ry = i / w, rx = i - ry * w;
+            keys[(size_t)o + i] = ((uint64_t)(tile_base + (sy0 + ry) * (uint32_t)prm.gx + sx0 + rx) << 32) | sd;
+            vals[(size_t)o + i] = sv;
         }
+    }
 }
 
 cudaError_t launch_emit(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,

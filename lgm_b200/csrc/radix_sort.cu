@@ -472,7 +472,7 @@ struct Variant {
 constexpr Variant kVariants[] = {{256, 16, 2, true, false}, {512, 8, 2, true, false},  {256, 8, 4, true, false},
                                  {256, 16, 2, false, false}, {512, 8, 2, false, false}, {256, 8, 4, false, false},
                                  {384, 8, 2, true, true},   {384, 8, 3, false, false}, {384, 8, 3, true, false},
-                                 {256, 12, 3, false, false}, {384, 6, 4, false, false}, {1024, 4, 1, false, false}};
+                                 {256, 12, 3, false, false}, {384, 6, 4, false, false}, {1024, 8, 1, false, false}};
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 4;
 
@@ -595,7 +595,7 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
             case 8: err = LGM_PASS(384, 8, 3, true); break;
             case 9: err = LGM_PASS(256, 12, 3, false); break;
             case 10: err = LGM_PASS(384, 6, 4, false); break;
-            default: err = LGM_PASS(1024, 4, 1, false); break;
+            default: err = LGM_PASS(1024, 8, 1, false); break;
         }
 #undef LGM_PASS
         if (err != cudaSuccess) return err;
