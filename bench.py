@@ -290,7 +290,8 @@ def run_native(args):
 
     # ---- stage breakdown + roofline of the HBM-bound group, measured live with CUDA events (rank 0) ----
     stages, roofline, extra = None, None, {}
-    if rank == 0 and not args.no_stages:
+    # (N = 1 only: at N > 1 a step contains collectives, which rank 0 must not enter alone)
+    if rank == 0 and world == 1 and not args.no_stages:
         ops.enable_stage_timing(True)
         for _ in range(2):
             step_resident()
