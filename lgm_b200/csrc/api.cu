@@ -3,6 +3,7 @@
 #include "../../include/lgm_b200.h"
 #include "common.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -81,7 +82,7 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     w.keys_tmp = off; off = align_up(off + (size_t)L * 8, 256);
     w.vals_tmp = off; off = align_up(off + (size_t)L * 4, 256);
     w.sort_scratch = off;
-    w.sort_scratch_bytes = lgm::sort_scratch_bytes(L, key_end_bit(p));
+    w.sort_scratch_bytes = lgm::sort_scratch_bytes(L, 0, key_end_bit(p));  // the full sort needs the most
     off = align_up(off + w.sort_scratch_bytes, 256);
     w.total = off;
     return w;
@@ -137,7 +138,8 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
 
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
-                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes)
+                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
+                    int32_t want_sorted_keys)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
@@ -159,14 +161,24 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     uint64_t* keys_tmp = reinterpret_cast<uint64_t*>(ws + w.keys_tmp);
     uint32_t* vals_tmp = reinterpret_cast<uint32_t*>(ws + w.vals_tmp);
     const int end_bit = key_end_bit(p);
-    const bool in_tmp = lgm::sort_input_is_tmp(end_bit);
+    // Hybrid sort (default): onesweep passes over the (view|tile) bits only, then every tile's segment is sorted on
+    // its 31 depth bits in shared memory — the same stable order as sorting all key bits with onesweep passes
+    // (LGM_BIN_MODE=full selects that single-stage form), at a fraction of the HBM traffic.
+    const char* mode = getenv("LGM_BIN_MODE");
+    const bool full = mode && mode[0] == 'f';
+    const int begin_bit = full ? 0 : 31;
+    const bool in_tmp = lgm::sort_input_is_tmp(begin_bit, end_bit);
     LGM_CUDA(lgm::launch_emit(s, p, radii, reinterpret_cast<const float2*>(xy), depth, block_offsets,
                               in_tmp ? keys_tmp : keys_sorted, in_tmp ? vals_tmp : vals_sorted),
              "forward_bin: emit");
-    LGM_CUDA(lgm::launch_onesweep_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, L, end_bit, /*compress=*/1, ws + w.sort_scratch,
-                                       w.sort_scratch_bytes),
+    LGM_CUDA(lgm::launch_onesweep_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, L, begin_bit, end_bit, /*compress=*/1,
+                                       ws + w.sort_scratch, w.sort_scratch_bytes),
              "forward_bin: sort");
     LGM_CUDA(lgm::launch_tile_ranges(s, keys_sorted, L, reinterpret_cast<uint2*>(ranges)), "forward_bin: ranges");
+    if (!full)
+        LGM_CUDA(lgm::launch_tile_depth_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, reinterpret_cast<const uint2*>(ranges),
+                                             (uint32_t)n_ranges, want_sorted_keys ? 1 : 0),
+                 "forward_bin: tile depth sort");
     return LGM_OK;
 }
 
@@ -197,7 +209,7 @@ int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const flo
                            float* alpha, float* depth_img, uint32_t* n_contrib)
 {
     if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, keys_sorted, vals_sorted, ranges,
-                                 workspace, workspace_bytes))
+                                 workspace, workspace_bytes, /*want_sorted_keys=*/1))
         return rc;
     return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg,
                                  clamp_image, image, alpha, depth_img, n_contrib);
@@ -261,14 +273,14 @@ int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const f
     return LGM_OK;
 }
 
-int lgm_sort_input_is_tmp(int32_t end_bit) { return lgm::sort_input_is_tmp(end_bit) ? 1 : 0; }
+int lgm_sort_input_is_tmp(int32_t end_bit) { return lgm::sort_input_is_tmp(0, end_bit) ? 1 : 0; }
 
 int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes)
 {
     LGM_NOTNULL(bytes);
     if (n < 0 || n >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "sort: n must be in [0, 2^30)");
     if (end_bit < 1 || end_bit > 64) return fail(LGM_ERR_BAD_VALUE, "sort: end_bit must be in [1, 64]");
-    *bytes = lgm::sort_scratch_bytes((uint32_t)n, end_bit);
+    *bytes = lgm::sort_scratch_bytes((uint32_t)n, 0, end_bit);
     return LGM_OK;
 }
 
@@ -280,9 +292,9 @@ int lgm_sort_pairs(void* stream, uint64_t* keys_out, uint32_t* vals_out, uint64_
     if (compress && end_bit > 63) return fail(LGM_ERR_BAD_VALUE, "sort: compressed keys have at most 63 bits");
     if (n == 0) return LGM_OK;
     LGM_NOTNULL(keys_out); LGM_NOTNULL(vals_out); LGM_NOTNULL(keys_tmp); LGM_NOTNULL(vals_tmp); LGM_NOTNULL(workspace);
-    if (workspace_bytes < lgm::sort_scratch_bytes((uint32_t)n, end_bit))
+    if (workspace_bytes < lgm::sort_scratch_bytes((uint32_t)n, 0, end_bit))
         return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "sort: workspace too small (see lgm_sort_workspace_bytes)");
-    LGM_CUDA(lgm::launch_onesweep_sort((cudaStream_t)stream, keys_out, vals_out, keys_tmp, vals_tmp, (uint32_t)n, end_bit,
+    LGM_CUDA(lgm::launch_onesweep_sort((cudaStream_t)stream, keys_out, vals_out, keys_tmp, vals_tmp, (uint32_t)n, 0, end_bit,
                                        compress ? 1 : 0, workspace, workspace_bytes),
              "sort_pairs");
     return LGM_OK;

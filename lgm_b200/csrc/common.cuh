@@ -37,15 +37,19 @@ cudaError_t launch_emit(cudaStream_t stream, const RenderParams& prm, const int3
                         const float* depth, const uint32_t* block_offsets, uint64_t* keys, uint32_t* vals);
 cudaError_t launch_tile_ranges(cudaStream_t stream, const uint64_t* keys, uint32_t L, uint2* ranges);
 
-// onesweep radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit).  The sorted result lands in
-// keys_out / vals_out; keys_tmp / vals_tmp are the alternate buffers; `in` says where the unsorted data is
-// (sort_input_is_tmp(end_bit) tells the caller which of the two to fill).
-int sort_num_passes(int end_bit);
-bool sort_input_is_tmp(int end_bit);
-size_t sort_scratch_bytes(uint32_t n, int end_bit);
+// onesweep radix sort of (u64 key, u32 value) pairs, stable, on key bits [begin_bit, end_bit) (of the compressed key when
+// compress != 0).  The sorted result lands in keys_out / vals_out; keys_tmp / vals_tmp are the alternate buffers;
+// sort_input_is_tmp(begin_bit, end_bit) tells the caller which of the two to fill with the unsorted data.
+int sort_num_passes(int begin_bit, int end_bit);
+bool sort_input_is_tmp(int begin_bit, int end_bit);
+size_t sort_scratch_bytes(uint32_t n, int begin_bit, int end_bit);
 cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp,
-                                 uint32_t* vals_tmp, uint32_t n, int end_bit, int compress, void* scratch,
+                                 uint32_t* vals_tmp, uint32_t n, int begin_bit, int end_bit, int compress, void* scratch,
                                  size_t scratch_bytes);
+// per-tile (segment) stable sort of the instances on the 31 depth bits, in shared memory; keys must already be grouped
+// by global tile (ranges filled).  write_keys == 0 leaves keys_sorted grouped by tile only (vals are always sorted).
+cudaError_t launch_tile_depth_sort(cudaStream_t stream, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                                   const uint2* ranges, uint32_t n_ranges, int write_keys);
 
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,

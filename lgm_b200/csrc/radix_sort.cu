@@ -41,7 +41,8 @@ __device__ __forceinline__ uint64_t sort_bits(uint64_t k, int compress)
 // (view, tile row, depth exponent) are usually identical across a warp: a warp-uniform digit costs two REDUX and one
 // shared-memory atomic; otherwise every lane adds 1 (distinct digits -> distinct banks, few conflicts).
 __global__ void __launch_bounds__(kHistThreads)
-histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int end_bit, int compress,
+histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int begin_bit, int end_bit, int compress,
+                 int n_low /* leading passes whose digits are lane-random (depth mantissa bytes) */,
                  uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[kMaxPasses * kRadix];
@@ -64,23 +65,22 @@ histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int n_pass, int 
             const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, ok[j]));
             if (nvalid == 0) continue;  // warp-uniform
             // bits at and above end_bit are ignored (the last pass may cover fewer than 8 significant bits)
-            const uint64_t kk = end_bit < 64 ? (k[j] & ((1ull << end_bit) - 1ull)) : k[j];
+            const uint64_t kk = (end_bit < 64 ? (k[j] & ((1ull << end_bit) - 1ull)) : k[j]) >> begin_bit;
             // passes 0..2 (low mantissa bytes of the depth): digits differ across lanes, plain shared atomics
-            const int n_low = min(n_pass, 3);
             if (ok[j])
                 for (int p = 0; p < n_low; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(kk >> (p * kRadixBits)) & 0xffu)], 1u);
-            if (n_pass > 3) {
+            if (n_pass > n_low) {
                 // passes 3.. : one uniformity test (two REDUX each on the two 32-bit halves of the upper bits) covers them all
-                const uint64_t hi = kk >> 24;
+                const uint64_t hi = kk >> (n_low * kRadixBits);
                 const uint32_t h0 = (uint32_t)hi, h1 = (uint32_t)(hi >> 32);
                 const bool uni = __reduce_min_sync(0xffffffffu, ok[j] ? h0 : 0xffffffffu) == __reduce_max_sync(0xffffffffu, ok[j] ? h0 : 0u) &&
                                  __reduce_min_sync(0xffffffffu, ok[j] ? h1 : 0xffffffffu) == __reduce_max_sync(0xffffffffu, ok[j] ? h1 : 0u);
                 const uint64_t hv = __shfl_sync(0xffffffffu, hi, __ffs(__ballot_sync(0xffffffffu, ok[j])) - 1);
                 if (uni) {
                     if (lane == 0)
-                        for (int p = 3; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hv >> ((p - 3) * kRadixBits)) & 0xffu)], nvalid);
+                        for (int p = n_low; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hv >> ((p - n_low) * kRadixBits)) & 0xffu)], nvalid);
                 } else if (ok[j]) {
-                    for (int p = 3; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hi >> ((p - 3) * kRadixBits)) & 0xffu)], 1u);
+                    for (int p = n_low; p < n_pass; p++) atomicAdd(&s_hist[p * kRadix + ((uint32_t)(hi >> ((p - n_low) * kRadixBits)) & 0xffu)], 1u);
                 }
             }
         }
@@ -528,29 +528,29 @@ cudaError_t launch_pass_persistent(cudaStream_t stream, uint32_t tiles, const ui
 
 }  // namespace
 
-int sort_num_passes(int end_bit) { return (end_bit + kRadixBits - 1) / kRadixBits; }
+int sort_num_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + kRadixBits - 1) / kRadixBits; }
 // pass p reads buffer (p even ? start : other); the result of the last pass must be keys_out.
-bool sort_input_is_tmp(int end_bit) { return (sort_num_passes(end_bit) & 1) != 0; }
+bool sort_input_is_tmp(int begin_bit, int end_bit) { return (sort_num_passes(begin_bit, end_bit) & 1) != 0; }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static uint32_t tile_items() { const Variant v = kVariants[variant_index()]; return (uint32_t)(v.threads * v.items); }
 
-size_t sort_scratch_bytes(uint32_t n, int end_bit)
+size_t sort_scratch_bytes(uint32_t n, int begin_bit, int end_bit)
 {
-    const int np = sort_num_passes(end_bit);
+    const int np = sort_num_passes(begin_bit, end_bit);
     const size_t tiles = (n + tile_items() - 1) / tile_items();
     // [hist: np*256 u32][tickets: np u32 (padded)][lookback: np * tiles * 256 u32]
     return align_up((size_t)np * kRadix * 4, 256) + 256 + (size_t)np * tiles * kRadix * 4;
 }
 
 cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp,
-                                 uint32_t* vals_tmp, uint32_t n, int end_bit, int compress, void* scratch,
+                                 uint32_t* vals_tmp, uint32_t n, int begin_bit, int end_bit, int compress, void* scratch,
                                  size_t scratch_bytes)
 {
-    const int np = sort_num_passes(end_bit);
+    const int np = sort_num_passes(begin_bit, end_bit);
     if (np > kMaxPasses || np < 1) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
-    const size_t need = sort_scratch_bytes(n, end_bit);
+    const size_t need = sort_scratch_bytes(n, begin_bit, end_bit);
     if (scratch_bytes < need) return cudaErrorInvalidValue;
     const uint32_t tiles = (n + tile_items() - 1) / tile_items();
     unsigned char* sp = static_cast<unsigned char*>(scratch);
@@ -560,7 +560,7 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
     cudaError_t err = cudaMemsetAsync(scratch, 0, need, stream);
     if (err != cudaSuccess) return err;
 
-    const bool in_tmp = sort_input_is_tmp(end_bit);
+    const bool in_tmp = sort_input_is_tmp(begin_bit, end_bit);
     uint64_t* kin = in_tmp ? keys_tmp : keys_out;
     uint32_t* vin = in_tmp ? vals_tmp : vals_out;
     uint64_t* kalt = in_tmp ? keys_out : keys_tmp;
@@ -568,13 +568,16 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
 
     const uint32_t chunk = kHistThreads * kHistItems;
     const int hist_grid = (int)min((size_t)148 * 8, (size_t)(n + chunk - 1) / chunk);
-    histogram_kernel<<<hist_grid, kHistThreads, 0, stream>>>(kin, n, np, end_bit, compress, hist);
+    // passes over the low 24 bits (depth mantissa) see lane-random digits; higher digits are near-uniform per warp
+    int n_low = (24 - begin_bit + kRadixBits - 1) / kRadixBits;
+    n_low = n_low < 0 ? 0 : (n_low > np ? np : n_low);
+    histogram_kernel<<<hist_grid, kHistThreads, 0, stream>>>(kin, n, np, begin_bit, end_bit, compress, n_low, hist);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
 
     const int vi = variant_index();
     for (int p = 0; p < np; p++) {
-        const int shift = p * kRadixBits;
+        const int shift = begin_bit + p * kRadixBits;
         const int sig = end_bit - shift < kRadixBits ? end_bit - shift : kRadixBits;
         const uint32_t dmask = (1u << sig) - 1u;
         const uint32_t* h = hist + p * kRadix;

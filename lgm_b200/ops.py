@@ -131,13 +131,15 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)
     _timed("bin", lambda: _lib.check(L.lgm_forward_bin(
         s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, _lib.ptr(keys),
-        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel()), "lgm_forward_bin"))
+        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel(), 1 if cfg.keep_binning else 0),
+        "lgm_forward_bin"))
     _timed("composite_fwd", lambda: _lib.check(L.lgm_forward_composite(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.depth),
         _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), 1 if cfg.clamp_image else 0, _lib.ptr(image), _lib.ptr(alpha),
         _lib.ptr(depth_img), _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
     if n_inst > 0:
-        launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)  # emit, histogram, ranges + onesweep passes
+        # emit, histogram, ranges, 2 tile-depth-sort classes + onesweep passes over the (view|tile) bits
+        launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
     launch_counter["kernels"] += 1 if VW else 0                     # compositing
     st.keys = keys if cfg.keep_binning else None
     return image, alpha, depth_img, st
@@ -145,6 +147,11 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
 
 def sort_passes(n_global_tiles):
     return (sort_end_bit(n_global_tiles) + 7) // 8
+
+
+def tile_bit_passes(n_global_tiles):
+    """onesweep passes of the hybrid sort: the (view|tile) bits only (api.cu lgm_forward_bin)."""
+    return (sort_end_bit(n_global_tiles) - 31 + 7) // 8
 
 
 def sort_end_bit(n_global_tiles):
