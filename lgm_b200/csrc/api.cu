@@ -73,7 +73,7 @@ int key_end_bit(const lgm::RenderParams& p)
 }
 
 struct BinWorkspace {
-    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, total;
+    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, total;
 };
 BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
 {
@@ -84,6 +84,8 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     w.sort_scratch = off;
     w.sort_scratch_bytes = lgm::sort_scratch_bytes(L, 0, key_end_bit(p));  // the full sort needs the most
     off = align_up(off + w.sort_scratch_bytes, 256);
+    w.tile_scratch = off;
+    off = align_up(off + lgm::tile_sort_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
     w.total = off;
     return w;
 }
@@ -177,7 +179,7 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     LGM_CUDA(lgm::launch_tile_ranges(s, keys_sorted, L, reinterpret_cast<uint2*>(ranges)), "forward_bin: ranges");
     if (!full)
         LGM_CUDA(lgm::launch_tile_depth_sort(s, keys_sorted, vals_sorted, keys_tmp, vals_tmp, reinterpret_cast<const uint2*>(ranges),
-                                             (uint32_t)n_ranges, want_sorted_keys ? 1 : 0),
+                                             (uint32_t)n_ranges, want_sorted_keys ? 1 : 0, ws + w.tile_scratch),
                  "forward_bin: tile depth sort");
     return LGM_OK;
 }

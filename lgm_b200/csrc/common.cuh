@@ -48,8 +48,9 @@ cudaError_t launch_onesweep_sort(cudaStream_t stream, uint64_t* keys_out, uint32
                                  size_t scratch_bytes);
 // per-tile (segment) stable sort of the instances on the 31 depth bits, in shared memory; keys must already be grouped
 // by global tile (ranges filled).  write_keys == 0 leaves keys_sorted grouped by tile only (vals are always sorted).
+size_t tile_sort_scratch_bytes(uint32_t n_ranges);
 cudaError_t launch_tile_depth_sort(cudaStream_t stream, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                                   const uint2* ranges, uint32_t n_ranges, int write_keys);
+                                   const uint2* ranges, uint32_t n_ranges, int write_keys, void* scratch);
 
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
