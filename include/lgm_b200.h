@@ -80,10 +80,10 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
 /* K2 emit + K3 sort + K4 ranges.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
  * n_instances = the value forward_geom left in total_instances.  keys_sorted u64[L] (view*tiles+tile << 32 |
  * depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges uint2[n_views * tiles] = [start,end).
- * The sort is a hybrid with the same stable order as an LSD sort of the whole key: onesweep passes over the
- * (view|tile) bits, then a per-tile shared-memory radix sort of the 31 depth bits.  want_sorted_keys == 0 skips
- * writing the depth-sorted keys back (keys_sorted is then grouped by tile only; vals_sorted and ranges, which are
- * all the renderer consumes, are always final).                                                              */
+ * The sort is a stable LSD onesweep over the (compressed) key bits.  want_sorted_keys only matters in the
+ * alternative two-stage mode (environment LGM_BIN_MODE=hybrid: onesweep over the (view|tile) bits, then a per-tile
+ * shared-memory radix sort of the depth bits — same order bit for bit): 0 skips writing the depth-sorted keys back
+ * (keys_sorted is then grouped by tile only; vals_sorted and ranges, all the renderer consumes, are always final). */
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
                     uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,

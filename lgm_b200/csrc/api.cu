@@ -163,11 +163,13 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     uint64_t* keys_tmp = reinterpret_cast<uint64_t*>(ws + w.keys_tmp);
     uint32_t* vals_tmp = reinterpret_cast<uint32_t*>(ws + w.vals_tmp);
     const int end_bit = key_end_bit(p);
-    // Hybrid sort (default): onesweep passes over the (view|tile) bits only, then every tile's segment is sorted on
-    // its 31 depth bits in shared memory — the same stable order as sorting all key bits with onesweep passes
-    // (LGM_BIN_MODE=full selects that single-stage form), at a fraction of the HBM traffic.
+    // Default: one-stage LSD onesweep over all sort bits.  LGM_BIN_MODE=hybrid selects the two-stage form — onesweep
+    // passes over the (view|tile) bits only, then every tile's segment sorted on its 31 depth bits in shared memory
+    // (tile_sort.cu): same stable order bit for bit and ~1.5x less HBM traffic, but measured SLOWER on B200 in all three
+    // regimes (208-view step: bin 5.05 vs 3.94 ms; init-like 64.2 vs 49.9 ms; 1M-Gaussian 1024^2 views 37.5 vs 30.3 ms):
+    // the stable ballot ranking costs ~250 instructions per element in the per-tile sort.  Kept as a tested alternative.
     const char* mode = getenv("LGM_BIN_MODE");
-    const bool full = mode && mode[0] == 'f';
+    const bool full = !(mode && mode[0] == 'h');
     const int begin_bit = full ? 0 : 31;
     const bool in_tmp = lgm::sort_input_is_tmp(begin_bit, end_bit);
     LGM_CUDA(lgm::launch_emit(s, p, radii, reinterpret_cast<const float2*>(xy), depth, block_offsets,

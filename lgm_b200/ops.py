@@ -138,8 +138,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), 1 if cfg.clamp_image else 0, _lib.ptr(image), _lib.ptr(alpha),
         _lib.ptr(depth_img), _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
     if n_inst > 0:
-        # emit, histogram, ranges, 2 tile-depth-sort classes + onesweep passes over the (view|tile) bits
-        launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
+        launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)  # emit, histogram, ranges + onesweep passes
     launch_counter["kernels"] += 1 if VW else 0                     # compositing
     st.keys = keys if cfg.keep_binning else None
     return image, alpha, depth_img, st

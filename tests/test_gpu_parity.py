@@ -477,3 +477,23 @@ def test_sharded_renderer_single_rank_equals_renderer():
     b = ShardedGaussianRenderer(opt, device=DEV).render(g.to(DEV), cv, cvp, cp)
     assert b["views"] == (0, B * V)
     assert torch.equal(a["image"].reshape(B * V, 3, S, S), b["image"]) and torch.equal(a["alpha"].reshape(B * V, 1, S, S), b["alpha"])
+
+
+def test_hybrid_binning_mode_is_bit_identical(oracle32, monkeypatch):
+    """LGM_BIN_MODE=hybrid (onesweep over the (view|tile) bits + per-tile shared-memory depth sort, tile_sort.cu) gives
+    the same sorted keys / values / ranges as the default one-stage onesweep, short and long tiles alike."""
+    res = {}
+    for mode in ("full", "hybrid"):
+        monkeypatch.setenv("LGM_BIN_MODE", mode)
+        for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96)):   # init: tiles far above the 2048 short cap
+            g = make_gaussians(2, N, kind, seed=17).numpy()
+            cv, cvp, _ = make_cameras(2, 2, seed=17)
+            t = tan_half(49.1)
+            _, _, _, _, img, al, dp, st = _cuda_forward(g, cv, cvp, [0.5, 0.5, 0.5], S, S, t, t)
+            L = st.num_rendered
+            res[(mode, kind)] = (st.keys[:L].clone(), st.vals[:L].clone(), st.ranges.clone(), img.clone(),
+                                 int((st.ranges[:, 1] - st.ranges[:, 0]).max()))
+    for kind in ("trained", "init"):
+        a, b = res[("full", kind)], res[("hybrid", kind)]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert res[("full", "init")][4] > 2048   # the long-tile path was exercised
