@@ -133,6 +133,20 @@ int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* g
 /* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
+/* Colours from spherical harmonics — the `shs` argument of GaussianRasterizer.forward
+ * (diff_gaussian_rasterization/__init__.py: shs / sh_degree / campos; upstream computeColorFromSH in
+ * cuda_rasterizer/forward.cu and its backward in backward.cu).  LGM itself passes colors_precomp
+ * (core/gs.py:79-80); this exists so that the rasterizer class is a full drop-in.
+ *   means [P,3], campos [3], shs [P, max_coeffs, 3] (max_coeffs >= (degree+1)^2, degree in 0..3),
+ *   colors [P,3] = max(0.5 + SH(dir), 0), clamped u8[P,3] = the clamp mask the backward needs.
+ * Backward: dL_dcolor [P,3] -> dL_dshs [P, max_coeffs, 3] (inactive bands zero) and dL_dmeans [P,3] (through the
+ * normalised view direction), both overwritten. */
+int lgm_sh_forward(void* stream, int32_t n_points, int32_t degree, int32_t max_coeffs, const float* means,
+                   const float* campos, const float* shs, float* colors, uint8_t* clamped);
+int lgm_sh_backward(void* stream, int32_t n_points, int32_t degree, int32_t max_coeffs, const float* means,
+                    const float* campos, const float* shs, const uint8_t* clamped, const float* dL_dcolor,
+                    float* dL_dshs, float* dL_dmeans);
+
 /* The sort on its own (parity / benchmark hook): sorts n pairs, stably, on key bits [0, end_bit).  The unsorted
  * input must be in (keys_tmp, vals_tmp) when lgm_sort_input_is_tmp(end_bit) != 0, else in (keys_out, vals_out);
  * the result is always in (keys_out, vals_out).  compress != 0: every key has bit 31 clear (a positive float in

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "lgm_backward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
     "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i32]),
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lgm_sh_backward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sort_input_is_tmp": (ctypes.c_int, [_i32]),
     "lgm_sort_workspace_bytes": (ctypes.c_int, [_i64, _i32, ctypes.POINTER(_sz)]),
     "lgm_sort_pairs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),

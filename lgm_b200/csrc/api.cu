@@ -277,6 +277,38 @@ int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const f
     return LGM_OK;
 }
 
+static int sh_shape_ok(int32_t n_points, int32_t degree, int32_t max_coeffs)
+{
+    if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");
+    if (degree < 0 || degree > 3) return fail(LGM_ERR_BAD_SHAPE, "sh degree must be 0..3");
+    if (max_coeffs < (degree + 1) * (degree + 1)) return fail(LGM_ERR_BAD_SHAPE, "max_coeffs < (degree+1)^2");
+    return LGM_OK;
+}
+
+int lgm_sh_forward(void* stream, int32_t n_points, int32_t degree, int32_t max_coeffs, const float* means,
+                   const float* campos, const float* shs, float* colors, uint8_t* clamped)
+{
+    if (int rc = sh_shape_ok(n_points, degree, max_coeffs)) return rc;
+    if (n_points == 0) return LGM_OK;
+    LGM_NOTNULL(means); LGM_NOTNULL(campos); LGM_NOTNULL(shs); LGM_NOTNULL(colors); LGM_NOTNULL(clamped);
+    LGM_CUDA(lgm::launch_sh_forward((cudaStream_t)stream, n_points, degree, max_coeffs, means, campos, shs, colors, clamped),
+             "sh_forward");
+    return LGM_OK;
+}
+
+int lgm_sh_backward(void* stream, int32_t n_points, int32_t degree, int32_t max_coeffs, const float* means,
+                    const float* campos, const float* shs, const uint8_t* clamped, const float* dL_dcolor,
+                    float* dL_dshs, float* dL_dmeans)
+{
+    if (int rc = sh_shape_ok(n_points, degree, max_coeffs)) return rc;
+    if (n_points == 0) return LGM_OK;
+    LGM_NOTNULL(means); LGM_NOTNULL(campos); LGM_NOTNULL(shs); LGM_NOTNULL(clamped); LGM_NOTNULL(dL_dcolor);
+    LGM_NOTNULL(dL_dshs); LGM_NOTNULL(dL_dmeans);
+    LGM_CUDA(lgm::launch_sh_backward((cudaStream_t)stream, n_points, degree, max_coeffs, means, campos, shs, clamped,
+                                     dL_dcolor, dL_dshs, dL_dmeans), "sh_backward");
+    return LGM_OK;
+}
+
 int lgm_sort_input_is_tmp(int32_t end_bit) { return lgm::sort_input_is_tmp(0, end_bit) ? 1 : 0; }
 
 int lgm_sort_workspace_bytes(int64_t n, int32_t end_bit, size_t* bytes)

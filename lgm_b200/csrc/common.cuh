@@ -27,6 +27,12 @@ cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, 
                                   float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
                                   uint32_t* tiles_touched /*nullable*/, uint32_t* block_sums);
 cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, const float* view_mat, uint8_t* visible);
+// sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
+cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
+                              const float* shs, float* colors, uint8_t* clamped);
+cudaError_t launch_sh_backward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
+                               const float* shs, const uint8_t* clamped, const float* dL_dcolor, float* dL_dshs,
+                               float* dL_dmeans);
 cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
                                   const int32_t* radii, const float* grad_rows, float* dL_dgaussians, int accumulate);

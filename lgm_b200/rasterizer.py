@@ -3,8 +3,9 @@
 (color, radii, depth, alpha) and error behaviour (SURVEY.md §8b level 1) — backed by the batched sm_100a kernels
 with n_views = 1.
 
-Not on LGM's path and not implemented yet (raise NotImplementedError, never a silent fallback):
-spherical-harmonics colours (`shs`) and `cov3D_precomp` inputs.
+`shs` (spherical-harmonics colours, not on LGM's path — core/gs.py:79-80 passes colors_precomp) is served by the
+sh.cu kernels, whose output enters the renderer exactly like colors_precomp.  `cov3D_precomp` is not on LGM's path
+and is not implemented (NotImplementedError, never a silent fallback).
 """
 from typing import NamedTuple
 
@@ -71,6 +72,38 @@ class _RasterizeGaussians(torch.autograd.Function):
         return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], d[:, 4:7], d[:, 7:11], None
 
 
+class _SHToColor(torch.autograd.Function):
+    """colors [P,3] = max(0.5 + SH(normalize(means3D - campos)) . shs, 0) with the active degree of the raster
+    settings (upstream computeColorFromSH); gradients to means3D (through the view direction) and shs."""
+
+    @staticmethod
+    def forward(ctx, means3D, shs, campos, degree):
+        P = means3D.shape[0]
+        if shs.dim() != 3 or shs.shape[0] != P or shs.shape[2] != 3:
+            raise _lib.LgmError("shs must have dimensions (num_points, num_coeffs, 3)")
+        means, sh, cam = means3D.float().contiguous(), shs.float().contiguous(), campos.float().reshape(3).contiguous()
+        colors = torch.empty(P, 3, device=means.device)
+        clamped = torch.empty(P, 3, dtype=torch.uint8, device=means.device)
+        _lib.check(_lib.lib().lgm_sh_forward(ops._stream(), P, int(degree), sh.shape[1], _lib.ptr(means), _lib.ptr(cam),
+                                             _lib.ptr(sh), _lib.ptr(colors), _lib.ptr(clamped)), "lgm_sh_forward")
+        ops.launch_counter["kernels"] += 1 if P else 0
+        ctx.degree = int(degree)
+        ctx.save_for_backward(means, sh, cam, clamped)
+        return colors
+
+    @staticmethod
+    def backward(ctx, grad_colors):
+        means, sh, cam, clamped = ctx.saved_tensors
+        P = means.shape[0]
+        g = grad_colors.float().contiguous()
+        d_sh, d_means = torch.empty_like(sh), torch.empty_like(means)
+        _lib.check(_lib.lib().lgm_sh_backward(ops._stream(), P, ctx.degree, sh.shape[1], _lib.ptr(means), _lib.ptr(cam),
+                                              _lib.ptr(sh), _lib.ptr(clamped), _lib.ptr(g), _lib.ptr(d_sh),
+                                              _lib.ptr(d_means)), "lgm_sh_backward")
+        ops.launch_counter["kernels"] += 1 if P else 0
+        return d_means, d_sh, None, None
+
+
 class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
@@ -97,9 +130,6 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        if shs is not None:
-            raise NotImplementedError("lgm_b200: spherical-harmonics colours (shs) are not on LGM's path and are not "
-                                      "implemented; pass colors_precomp")
         if cov3D_precomp is not None:
             raise NotImplementedError("lgm_b200: cov3D_precomp is not on LGM's path and is not implemented; "
                                       "pass scales and rotations")
@@ -107,5 +137,8 @@ class GaussianRasterizer(nn.Module):
             raise _lib.LgmError("means3D must have dimensions (num_points, 3)")
         if not means3D.is_cuda:
             raise _lib.LgmError("lgm_b200 has no CPU path: tensors must be on a CUDA device")
+        if shs is not None:
+            rs = self.raster_settings
+            colors_precomp = _SHToColor.apply(means3D, shs, rs.campos.to(means3D.device), int(rs.sh_degree))
         return _RasterizeGaussians.apply(means3D, means2D, colors_precomp, opacities, scales, rotations,
                                          self.raster_settings)

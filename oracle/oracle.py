@@ -137,6 +137,24 @@ class Oracle:
             _p(out["dL_dcov3d"]))
         return out
 
+    # ---- SH colours (the `shs` input; not on LGM's path) -------------------------------------------
+    def sh_forward(self, means, campos, shs, deg):
+        P, M = shs.shape[0], shs.shape[1]
+        means, campos, shs = self._a(means, (P, 3)), self._a(campos, (3,)), self._a(shs, (P, M, 3))
+        colors, clamped = np.zeros((P, 3), self.dt), np.zeros((P, 3), np.uint8)
+        self.lib.orc_sh_forward(ctypes.c_int(P), ctypes.c_int(deg), ctypes.c_int(M), _p(means), _p(campos), _p(shs),
+                                _p(colors), _p(clamped))
+        return colors, clamped
+
+    def sh_backward(self, means, campos, shs, deg, clamped, dL_dcolor):
+        P, M = shs.shape[0], shs.shape[1]
+        means, campos, shs = self._a(means, (P, 3)), self._a(campos, (3,)), self._a(shs, (P, M, 3))
+        dsh, dmeans = np.zeros((P, M, 3), self.dt), np.zeros((P, 3), self.dt)
+        self.lib.orc_sh_backward(ctypes.c_int(P), ctypes.c_int(deg), ctypes.c_int(M), _p(means), _p(campos), _p(shs),
+                                 _p(np.ascontiguousarray(clamped, np.uint8)), _p(self._a(dL_dcolor, (P, 3))), _p(dsh),
+                                 _p(dmeans))
+        return dsh, dmeans
+
     # ---- single view, the GaussianRasterizer call of core/gs.py:76-85 ------------------------------
     def rasterize(self, means, scales, rots, opac, colors, view, proj, bg, W, H, tanfovx, tanfovy,
                   scale_modifier=1.0):

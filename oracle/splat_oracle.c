@@ -592,3 +592,81 @@ void orc_set_num_threads(int n)
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Spherical-harmonics colour (the `shs` input of GaussianRasterizer; upstream computeColorFromSH, not on LGM's
+ * path).  shs [P, M, 3]; active bands 0..deg; colour = max(0.5 + sum_k basis_k(dir) sh_k, 0), dir = normalize(mean -
+ * campos).  The backward is written from the basis table below (independent of the CUDA kernel's closed forms):
+ * dL/dsh_k = basis_k * g, dL/ddir = sum_k grad(basis_k) sh_k g, then through the normalisation.                 */
+static void sh_basis(int deg, real x, real y, real z, real *b, real (*db)[3])
+{
+    const real C0 = R(0.28209479177387814), C1 = R(0.4886025119029199);
+    const real C2[5] = {R(1.0925484305920792), R(-1.0925484305920792), R(0.31539156525252005), R(-1.0925484305920792), R(0.5462742152960396)};
+    const real C3[7] = {R(-0.5900435899266435), R(2.890611442640554), R(-0.4570457994644658), R(0.3731763325901154), R(-0.4570457994644658), R(1.445305721320277), R(-0.5900435899266435)};
+    for (int k = 0; k < 16; k++) { b[k] = 0; db[k][0] = db[k][1] = db[k][2] = 0; }
+    b[0] = C0;
+    if (deg > 0) {
+        b[1] = -C1 * y; db[1][1] = -C1;
+        b[2] = C1 * z;  db[2][2] = C1;
+        b[3] = -C1 * x; db[3][0] = -C1;
+    }
+    if (deg > 1) {
+        b[4] = C2[0] * x * y; db[4][0] = C2[0] * y; db[4][1] = C2[0] * x;
+        b[5] = C2[1] * y * z; db[5][1] = C2[1] * z; db[5][2] = C2[1] * y;
+        b[6] = C2[2] * (2 * z * z - x * x - y * y); db[6][0] = -2 * C2[2] * x; db[6][1] = -2 * C2[2] * y; db[6][2] = 4 * C2[2] * z;
+        b[7] = C2[3] * x * z; db[7][0] = C2[3] * z; db[7][2] = C2[3] * x;
+        b[8] = C2[4] * (x * x - y * y); db[8][0] = 2 * C2[4] * x; db[8][1] = -2 * C2[4] * y;
+    }
+    if (deg > 2) {
+        b[9] = C3[0] * y * (3 * x * x - y * y); db[9][0] = 6 * C3[0] * x * y; db[9][1] = C3[0] * (3 * x * x - 3 * y * y);
+        b[10] = C3[1] * x * y * z; db[10][0] = C3[1] * y * z; db[10][1] = C3[1] * x * z; db[10][2] = C3[1] * x * y;
+        b[11] = C3[2] * y * (4 * z * z - x * x - y * y); db[11][0] = -2 * C3[2] * x * y; db[11][1] = C3[2] * (4 * z * z - x * x - 3 * y * y); db[11][2] = 8 * C3[2] * y * z;
+        b[12] = C3[3] * z * (2 * z * z - 3 * x * x - 3 * y * y); db[12][0] = -6 * C3[3] * x * z; db[12][1] = -6 * C3[3] * y * z; db[12][2] = C3[3] * (6 * z * z - 3 * x * x - 3 * y * y);
+        b[13] = C3[4] * x * (4 * z * z - x * x - y * y); db[13][0] = C3[4] * (4 * z * z - 3 * x * x - y * y); db[13][1] = -2 * C3[4] * x * y; db[13][2] = 8 * C3[4] * x * z;
+        b[14] = C3[5] * z * (x * x - y * y); db[14][0] = 2 * C3[5] * x * z; db[14][1] = -2 * C3[5] * y * z; db[14][2] = C3[5] * (x * x - y * y);
+        b[15] = C3[6] * x * (x * x - 3 * y * y); db[15][0] = C3[6] * (3 * x * x - 3 * y * y); db[15][1] = -6 * C3[6] * x * y;
+    }
+}
+
+void orc_sh_forward(int P, int deg, int M, const real *means, const real *campos, const real *shs, real *colors,
+                    uint8_t *clamped)
+{
+    for (int i = 0; i < P; i++) {
+        real d[3] = {means[3 * i] - campos[0], means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2]};
+        real inv = R(1.0) / SQRT(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        real b[16], db[16][3];
+        sh_basis(deg, d[0] * inv, d[1] * inv, d[2] * inv, b, db);
+        int nk = (deg + 1) * (deg + 1);
+        for (int c = 0; c < 3; c++) {
+            real r = R(0.5);
+            for (int k = 0; k < nk; k++) r += b[k] * shs[((size_t)i * M + k) * 3 + c];
+            clamped[3 * i + c] = r < 0;
+            colors[3 * i + c] = r < 0 ? 0 : r;
+        }
+    }
+}
+
+void orc_sh_backward(int P, int deg, int M, const real *means, const real *campos, const real *shs,
+                     const uint8_t *clamped, const real *dL_dcolor, real *dL_dshs, real *dL_dmeans)
+{
+    for (int i = 0; i < P; i++) {
+        real d[3] = {means[3 * i] - campos[0], means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2]};
+        real inv = R(1.0) / SQRT(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        real u[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+        real b[16], db[16][3];
+        sh_basis(deg, u[0], u[1], u[2], b, db);
+        int nk = (deg + 1) * (deg + 1);
+        real gdir[3] = {0, 0, 0};
+        for (int k = 0; k < M; k++)
+            for (int c = 0; c < 3; c++) dL_dshs[((size_t)i * M + k) * 3 + c] = 0;
+        for (int c = 0; c < 3; c++) {
+            real g = clamped[3 * i + c] ? 0 : dL_dcolor[3 * i + c];
+            for (int k = 0; k < nk; k++) {
+                dL_dshs[((size_t)i * M + k) * 3 + c] = b[k] * g;
+                for (int a = 0; a < 3; a++) gdir[a] += db[k][a] * shs[((size_t)i * M + k) * 3 + c] * g;
+            }
+        }
+        real dot = u[0] * gdir[0] + u[1] * gdir[1] + u[2] * gdir[2];
+        for (int a = 0; a < 3; a++) dL_dmeans[3 * i + a] = (gdir[a] - u[a] * dot) * inv;
+    }
+}

@@ -497,3 +497,51 @@ def test_hybrid_binning_mode_is_bit_identical(oracle32, monkeypatch):
         a, b = res[("full", kind)], res[("hybrid", kind)]
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
     assert res[("full", "init")][4] > 2048   # the long-tile path was exercised
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_colours_match_oracle(oracle32, oracle64, deg):
+    """lgm_sh_forward / lgm_sh_backward (the `shs` input of GaussianRasterizer) against the oracle."""
+    from lgm_b200.rasterizer import _SHToColor
+    rng = np.random.RandomState(10 + deg)
+    P, M = 4099, 16
+    means, campos, shs = rng.randn(P, 3).astype(np.float32), np.array([0.3, -0.2, 2.0], np.float32), (rng.randn(P, M, 3) * 0.5).astype(np.float32)
+    w = rng.randn(P, 3).astype(np.float32)
+    tm = torch.tensor(means, device="cuda", requires_grad=True)
+    ts = torch.tensor(shs, device="cuda", requires_grad=True)
+    col = _SHToColor.apply(tm, ts, torch.tensor(campos, device="cuda"), deg)
+    (col * torch.tensor(w, device="cuda")).sum().backward()
+    ref, cl = oracle64.sh_forward(means, campos, shs, deg)
+    # a colour within rounding of the clamp may land on either side of it; exclude those rows from the gradient check
+    safe = (np.abs(ref) > 1e-5).all(axis=1)
+    assert np.abs(col.detach().cpu().numpy() - ref).max() <= 1e-5
+    dsh, dm = oracle64.sh_backward(means, campos, shs, deg, cl, w)
+    got_sh, got_m = ts.grad.cpu().numpy(), tm.grad.cpu().numpy()
+    assert (got_sh[:, (deg + 1) ** 2:] == 0).all()
+    assert np.abs(got_sh - dsh)[safe].max() <= 1e-5 * max(1.0, np.abs(dsh).max())
+    assert np.abs(got_m - dm)[safe].max() <= 1e-4 * max(1.0, np.abs(dm).max())
+
+
+def test_rasterizer_with_shs_matches_precomputed_colours(oracle64):
+    """GaussianRasterizer(shs=...) == GaussianRasterizer(colors_precomp = oracle SH colours), and the gradient reaches
+    shs and means3D through the SH stage."""
+    from lgm_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    N, S, deg = 3000, 64, 2
+    g = make_gaussians(1, N, "trained", seed=3)[0]
+    g[:, 4:7] *= 5.0
+    cv, cvp, cp = make_cameras(1, 1, seed=3)
+    t = tan_half(49.1)
+    rs = GaussianRasterizationSettings(image_height=S, image_width=S, tanfovx=t, tanfovy=t, bg=torch.ones(3, device=DEV),
+                                       scale_modifier=1.0, viewmatrix=cv[0, 0].to(DEV), projmatrix=cvp[0, 0].to(DEV),
+                                       sh_degree=deg, campos=cp[0, 0].to(DEV), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    shs = (0.4 * torch.randn(N, 9, 3, generator=torch.Generator().manual_seed(0))).float()
+    leaf = lambda x: x.clone().to(DEV).contiguous().requires_grad_(True)
+    m3, sh = leaf(g[:, 0:3]), leaf(shs)
+    args = dict(opacities=g[:, 3:4].to(DEV), scales=g[:, 4:7].to(DEV), rotations=g[:, 7:11].to(DEV))
+    img, radii, depth, alpha = rast(m3, torch.zeros_like(m3), shs=sh, **args)
+    col_ref, _ = oracle64.sh_forward(g[:, 0:3].numpy(), cp[0, 0].numpy(), shs.numpy(), deg)
+    img2, *_ = rast(g[:, 0:3].to(DEV), torch.zeros_like(m3), colors_precomp=torch.tensor(col_ref, dtype=torch.float32, device=DEV), **args)
+    assert (img - img2).abs().max().item() <= 1e-5
+    img.sum().backward()
+    assert sh.grad.abs().sum().item() > 0 and torch.isfinite(sh.grad).all() and torch.isfinite(m3.grad).all()

@@ -42,7 +42,7 @@ def test_argument_exclusivity_errors():
         r(m, m2, o, colors_precomp=c)
     with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
         r(m, m2, o, colors_precomp=c, scales=s, rotations=q, cov3D_precomp=torch.zeros(P, 6))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(LgmError, match="no CPU path"):  # shs is served (sh.cu), but only on the GPU
         r(m, m2, o, shs=torch.zeros(P, 1, 3), scales=s, rotations=q)
     with pytest.raises(NotImplementedError):
         r(m, m2, o, colors_precomp=c, cov3D_precomp=torch.zeros(P, 6))

@@ -219,3 +219,33 @@ def test_render_step_matches_single_view_loop(oracle32):
             dg[b, :, 0:3] += gr["dL_dmeans"]; dg[b, :, 3] += gr["dL_dopacity"]; dg[b, :, 4:7] += gr["dL_dscales"]
             dg[b, :, 7:11] += gr["dL_drots"]; dg[b, :, 11:14] += gr["dL_dcolor"]
     np.testing.assert_allclose(r["dgaussians"], dg, rtol=1e-4, atol=1e-5 * np.abs(dg).max())
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_backward_matches_finite_differences(oracle64, deg):
+    """orc_sh_backward (basis-table form) against central differences of orc_sh_forward in fp64."""
+    rng = np.random.RandomState(deg)
+    P, M = 5, 16
+    means, campos, shs = rng.randn(P, 3), np.array([0.3, -0.2, 2.0]), rng.randn(P, M, 3) * 0.5
+    w = rng.randn(P, 3)
+    col, cl = oracle64.sh_forward(means, campos, shs, deg)
+    dsh, dm = oracle64.sh_backward(means, campos, shs, deg, cl, w)
+    assert (col >= 0).all() and ((col == 0) == (cl == 1)).all()
+    assert (dsh[:, (deg + 1) ** 2:] == 0).all()
+
+    def loss(m, s):
+        return float((oracle64.sh_forward(m, campos, s, deg)[0] * w).sum())
+
+    eps = 1e-6
+    for idx in np.ndindex(means.shape):
+        a, b = means.copy(), means.copy()
+        a[idx] += eps
+        b[idx] -= eps
+        num = (loss(a, shs) - loss(b, shs)) / (2 * eps)
+        assert abs(num - dm[idx]) <= 1e-6 * max(1.0, abs(num))
+    for idx in list(np.ndindex(shs.shape))[::5]:
+        a, b = shs.copy(), shs.copy()
+        a[idx] += eps
+        b[idx] -= eps
+        num = (loss(means, a) - loss(means, b)) / (2 * eps)
+        assert abs(num - dsh[idx]) <= 1e-6 * max(1.0, abs(num))
