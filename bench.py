@@ -14,8 +14,8 @@ broadcast from rank 0, per-Gaussian gradients are combined with one NCCL all-red
 
 Prints ONE JSON line (rank 0).  `value` = whole-job views/s with inputs resident in HBM; `e2e` = the same metric
 with, every step, the step's inputs (Gaussians, cameras, ground-truth images and masks) copied from pinned host
-memory and the loss read back; `roofline` = the onesweep sort (dominant HBM-bound kernel group), algorithmic bytes /
-CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port on a bounded sample.
+memory and the loss read back; `roofline` = the HBM-bound group K1-K4 (preprocess + binning), SURVEY.md 8d's algorithmic
+bytes / CUDA-event time against MEASURED_PEAKS.json (the onesweep sort alone is reported beside it); `cpu_baseline` = the CPU oracle port on a bounded sample.
 """
 import argparse
 import json
@@ -361,25 +361,40 @@ def run_native(args):
         peak, peak_src = load_peaks()
         sort_bytes = (npass * 24 + 8) * Lr
         ach = sort_bytes / (t_sort * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": f"onesweep radix sort (histogram + {npass} passes, u64 key + u32 value)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # DRAM bytes from the ncu --set full capture of this workload (profiles/r01_summary.md):
-                    # 752 + 716 MB per pass and 498 MB for the histogram at L = 62.2 M -> 23.6 and 8.0 B per pair
-                    "traffic": int((npass * 23.6 + 8.0) * Lr),
-                    "traffic_source": "profiles/r01_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per pair, scaled by L)",
-                    "peak_source": peak_src, "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
-                    "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
-        # SURVEY §8d group accounting: preprocess + emit + sort + ranges
+        onesweep_sort = {"kernel": f"onesweep radix sort alone (histogram + {npass} passes, u64 key + u32 value)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         # DRAM bytes from the ncu --set full capture (profiles/r01_summary.md): 23.6 B per pair per
+                         # pass and 8.0 B per pair for the histogram
+                         "traffic": int((npass * 23.6 + 8.0) * Lr), "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
+                         "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
+        # roofline.achieved = (B_pre + B_emit + B_sort + B_rng) x n_views / t(K1..K4), with
+        # B_pre = 80 P, B_emit = 20 P + 12 L, B_sort = n_pass x 24 L + 8 L (n_pass = 6: an LSD sort of the 41..48-bit
+        # keys), B_rng = 8 L + 8 tiles.  t(K1..K4) = the geom + bin stages of the step (CUDA events around the C-ABI calls).
+        # The binning path the step actually took is named; the direct path (count / scatter / per-tile shared-memory
+        # sort) moves ~20 B per instance instead of the definition's 152, so `implemented_bytes` is given beside it.
         P_ = N
-        grp_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
+        bin_mode = ops.last_bin_mode["mode"]
+        grp_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + (6 * 24 + 8) * Lr + 8 * Lr + 8 * n_local * n_tiles
+        if bin_mode == "direct":
+            impl_bytes = n_local * (80 * P_ + 2 * 12 * P_ + 4 * P_) + 20 * Lr + 20 * n_local * n_tiles
+            # dram__bytes_read.sum + dram__bytes_write.sum of K1 + D1..D4 from the ncu --set full capture, per instance
+            traffic = None
+        else:
+            impl_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
+            traffic = int(n_local * 100 * P_ + 12 * Lr + (npass * 23.6 + 8.0) * Lr + 8 * Lr)
         t_grp = stages.get("geom", 0.0) + stages.get("bin", 0.0)
+        ach_grp = grp_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None
+        roofline = {"bound": "hbm", "kernel": f"K1-K4 group: preprocess + binning ({bin_mode} path)",
+                    "achieved": ach_grp, "peak": peak, "unit": "GB/s", "frac": ach_grp / peak if ach_grp else None,
+                    "traffic": traffic, "traffic_source": "profiles/r01_summary.md (ncu --set full, dram bytes per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes": int(grp_bytes), "implemented_bytes": int(impl_bytes),
+                    "achieved_implemented": impl_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
+                    "ms": t_grp, "definition": "SURVEY.md 8d: (80P+20P) per view + (12 + 6*24+8 + 8) per instance + 8 per tile"}
         lens = (st.ranges[:, 1] - st.ranges[:, 0]).long()
         pair_evals = int(lens.sum()) * 256
         extra = {
             "instances_per_step_rank0": Lr, "instances_per_view": Lr / max(n_local, 1), "sort_variants_ms": sort_variants,
-            "roofline_preprocess_sort": {"bound": "hbm", "achieved": grp_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
-                                         "peak": peak, "unit": "GB/s", "frac": (grp_bytes / (t_grp * 1e-3) / 1e9) / peak if t_grp > 0 else None,
-                                         "algorithmic_bytes": int(grp_bytes), "ms": t_grp},
+            "bin_mode": bin_mode, "onesweep_sort": onesweep_sort,
             "composite": {"pair_evals_upper_bound": pair_evals,
                           "fwd_gpairs_per_s": pair_evals / (stages.get("composite_fwd", float("nan")) * 1e-3) / 1e9,
                           "bwd_gpairs_per_s": pair_evals / (stages.get("composite_bwd", float("nan")) * 1e-3) / 1e9,

@@ -80,10 +80,15 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
 /* K2 emit + K3 sort + K4 ranges.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
  * n_instances = the value forward_geom left in total_instances.  keys_sorted u64[L] (view*tiles+tile << 32 |
  * depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges uint2[n_views * tiles] = [start,end).
- * The sort is a stable LSD onesweep over the (compressed) key bits.  want_sorted_keys only matters in the
- * alternative two-stage mode (environment LGM_BIN_MODE=hybrid: onesweep over the (view|tile) bits, then a per-tile
- * shared-memory radix sort of the depth bits — same order bit for bit): 0 skips writing the depth-sorted keys back
- * (keys_sorted is then grouped by tile only; vals_sorted and ranges, all the renderer consumes, are always final). */
+ * The list order is upstream's: by tile, then depth bits, ties in emit order (ascending value).  Three internal
+ * paths produce it bit for bit (lgm_last_bin_mode tells which ran; environment LGM_BIN_MODE=direct|onesweep|hybrid
+ * forces one):
+ *   direct   (default when every tile fits the per-tile shared-memory sort) count -> scan -> scatter -> per-tile
+ *            sort; costs one extra 4-byte device->host readback (the longest tile) inside this call;
+ *   onesweep a stable LSD onesweep radix sort over the (compressed) 64-bit keys (heavy tiles);
+ *   hybrid   onesweep over the (view|tile) bits, then a per-tile radix sort of the depth bits.
+ * want_sorted_keys == 0 lets direct / hybrid skip writing keys_sorted (its contents are then unspecified);
+ * vals_sorted and ranges, all the renderer consumes, are always final. */
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
                     uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
@@ -131,6 +136,13 @@ int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* g
                       const float* grad_rows, float* dL_dgaussians, int32_t accumulate);
 
 /* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
+/* Which binning path the calling thread's last lgm_forward_bin took (diagnostics / launch accounting). */
+#define LGM_BIN_NONE 0
+#define LGM_BIN_ONESWEEP 1
+#define LGM_BIN_HYBRID 2
+#define LGM_BIN_DIRECT 3
+int lgm_last_bin_mode(void);
+
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
 /* Colours from spherical harmonics — the `shs` argument of GaussianRasterizer.forward

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "lgm_backward": (ctypes.c_int, [_vp, _pp] + [_vp] * 19 + [_i32]),
     "lgm_backward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
     "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i32]),
+    "lgm_last_bin_mode": (ctypes.c_int, []),
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sh_backward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

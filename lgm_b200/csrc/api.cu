@@ -73,7 +73,7 @@ int key_end_bit(const lgm::RenderParams& p)
 }
 
 struct BinWorkspace {
-    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, total;
+    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, direct_scratch, total;
 };
 BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
 {
@@ -86,15 +86,23 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     off = align_up(off + w.sort_scratch_bytes, 256);
     w.tile_scratch = off;
     off = align_up(off + lgm::tile_sort_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
+    w.direct_scratch = off;
+    off = align_up(off + lgm::direct_bin_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
     w.total = off;
     return w;
 }
+
+thread_local int g_last_bin_mode = LGM_BIN_NONE;
+// the direct path is tried when the MEAN tile holds at most this many instances (a longer mean makes a tile above
+// the shared-memory capacity near certain, and the count pass would be wasted)
+constexpr uint64_t kDirectMaxMeanTile = 2048;
 
 }  // namespace
 
 extern "C" {
 
 int lgm_abi_version(void) { return 1; }
+int lgm_last_bin_mode(void) { return g_last_bin_mode; }
 const char* lgm_last_error_string(void) { return g_err; }
 
 int lgm_tiles_per_view(int32_t H, int32_t W) { return ((W + 15) / 16) * ((H + 15) / 16); }
@@ -169,7 +177,32 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     // regimes (208-view step: bin 5.05 vs 3.94 ms; init-like 64.2 vs 49.9 ms; 1M-Gaussian 1024^2 views 37.5 vs 30.3 ms):
     // the stable ballot ranking costs ~250 instructions per element in the per-tile sort.  Kept as a tested alternative.
     const char* mode = getenv("LGM_BIN_MODE");
-    const bool full = !(mode && mode[0] == 'h');
+    const char m0 = mode ? mode[0] : 'a';
+    // Auto (default): the DIRECT path (direct_bin.cu: count, scan, scatter, per-tile shared-memory sort — no global
+    // radix sort, 20 B instead of 152 B of HBM traffic per instance) whenever every tile fits its shared-memory sort.
+    // That needs the longest tile: a second 4-byte readback, after the count pass.  Steps with heavy tiles (untrained
+    // Gaussians, 1024^2 views of 1M Gaussians) take the onesweep path below; LGM_BIN_MODE=onesweep|hybrid|direct forces.
+    g_last_bin_mode = LGM_BIN_NONE;
+    if (m0 == 'd' || (m0 == 'a' && (uint64_t)L <= kDirectMaxMeanTile * (uint64_t)n_ranges)) {
+        const uint32_t* longest_dev = nullptr;
+        LGM_CUDA(lgm::launch_direct_bin_count(s, p, radii, reinterpret_cast<const float2*>(xy), reinterpret_cast<uint2*>(ranges),
+                                              ws + w.direct_scratch, &longest_dev),
+                 "forward_bin: tile count");
+        uint32_t longest = 0;
+        LGM_CUDA(cudaMemcpyAsync(&longest, longest_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "forward_bin: longest tile");
+        LGM_CUDA(cudaStreamSynchronize(s), "forward_bin: longest tile sync");
+        if ((int)longest <= lgm::direct_bin_tile_cap()) {
+            LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
+                                                 reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
+                                                 want_sorted_keys ? keys_sorted : nullptr, ws + w.direct_scratch),
+                     "forward_bin: direct sort");
+            g_last_bin_mode = LGM_BIN_DIRECT;
+            return LGM_OK;
+        }
+        LGM_CUDA(cudaMemsetAsync(ranges, 0, n_ranges * sizeof(uint2), s), "forward_bin: memset ranges");
+    }
+    const bool full = m0 != 'h';
+    g_last_bin_mode = full ? LGM_BIN_ONESWEEP : LGM_BIN_HYBRID;
     const int begin_bit = full ? 0 : 31;
     const bool in_tmp = lgm::sort_input_is_tmp(begin_bit, end_bit);
     LGM_CUDA(lgm::launch_emit(s, p, radii, reinterpret_cast<const float2*>(xy), depth, block_offsets,

@@ -27,6 +27,15 @@ cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, 
                                   float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
                                   uint32_t* tiles_touched /*nullable*/, uint32_t* block_sums);
 cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, const float* view_mat, uint8_t* visible);
+// direct_bin.cu: count -> scan -> scatter -> per-tile shared-memory sort (no global radix sort); a step whose longest
+// tile exceeds direct_bin_tile_cap() must use the onesweep path
+int direct_bin_tile_cap();
+size_t direct_bin_scratch_bytes(uint32_t n_ranges);
+cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                                    uint2* ranges, void* scratch, const uint32_t** longest_tile_dev);
+cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                                   const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
+                                   uint64_t* keys_sorted, void* scratch);
 // sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
 cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
                               const float* shs, float* colors, uint8_t* clamped);

@@ -1,0 +1,282 @@
+// direct_bin.cu — "direct" binning: the (view|tile|depth) order of the sorted instance list WITHOUT a global radix
+// sort.  Same output, bit for bit, as emit + onesweep + tile ranges (binning.cu / radix_sort.cu), i.e. as upstream's
+// duplicateWithKeys + cub::DeviceRadixSort::SortPairs + identifyTileRanges:
+//
+//   D1  count     one thread per (view, Gaussian): one RED per touched tile into tile_counts[global tile]
+//   D2  scan      exclusive scan of the counts (scan_block_sums_kernel) = every tile's [start, end) in the final list
+//       ranges    ranges[] written from counts + offsets (empty tiles stay (0,0)), non-empty tiles appended to a work
+//                 list, longest tile recorded
+//   D3  scatter   same enumeration as D1; each instance takes a slot of its tile's segment with one atomic and stores
+//                 (value, depth bits) there — 8 B, in arbitrary order inside the segment
+//   D4  tile sort one CTA per non-empty tile orders its segment in SHARED MEMORY by the 64-bit key
+//                 (depth bits << 32 | value) and writes the values (and, on request, the upstream 64-bit keys)
+//
+// Why the order is exact: inside one tile the stable LSD sort leaves instances ordered by depth bits, ties in emit
+// order; emit order inside one tile is ascending value (value = view * P + Gaussian index, each Gaussian touches a
+// tile once).  So the final order of a tile is ascending (depth bits, value) — a total order on unique keys, which any
+// correct sort reproduces no matter in which order the atomics of D3 filled the segment.
+//
+// D4 is a bucket sort: keys are mapped monotonically to ~n/2 buckets by (depth - min) * nb / (range + 1), counted and
+// grouped with shared-memory atomics (two sweeps), and each element finds its final slot by counting the smaller keys
+// in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
+// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  A tile longer than kSortCap cannot be staged
+// in shared memory: the caller (api.cu) reads the longest tile back and uses the onesweep path for such a step.
+#include "common.cuh"
+#include "splat_math.cuh"
+
+namespace lgm {
+namespace {
+
+constexpr int kSortThreads = 512;
+constexpr int kSortCap = 5632;      // elements of one tile staged in shared memory (11 per thread)
+constexpr int kMaxBuckets = 2048;
+constexpr size_t kSortSmem = (size_t)kSortCap * 8 + (size_t)kSortCap * 2 + (size_t)(kMaxBuckets + 1) * 4 + 32 * 4;
+constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
+
+// D1 / D3 share the enumeration.  SCATTER = false: counts[gtile] += 1.  SCATTER = true: counts[] (now holding the
+// totals) is counted back down, the returned value - 1 is the slot inside the tile's segment.
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock)
+tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+                      const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
+                      uint2* __restrict__ pairs)
+{
+    const int view = blockIdx.y;
+    const int idx = blockIdx.x * kBlock + threadIdx.x;
+    const size_t gi = (size_t)view * prm.P + idx;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t area = 0;
+    if (idx < prm.P) {
+        const int r = radii[gi];
+        if (r > 0) {
+            const float2 p = xy[gi];
+            tile_rect(p.x, p.y, r, prm.gx, prm.gy, x0, y0, x1, y1);
+            area = (uint32_t)((x1 - x0) * (y1 - y0));
+        }
+    }
+    const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    uint32_t dbits = 0;
+    if (SCATTER && area) dbits = __float_as_uint(depth[gi]);
+    const uint32_t val = (uint32_t)gi;
+    const bool big = area > kCoopAreaD;
+
+    if (area != 0 && !big) {
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                const uint32_t gt = tile_base + (uint32_t)(y * prm.gx + x);
+                if (SCATTER) {
+                    const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
+                    pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
+                } else {
+                    atomicAdd(&counts[gt], 1u);
+                }
+            }
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t a = __shfl_sync(0xffffffffu, area, src);
+        const uint32_t sx0 = __shfl_sync(0xffffffffu, (uint32_t)x0, src), sy0 = __shfl_sync(0xffffffffu, (uint32_t)y0, src);
+        const uint32_t w = __shfl_sync(0xffffffffu, (uint32_t)(x1 - x0), src);
+        const uint32_t sd = __shfl_sync(0xffffffffu, dbits, src), sv = __shfl_sync(0xffffffffu, val, src);
+        for (uint32_t i = lane; i < a; i += 32) {
+            const uint32_t ry = i / w, rx = i - ry * w;
+            const uint32_t gt = tile_base + (sy0 + ry) * (uint32_t)prm.gx + sx0 + rx;
+            if (SCATTER) {
+                const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
+                pairs[ranges[gt].x + slot] = make_uint2(sv, sd);
+            } else {
+                atomicAdd(&counts[gt], 1u);
+            }
+        }
+    }
+}
+
+// ranges from counts + offsets; non-empty tiles -> work list (warp-aggregated append); head[0] = list length,
+// head[1] = work cursor (zeroed by the caller), head[2] = longest tile
+__global__ void __launch_bounds__(kBlock)
+tile_ranges_from_counts_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t n_ranges,
+                               uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
+{
+    const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = t < n_ranges ? counts[t] : 0u;
+    if (t < n_ranges) ranges[t] = n ? make_uint2(offsets[t], offsets[t] + n) : make_uint2(0u, 0u);
+    const unsigned m = __ballot_sync(0xffffffffu, n != 0u);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&head[0], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (n) list[base + __popc(m & ((1u << lane) - 1u))] = t;
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, n);
+    if (lane == leader) atomicMax(&head[2], mx);
+}
+
+// D4.  Persistent CTAs pull tiles from the work list.
+__global__ void __launch_bounds__(kSortThreads, 3)
+tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ list,
+                        uint32_t* __restrict__ head, uint32_t* __restrict__ vals_sorted, uint64_t* __restrict__ keys_sorted)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);                                // [kSortCap] depth << 32 | value
+    uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSortCap * 8);      // [kSortCap] bucket-grouped indices
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 10);    // [kMaxBuckets + 1]
+    uint32_t* s_red = bucket + kMaxBuckets + 1;                                          // [32]
+    __shared__ uint32_t s_item;
+    constexpr int T = kSortThreads, kWarps = T / 32;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t n_list = head[0];
+
+    while (true) {
+        if (t == 0) s_item = atomicAdd(&head[1], 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_list) break;
+        const uint32_t tile = list[item];
+        const uint2 range = ranges[tile];
+        const int n = (int)(range.y - range.x);
+        const uint2* src = pairs + range.x;
+        if (n > kSortCap) {  // cannot happen: api.cu only takes this path when the longest tile fits
+            __syncthreads();
+            continue;
+        }
+
+        // number of buckets: a power of two in [n/2, n), 32..kMaxBuckets
+        int lg_nb = 32 - __clz((unsigned)max(n - 1, 1)) - 1;
+        lg_nb = min(max(lg_nb, 5), 11);
+        const int nb = 1 << lg_nb;
+
+        // sweep 0: stage, min / max of the depth bits
+        uint32_t dmin = 0xffffffffu, dmax = 0u;
+        for (int i = t; i < n; i += T) {
+            const uint2 p = src[i];
+            A[i] = ((uint64_t)p.y << 32) | p.x;
+            dmin = min(dmin, p.y);
+            dmax = max(dmax, p.y);
+        }
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0) { s_red[warp] = dmin; s_red[kWarps + warp] = dmax; }
+        for (int i = t; i <= nb; i += T) bucket[i] = 0u;
+        __syncthreads();  // also orders the read of s_item above against the next iteration's write
+        dmin = __reduce_min_sync(0xffffffffu, s_red[lane & (kWarps - 1)]);
+        dmax = __reduce_max_sync(0xffffffffu, s_red[kWarps + (lane & (kWarps - 1))]);
+        // monotone map of depth bits to buckets: floor((d - dmin) * nb / (span + 1)), or d - dmin when span < nb
+        const uint32_t span = dmax - dmin;
+        const bool direct = span < (uint32_t)nb;
+        const uint32_t mul = direct ? 0u : (uint32_t)((((uint64_t)nb) << 32) / ((uint64_t)span + 1ull));
+#define LGM_BUCKET(d) (direct ? ((d) - dmin) : __umulhi((d) - dmin, mul))
+
+        // sweep 1: bucket sizes
+        for (int i = t; i < n; i += T) atomicAdd(&bucket[LGM_BUCKET((uint32_t)(A[i] >> 32))], 1u);
+        __syncthreads();
+
+        // exclusive scan of the nb sizes (each thread owns nb / T consecutive buckets, or one when nb < T)
+        {
+            const int per = nb >= T ? nb / T : 1;
+            const int b0 = t * per;
+            uint32_t sum = 0;
+            if (b0 < nb)
+                for (int j = 0; j < per; j++) sum += bucket[b0 + j];
+            const uint32_t incl = warp_incl_scan(sum, lane);
+            if (lane == 31) s_red[warp] = incl;
+            __syncthreads();
+            uint32_t base = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) base += (w < warp) ? s_red[w] : 0u;
+            uint32_t run = base + incl - sum;
+            if (b0 < nb)
+                for (int j = 0; j < per; j++) {
+                    const uint32_t c = bucket[b0 + j];
+                    bucket[b0 + j] = run;
+                    run += c;
+                }
+        }
+        __syncthreads();
+
+        // sweep 2: group the element indices by bucket; bucket[b] runs from the bucket's start to its end
+        for (int i = t; i < n; i += T) {
+            const uint32_t pos = atomicAdd(&bucket[LGM_BUCKET((uint32_t)(A[i] >> 32))], 1u);
+            order[pos] = (uint16_t)i;
+        }
+        __syncthreads();
+
+        // sweep 3: final slot = bucket start + number of smaller keys in the bucket
+        const uint64_t hi = (uint64_t)tile << 32;
+        for (int p = t; p < n; p += T) {
+            const uint64_t key = A[order[p]];
+            const uint32_t b = LGM_BUCKET((uint32_t)(key >> 32));
+            const uint32_t s0 = b ? bucket[b - 1] : 0u, e0 = bucket[b];
+            uint32_t rank = 0;
+            for (uint32_t q = s0; q < e0; q++) rank += (A[order[q]] < key) ? 1u : 0u;
+            const uint32_t out = range.x + s0 + rank;
+            vals_sorted[out] = (uint32_t)key;
+            if (keys_sorted) keys_sorted[out] = hi | (key >> 32);
+        }
+#undef LGM_BUCKET
+        __syncthreads();  // shared memory is reused by the next tile
+    }
+}
+
+}  // namespace
+
+int direct_bin_tile_cap() { return kSortCap; }
+
+// small arrays of the direct path: counts [n_ranges], offsets [n_ranges], list [n_ranges], head [64 u32],
+// total [1 u64 + pad]
+size_t direct_bin_scratch_bytes(uint32_t n_ranges) { return ((size_t)n_ranges * 3 + 64 + 16) * sizeof(uint32_t); }
+
+static inline uint32_t* db_counts(void* scratch) { return static_cast<uint32_t*>(scratch) + 64 + 16; }
+
+// D1 + D2: after this, head[2] (device) holds the longest tile.  `scratch` as direct_bin_scratch_bytes.
+cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                                    uint2* ranges, void* scratch, const uint32_t** longest_tile_dev)
+{
+    const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
+    uint32_t* head = static_cast<uint32_t*>(scratch);
+    unsigned long long* total = reinterpret_cast<unsigned long long*>(head + 64);
+    uint32_t* counts = db_counts(scratch);
+    uint32_t* offsets = counts + n_ranges;
+    uint32_t* list = offsets + n_ranges;
+    cudaError_t err = cudaMemsetAsync(scratch, 0, ((size_t)n_ranges + 64 + 16) * sizeof(uint32_t), stream);  // head, total, counts
+    if (err != cudaSuccess) return err;
+    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
+    tile_enumerate_kernel<false><<<grid, kBlock, 0, stream>>>(prm, radii, xy, nullptr, counts, nullptr, nullptr);
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    if ((err = launch_scan_block_sums(stream, counts, n_ranges, offsets, total)) != cudaSuccess) return err;
+    tile_ranges_from_counts_kernel<<<(n_ranges + kBlock - 1) / kBlock, kBlock, 0, stream>>>(counts, offsets, n_ranges, ranges, list, head);
+    *longest_tile_dev = head + 2;
+    return cudaGetLastError();
+}
+
+// D3 + D4.  pairs: L x 8 B of workspace.  keys_sorted may be null (keys not wanted).
+cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                                   const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
+                                   uint64_t* keys_sorted, void* scratch)
+{
+    const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
+    uint32_t* head = static_cast<uint32_t*>(scratch);
+    uint32_t* counts = db_counts(scratch);
+    const uint32_t* list = counts + 2 * (size_t)n_ranges;
+    static int n_sm = 0;
+    if (!n_sm) {
+        cudaError_t e = cudaFuncSetAttribute(tile_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
+    tile_enumerate_kernel<true><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, ranges, static_cast<uint2*>(pairs));
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
+    tile_bucket_sort_kernel<<<n_cta, kSortThreads, kSortSmem, stream>>>(static_cast<const uint2*>(pairs), ranges, list, head,
+                                                                        vals_sorted, keys_sorted);
+    return cudaGetLastError();
+}
+
+}  // namespace lgm

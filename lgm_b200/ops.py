@@ -18,6 +18,8 @@ MAX_PAIRS_PER_CALL = 1 << 28        # (view, Gaussian) pairs per launch group: ~
 
 # launch accounting for bench.py's "gpu_launches" (kernels this library enqueues; memsets not counted)
 launch_counter = {"kernels": 0}
+BIN_MODES = {0: "none", 1: "onesweep", 2: "hybrid", 3: "direct"}
+last_bin_mode = {"mode": "none"}
 
 # Optional per-stage CUDA-event timing (bench.py's stage breakdown; off in normal use).  When enabled, every stage
 # call is bracketed by events on the launching stream; read with stage_times_ms() after a synchronize.
@@ -138,7 +140,14 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), 1 if cfg.clamp_image else 0, _lib.ptr(image), _lib.ptr(alpha),
         _lib.ptr(depth_img), _lib.ptr(st.n_contrib)), "lgm_forward_composite"))
     if n_inst > 0:
-        launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)  # emit, histogram, ranges + onesweep passes
+        mode = int(L.lgm_last_bin_mode())
+        last_bin_mode["mode"] = BIN_MODES.get(mode, "none")
+        if mode == 3:    # count, scan, ranges, scatter, tile sort
+            launch_counter["kernels"] += 5
+        elif mode == 2:  # emit, histogram, tile-bit passes, ranges, short + long tile sort
+            launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
+        else:            # emit, histogram, ranges + onesweep passes
+            launch_counter["kernels"] += 3 + sort_passes(VW * n_tiles)
     launch_counter["kernels"] += 1 if VW else 0                     # compositing
     st.keys = keys if cfg.keep_binning else None
     return image, alpha, depth_img, st

@@ -479,24 +479,70 @@ def test_sharded_renderer_single_rank_equals_renderer():
     assert torch.equal(a["image"].reshape(B * V, 3, S, S), b["image"]) and torch.equal(a["alpha"].reshape(B * V, 1, S, S), b["alpha"])
 
 
-def test_hybrid_binning_mode_is_bit_identical(oracle32, monkeypatch):
-    """LGM_BIN_MODE=hybrid (onesweep over the (view|tile) bits + per-tile shared-memory depth sort, tile_sort.cu) gives
-    the same sorted keys / values / ranges as the default one-stage onesweep, short and long tiles alike."""
-    res = {}
-    for mode in ("full", "hybrid"):
-        monkeypatch.setenv("LGM_BIN_MODE", mode)
-        for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96)):   # init: tiles far above the 2048 short cap
-            g = make_gaussians(2, N, kind, seed=17).numpy()
-            cv, cvp, _ = make_cameras(2, 2, seed=17)
-            t = tan_half(49.1)
-            _, _, _, _, img, al, dp, st = _cuda_forward(g, cv, cvp, [0.5, 0.5, 0.5], S, S, t, t)
-            L = st.num_rendered
-            res[(mode, kind)] = (st.keys[:L].clone(), st.vals[:L].clone(), st.ranges.clone(), img.clone(),
-                                 int((st.ranges[:, 1] - st.ranges[:, 0]).max()))
-    for kind in ("trained", "init"):
-        a, b = res[("full", kind)], res[("hybrid", kind)]
-        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-    assert res[("full", "init")][4] > 2048   # the long-tile path was exercised
+def _bin_result(monkeypatch, mode, g, cv, cvp, S):
+    from lgm_b200 import ops
+    monkeypatch.setenv("LGM_BIN_MODE", mode)
+    t = tan_half(49.1)
+    _, _, _, _, img, al, dp, st = _cuda_forward(g, cv, cvp, [0.5, 0.5, 0.5], S, S, t, t)
+    L = st.num_rendered
+    return dict(keys=st.keys[:L].clone(), vals=st.vals[:L].clone(), ranges=st.ranges.clone(), img=img.clone(),
+                longest=int((st.ranges[:, 1] - st.ranges[:, 0]).max()), ran=ops.last_bin_mode["mode"], L=L)
+
+
+def _same_binning(a, b):
+    return all(torch.equal(a[k], b[k]) for k in ("keys", "vals", "ranges", "img"))
+
+
+def test_binning_modes_are_bit_identical(monkeypatch):
+    """The three binning paths of lgm_forward_bin — direct (count / scatter / per-tile shared-memory sort, direct_bin.cu),
+    onesweep (one LSD sort of the 64-bit keys) and hybrid (onesweep on the tile bits + per-tile radix sort) — give the
+    same sorted keys / values / ranges / image, light and heavy tiles alike; direct hands a step whose longest tile
+    exceeds its shared-memory capacity to onesweep."""
+    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 30000, 64)):
+        g = make_gaussians(2, N, kind, seed=17).numpy()
+        cv, cvp, _ = make_cameras(2, 2, seed=17)
+        res = {m: _bin_result(monkeypatch, m, g, cv, cvp, S) for m in ("onesweep", "hybrid", "direct", "auto")}
+        assert res["onesweep"]["ran"] == "onesweep" and res["hybrid"]["ran"] == "hybrid"
+        for m in ("hybrid", "direct", "auto"):
+            assert _same_binning(res["onesweep"], res[m]), f"{kind} N={N}: mode {m} differs from onesweep"
+        longest = res["onesweep"]["longest"]
+        assert res["direct"]["ran"] == ("direct" if longest <= 5632 else "onesweep"), (longest, res["direct"]["ran"])
+        if kind == "trained":
+            assert res["auto"]["ran"] == "direct"
+    assert longest > 5632  # the last case exercised the hand-over
+
+
+def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
+    """Direct binning on inputs made to hurt it: (a) every Gaussian duplicated 4x — equal depth bits inside every tile,
+    so the order must fall back to ascending Gaussian index exactly as the stable sort's tie-break; (b) one plane of
+    Gaussians at a single view-space depth (all keys of a tile in ONE bucket); (c) tiles close to the shared-memory
+    capacity."""
+    cv, cvp, _ = make_cameras(1, 3, seed=5)
+    # (a) duplicates
+    g = make_gaussians(1, 3000, "trained", seed=5)
+    g[:, :, 4:7] *= 6.0
+    g = g.repeat(1, 4, 1).contiguous().numpy()
+    a, b = _bin_result(monkeypatch, "onesweep", g, cv, cvp, 96), _bin_result(monkeypatch, "direct", g, cv, cvp, 96)
+    assert b["ran"] == "direct" and _same_binning(a, b)
+    k = a["keys"].cpu().numpy().view(np.uint64)
+    assert (k[1:] == k[:-1]).mean() > 0.5  # most neighbours tie on the full 64-bit key
+    # (b) a plane facing the first camera: identical depth for view 0 (up to rounding), spread for the others
+    g2 = make_gaussians(1, 4000, "trained", seed=6)
+    c2w = torch.linalg.inv(cv[0, 0].T)
+    right, up, fwd, pos = c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3]
+    uv = torch.rand(4000, 2, generator=torch.Generator().manual_seed(1)) - 0.5
+    g2[0, :, 0:3] = pos + 1.5 * fwd + uv[:, :1] * right + uv[:, 1:] * up
+    g2[0, :, 4:7] = 0.02
+    g2 = g2.numpy()
+    a, b = _bin_result(monkeypatch, "onesweep", g2, cv, cvp, 96), _bin_result(monkeypatch, "direct", g2, cv, cvp, 96)
+    assert a["L"] > 0 and b["ran"] == "direct" and _same_binning(a, b)
+    # (c) tiles of 3-5.6 k instances
+    g3 = make_gaussians(1, 60000, "trained", seed=7)
+    g3[:, :, 4:7] *= 3.0
+    g3 = g3.numpy()
+    a, b = _bin_result(monkeypatch, "onesweep", g3, cv, cvp, 64), _bin_result(monkeypatch, "direct", g3, cv, cvp, 64)
+    assert _same_binning(a, b)
+    assert a["longest"] > 2048, a["longest"]
 
 
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
