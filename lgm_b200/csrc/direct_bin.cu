@@ -2,12 +2,14 @@
 // sort.  Same output, bit for bit, as emit + onesweep + tile ranges (binning.cu / radix_sort.cu), i.e. as upstream's
 // duplicateWithKeys + cub::DeviceRadixSort::SortPairs + identifyTileRanges:
 //
-//   D1  count     one thread per (view, Gaussian): one RED per touched tile into tile_counts[global tile]
+//   D1  count     per (view, Gaussian): +1 per touched tile, aggregated per CTA in shared memory, then one global
+//                 atomic per (CTA, touched tile) into tile_counts[global tile]
 //   D2  scan      exclusive scan of the counts (scan_block_sums_kernel) = every tile's [start, end) in the final list
 //       ranges    ranges[] written from counts + offsets (empty tiles stay (0,0)), non-empty tiles appended to a work
 //                 list, longest tile recorded
-//   D3  scatter   same enumeration as D1; each instance takes a slot of its tile's segment with one atomic and stores
-//                 (value, depth bits) there — 8 B, in arbitrary order inside the segment
+//   D3  scatter   same enumeration as D1; each CTA reserves a run of every touched tile's segment with one global atomic,
+//                 its instances take the slots of the run (shared-memory atomics) and store (value, depth bits) there —
+//                 8 B, in arbitrary order inside the segment
 //   D4  tile sort one CTA per non-empty tile orders its segment in SHARED MEMORY by the 64-bit key
 //                 (depth bits << 32 | value) and writes the values (and, on request, the upstream 64-bit keys)
 //
@@ -21,6 +23,8 @@
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
 // for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  A tile longer than kSortCap cannot be staged
 // in shared memory: the caller (api.cu) reads the longest tile back and uses the onesweep path for such a step.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "splat_math.cuh"
 
@@ -33,16 +37,14 @@ constexpr int kMaxBuckets = 2048;
 constexpr size_t kSortSmem = (size_t)kSortCap * 8 + (size_t)kSortCap * 2 + (size_t)(kMaxBuckets + 1) * 4 + 32 * 4;
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
-// D1 / D3 share the enumeration.  SCATTER = false: counts[gtile] += 1.  SCATTER = true: counts[] (now holding the
-// totals) is counted back down, the returned value - 1 is the slot inside the tile's segment.
-template <bool SCATTER>
-__global__ void __launch_bounds__(kBlock)
-tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
-                      const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
-                      uint2* __restrict__ pairs)
+// Calls f(tile index inside the view, value, depth bits) once per (Gaussian, touched tile) for the Gaussian `idx` of
+// `view` held by this thread; footprints above kCoopAreaD tiles are enumerated by the whole warp (lanes across the
+// rect), so every lane of the warp must make this call together.
+template <bool WITH_DEPTH, typename F>
+__device__ __forceinline__ void for_each_touched_tile(const RenderParams& prm, const int32_t* __restrict__ radii,
+                                                      const float2* __restrict__ xy, const float* __restrict__ depth,
+                                                      int view, int idx, F&& f)
 {
-    const int view = blockIdx.y;
-    const int idx = blockIdx.x * kBlock + threadIdx.x;
     const size_t gi = (size_t)view * prm.P + idx;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     uint32_t area = 0;
@@ -54,23 +56,13 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
             area = (uint32_t)((x1 - x0) * (y1 - y0));
         }
     }
-    const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
     uint32_t dbits = 0;
-    if (SCATTER && area) dbits = __float_as_uint(depth[gi]);
+    if (WITH_DEPTH && area) dbits = __float_as_uint(depth[gi]);
     const uint32_t val = (uint32_t)gi;
     const bool big = area > kCoopAreaD;
-
     if (area != 0 && !big) {
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const uint32_t gt = tile_base + (uint32_t)(y * prm.gx + x);
-                if (SCATTER) {
-                    const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
-                    pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
-                } else {
-                    atomicAdd(&counts[gt], 1u);
-                }
-            }
+            for (int x = x0; x < x1; x++) f((uint32_t)(y * prm.gx + x), val, dbits);
     }
     const int lane = threadIdx.x & 31;
     unsigned m = __ballot_sync(0xffffffffu, big);
@@ -83,15 +75,94 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
         const uint32_t sd = __shfl_sync(0xffffffffu, dbits, src), sv = __shfl_sync(0xffffffffu, val, src);
         for (uint32_t i = lane; i < a; i += 32) {
             const uint32_t ry = i / w, rx = i - ry * w;
-            const uint32_t gt = tile_base + (sy0 + ry) * (uint32_t)prm.gx + sx0 + rx;
-            if (SCATTER) {
-                const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
-                pairs[ranges[gt].x + slot] = make_uint2(sv, sd);
-            } else {
-                atomicAdd(&counts[gt], 1u);
-            }
+            f((sy0 + ry) * (uint32_t)prm.gx + sx0 + rx, sv, sd);
         }
     }
+}
+
+// D1 / D3.  A CTA owns kEnumItems x 256 consecutive Gaussians of one view and aggregates in shared memory first: with
+// ~170 non-empty tiles per view, every one of the 62 M instances of a step going to global memory on its own piles
+// ~1,750 same-address atomics on each counter (measured: 2.8 ms count + 3.8 ms scatter, 4 % issue utilisation).
+// Per-CTA histograms cut the global atomics to one per (CTA, touched tile).
+//   SCATTER = false: counts[gtile] += this CTA's instances of the tile.
+//   SCATTER = true : counts[] (holding the totals) is counted back down by the CTA's number, which reserves a
+//                    contiguous run of the tile's segment; the CTA's instances take the slots of that run.
+constexpr int kEnumItems = 8;
+constexpr int kEnumMaxTiles = 6144;  // 2 x 4 B per tile of dynamic shared memory must stay under the default 48 KB
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock)
+tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+                      const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
+                      uint2* __restrict__ pairs)
+{
+    extern __shared__ uint32_t s_enum[];
+    uint32_t* s_hist = s_enum;                 // [n_tiles] instances of this CTA per tile, then the fill cursor
+    uint32_t* s_base = s_enum + prm.n_tiles;   // [n_tiles] first slot of this CTA's run (SCATTER)
+    const int view = blockIdx.y;
+    const int first = blockIdx.x * (kBlock * kEnumItems) + threadIdx.x;
+    const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < kEnumItems; k++)
+        for_each_touched_tile<false>(prm, radii, xy, depth, view, first + k * kBlock,
+                                     [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); });
+    __syncthreads();
+    for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
+        const uint32_t c = s_hist[i];
+        if (c == 0u) continue;
+        if (SCATTER) {
+            s_base[i] = ranges[tile_base + i].x + atomicSub(&counts[tile_base + i], c) - c;
+            s_hist[i] = 0u;
+        } else {
+            atomicAdd(&counts[tile_base + i], c);
+        }
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < kEnumItems; k++)
+        for_each_touched_tile<true>(prm, radii, xy, depth, view, first + k * kBlock,
+                                    [&](uint32_t tl, uint32_t val, uint32_t dbits) {
+                                        pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, dbits);
+                                    });
+}
+
+// the same without the shared-memory stage, for views of more than kEnumMaxTiles tiles
+template <bool SCATTER>
+__global__ void __launch_bounds__(kBlock)
+tile_enumerate_global_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+                             const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
+                             uint2* __restrict__ pairs)
+{
+    const int view = blockIdx.y;
+    const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    for_each_touched_tile<SCATTER>(prm, radii, xy, depth, view, blockIdx.x * kBlock + threadIdx.x,
+                                   [&](uint32_t tl, uint32_t val, uint32_t dbits) {
+                                       const uint32_t gt = tile_base + tl;
+                                       if (SCATTER) {
+                                           const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
+                                           pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
+                                       } else {
+                                           atomicAdd(&counts[gt], 1u);
+                                       }
+                                   });
+}
+
+template <bool SCATTER>
+cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
+                                  const float* depth, uint32_t* counts, const uint2* ranges, uint2* pairs)
+{
+    const bool force_global = getenv("LGM_ENUM_GLOBAL") != nullptr;  // test hook for the large-view variant
+    if (prm.n_tiles <= kEnumMaxTiles && !force_global) {
+        dim3 grid((prm.P + kBlock * kEnumItems - 1) / (kBlock * kEnumItems), prm.n_views);
+        tile_enumerate_kernel<SCATTER><<<grid, kBlock, (size_t)prm.n_tiles * 8, stream>>>(prm, radii, xy, depth, counts, ranges, pairs);
+    } else {
+        dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
+        tile_enumerate_global_kernel<SCATTER><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, ranges, pairs);
+    }
+    return cudaGetLastError();
 }
 
 // ranges from counts + offsets; non-empty tiles -> work list (warp-aggregated append); head[0] = list length,
@@ -164,10 +235,13 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
         __syncthreads();  // also orders the read of s_item above against the next iteration's write
         dmin = __reduce_min_sync(0xffffffffu, s_red[lane & (kWarps - 1)]);
         dmax = __reduce_max_sync(0xffffffffu, s_red[kWarps + (lane & (kWarps - 1))]);
-        // monotone map of depth bits to buckets: floor((d - dmin) * nb / (span + 1)), or d - dmin when span < nb
+        // monotone map of depth bits to buckets: floor((d - dmin) * mul / 2^32) with mul <= nb * 2^32 / (span + 1), so
+        // that the largest key lands below nb; any smaller mul is still monotone, so a 32-bit quotient that rounds
+        // the divisor up is enough (it leaves < 0.1 % of the buckets unused at the usual span / nb ~ 2^11).  d - dmin
+        // itself when the span is below the bucket count.
         const uint32_t span = dmax - dmin;
         const bool direct = span < (uint32_t)nb;
-        const uint32_t mul = direct ? 0u : (uint32_t)((((uint64_t)nb) << 32) / ((uint64_t)span + 1ull));
+        const uint32_t mul = direct ? 0u : 0xffffffffu / (((span + 1u) >> lg_nb) + 1u);
 #define LGM_BUCKET(d) (direct ? ((d) - dmin) : __umulhi((d) - dmin, mul))
 
         // sweep 1: bucket sizes
@@ -184,9 +258,7 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
             const uint32_t incl = warp_incl_scan(sum, lane);
             if (lane == 31) s_red[warp] = incl;
             __syncthreads();
-            uint32_t base = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) base += (w < warp) ? s_red[w] : 0u;
+            const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? s_red[lane] : 0u);  // warp < kWarps <= 32
             uint32_t run = base + incl - sum;
             if (b0 < nb)
                 for (int j = 0; j < per; j++) {
@@ -243,9 +315,7 @@ cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm
     uint32_t* list = offsets + n_ranges;
     cudaError_t err = cudaMemsetAsync(scratch, 0, ((size_t)n_ranges + 64 + 16) * sizeof(uint32_t), stream);  // head, total, counts
     if (err != cudaSuccess) return err;
-    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
-    tile_enumerate_kernel<false><<<grid, kBlock, 0, stream>>>(prm, radii, xy, nullptr, counts, nullptr, nullptr);
-    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, counts, nullptr, nullptr)) != cudaSuccess) return err;
     if ((err = launch_scan_block_sums(stream, counts, n_ranges, offsets, total)) != cudaSuccess) return err;
     tile_ranges_from_counts_kernel<<<(n_ranges + kBlock - 1) / kBlock, kBlock, 0, stream>>>(counts, offsets, n_ranges, ranges, list, head);
     *longest_tile_dev = head + 2;
@@ -269,9 +339,7 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
-    tile_enumerate_kernel<true><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, ranges, static_cast<uint2*>(pairs));
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, counts, ranges, static_cast<uint2*>(pairs));
     if (err != cudaSuccess) return err;
     const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
     tile_bucket_sort_kernel<<<n_cta, kSortThreads, kSortSmem, stream>>>(static_cast<const uint2*>(pairs), ranges, list, head,

@@ -519,11 +519,12 @@ def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
     capacity."""
     cv, cvp, _ = make_cameras(1, 3, seed=5)
     # (a) duplicates
-    g = make_gaussians(1, 3000, "trained", seed=5)
-    g[:, :, 4:7] *= 6.0
+    g = make_gaussians(1, 1500, "trained", seed=5)
+    g[:, :, 4:7] *= 4.0
     g = g.repeat(1, 4, 1).contiguous().numpy()
     a, b = _bin_result(monkeypatch, "onesweep", g, cv, cvp, 96), _bin_result(monkeypatch, "direct", g, cv, cvp, 96)
-    assert b["ran"] == "direct" and _same_binning(a, b)
+    assert b["ran"] == "direct", a["longest"]
+    assert _same_binning(a, b)
     k = a["keys"].cpu().numpy().view(np.uint64)
     assert (k[1:] == k[:-1]).mean() > 0.5  # most neighbours tie on the full 64-bit key
     # (b) a plane facing the first camera: identical depth for view 0 (up to rounding), spread for the others
@@ -535,7 +536,8 @@ def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
     g2[0, :, 4:7] = 0.02
     g2 = g2.numpy()
     a, b = _bin_result(monkeypatch, "onesweep", g2, cv, cvp, 96), _bin_result(monkeypatch, "direct", g2, cv, cvp, 96)
-    assert a["L"] > 0 and b["ran"] == "direct" and _same_binning(a, b)
+    assert a["L"] > 0 and b["ran"] == "direct", (a["L"], a["longest"])
+    assert _same_binning(a, b)
     # (c) tiles of 3-5.6 k instances
     g3 = make_gaussians(1, 60000, "trained", seed=7)
     g3[:, :, 4:7] *= 3.0
@@ -543,6 +545,10 @@ def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
     a, b = _bin_result(monkeypatch, "onesweep", g3, cv, cvp, 64), _bin_result(monkeypatch, "direct", g3, cv, cvp, 64)
     assert _same_binning(a, b)
     assert a["longest"] > 2048, a["longest"]
+    # (d) the count / scatter variant without the per-CTA shared-memory stage (views of more than 6144 tiles)
+    monkeypatch.setenv("LGM_ENUM_GLOBAL", "1")
+    c = _bin_result(monkeypatch, "direct", g3, cv, cvp, 64)
+    assert c["ran"] == b["ran"] and _same_binning(a, c)
 
 
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
