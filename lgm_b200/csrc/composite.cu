@@ -5,10 +5,13 @@
 //
 // Work skipping that cannot change a result: while Gaussians are staged in shared memory, the staging thread also
 // derives, ONCE per Gaussian, a conservative screen-space box outside of which alpha = min(0.99, o * exp(power)) is
-// certainly < 1/255 (the reference's skip threshold) and from it an 8-bit mask of the tile's eight 8x4-pixel patches
-// the Gaussian can reach.  Each warp owns one patch; per 32 staged Gaussians one ballot of the warp's mask bit selects
-// the Gaussians to evaluate — with the reference's exact, pinned per-pair arithmetic (splat_math.cuh).  A skipped pair
-// is one the reference evaluates and then discards.
+// certainly < 1/255 (the reference's skip threshold) and from it a bit mask of the tile's pixel patches the Gaussian can
+// reach.  A warp owns an 8x4-pixel region made of NSUB = 32 / LANES patches (LANES = 32: one 8x4 patch, 16: two 4x4,
+// 8: four 4x2); per 32 staged Gaussians one ballot per patch selects the Gaussians that patch must evaluate, and the
+// patches of a warp walk their own lists side by side (each lane group reads its own staged record) — with the
+// reference's exact, pinned per-pair arithmetic (splat_math.cuh).  A skipped pair is one the reference evaluates and
+// then discards.  Smaller patches waste fewer lanes on the small Gaussians of a trained scene: on the 208-view step the
+// warp iterations drop to 0.79x (4x4) / 0.68x (4x2) of the 8x4 count.
 //
 // Scheduling: after culling, the work of the 8 warps of a tile is uneven, so block barriers are the enemy.  512 (fwd)
 // / 768 (bwd) Gaussians (24 / 36 KB of the SM's 227 KB shared memory) are staged per barrier — most tiles need one or
@@ -26,6 +29,7 @@ namespace {
 // Gaussians: fwd 3.64 / 3.53 / 3.56 / 3.62 / 4.75 ms and bwd 7.07 / 6.85 / 6.77 / 7.42 / 8.09 ms at 256 / 512 / 768 / 1024 / 1536.
 constexpr int kFwdBatch = 512;
 constexpr int kBwdBatch = 768;
+constexpr int kPatchLanes = 32;  // lanes per pixel patch (LGM_PATCH_LANES overrides): 32 = 8x4, 16 = 4x4, 8 = 4x2 pixels
 constexpr uint32_t kClampFlag0 = 1u << 29;      // n_contrib bits 29..31: colour channel 0..2 was clamped
 constexpr uint32_t kContribMask = kClampFlag0 - 1u;
 constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 test (fp32 rounding of power / expf / logf)
@@ -34,50 +38,75 @@ constexpr float kCullPix = 0.02f;     // pixels
 
 struct __align__(16) Staged {
     float4 p0;    // px, py, conic xx, conic xy
-    float4 p1;    // conic yy, opacity, row index (view * P + idx) as bits, 8-bit patch mask as bits
+    float4 p1;    // conic yy, opacity, row index (view * P + idx) as bits, patch mask as bits
     float4 rgbd;  // r, g, b, depth
 };
 static_assert(sizeof(Staged) == 48, "staged record is three 16-byte vectors");
 
-// A warp owns an 8x4 pixel patch of the tile (compact footprint; 32-byte row segments on store): patch w of the tile
-// is column (w & 1), row (w >> 1).
+// Geometry of the patches.  Warp w owns the 8x4 region at column (w & 1), row (w >> 1) of the tile; its lanes are
+// split into NSUB groups of LANES, group s owning a PW x PH patch of the region.  Patch bits are numbered row-major
+// over the tile's grid of (16 / PW) x (16 / PH) patches.
+template <int LANES>
+struct Patch {
+    static constexpr int NSUB = 32 / LANES;
+    static constexpr int PW = LANES == 32 ? 8 : 4, PH = LANES == 8 ? 2 : 4;
+    static constexpr int NCOLS = kTile / PW, NROWS = kTile / PH;
+    // offset of patch s inside the warp's 8x4 region
+    static __device__ __forceinline__ int sub_x(int s) { return LANES == 32 ? 0 : (LANES == 16 ? s * 4 : (s & 1) * 4); }
+    static __device__ __forceinline__ int sub_y(int s) { return LANES == 8 ? (s >> 1) * 2 : 0; }
+    static __device__ __forceinline__ int bit(int warp, int s)
+    {
+        const int x = (warp & 1) * 8 + sub_x(s), y = (warp >> 1) * 4 + sub_y(s);
+        return (y / PH) * NCOLS + x / PW;
+    }
+};
+
+template <int LANES>
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
 {
+    using PT = Patch<LANES>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
-    py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    const int s = lane / LANES, sl = lane % LANES;
+    px = tile_x * kTile + (warp & 1) * 8 + PT::sub_x(s) + (sl % PT::PW);
+    py = tile_y * kTile + (warp >> 1) * 4 + PT::sub_y(s) + (sl / PT::PW);
 }
 
-// Which of the tile's eight 8x4 patches can this Gaussian reach with alpha >= 1/255 ?  (bit w = patch w)
+// Which of the tile's patches can this Gaussian reach with alpha >= 1/255 ?
 // alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. 0.5 d^T Q d <= tau = ln(255 o) with
 // Q = [[cx, cy], [cy, cz]]: an ellipse around the centre with axis-aligned half extents
 //   hx = sqrt(2 tau cz / det Q),  hy = sqrt(2 tau cx / det Q)          (+ safety margins for fp32 rounding).
-// Computed ONCE per staged Gaussian by its staging thread; each warp then only tests its bit.
+// Computed ONCE per staged Gaussian by its staging thread; each patch then only tests its bit.
 // 255 o <= 1: never visible (mask 0).  Q not positive definite (or NaN): the region is unbounded, all patches.
+template <int LANES>
 __device__ __forceinline__ uint32_t patch_mask(float px, float py, const float4 co, float tile_x0, float tile_y0)
 {
+    using PT = Patch<LANES>;
+    constexpr uint32_t kAll = (PT::NCOLS * PT::NROWS == 32) ? 0xffffffffu : ((1u << (PT::NCOLS * PT::NROWS)) - 1u);
     const float k = 255.0f * co.w;
     if (k <= 1.0f) return 0u;
     const float det = co.x * co.z - co.y * co.y;
-    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return 0xffu;
+    if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return kAll;
     const float t2 = 2.0f * __logf(k) * kCullScale + kCullPad;
     const float inv = __fdividef(t2, det);
     const float hx = sqrtf(co.z * inv) * kCullScale + kCullPix, hy = sqrtf(co.x * inv) * kCullScale + kCullPix;
     const float lo_x = px - hx - tile_x0, hi_x = px + hx - tile_x0;  // extent relative to the tile origin
     const float lo_y = py - hy - tile_y0, hi_y = py + hy - tile_y0;
-    // columns cover pixel centres [0,7] and [8,15]; rows [0,3], [4,7], [8,11], [12,15].  NaN compares false -> keep.
-    const uint32_t c0 = !(hi_x < 0.0f) && !(lo_x > 7.0f), c1 = !(hi_x < 8.0f) && !(lo_x > 15.0f);
-    const uint32_t cols = c0 | (c1 << 1);
+    // patch column c covers pixel centres [c PW, c PW + PW - 1], row r [r PH, r PH + PH - 1].  NaN compares false -> keep.
+    uint32_t cols = 0;
+#pragma unroll
+    for (int c = 0; c < PT::NCOLS; c++)
+        cols |= (!(hi_x < (float)(c * PT::PW)) && !(lo_x > (float)(c * PT::PW + PT::PW - 1))) ? (1u << c) : 0u;
     uint32_t m = 0;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const bool row = !(hi_y < 4.0f * r) && !(lo_y > 4.0f * r + 3.0f);
-        m |= row ? (cols << (2 * r)) : 0u;
+    for (int r = 0; r < PT::NROWS; r++) {
+        const bool row = !(hi_y < (float)(r * PT::PH)) && !(lo_y > (float)(r * PT::PH + PT::PH - 1));
+        m |= row ? (cols << (PT::NCOLS * r)) : 0u;
     }
     return m;
 }
 
 // Gather one instance (row g of the per-(view,Gaussian) arrays + its colour) into a staged record.
+template <int LANES>
 __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view_base, const float* __restrict__ scene_g,
                                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                                           const float* __restrict__ depth, float tile_x0, float tile_y0)
@@ -86,10 +115,26 @@ __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view
     const float4 co = conic_opacity[g];
     const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
     dst.p0 = make_float4(p.x, p.y, co.x, co.y);
-    dst.p1 = make_float4(co.z, co.w, __uint_as_float(g), __uint_as_float(patch_mask(p.x, p.y, co, tile_x0, tile_y0)));
+    dst.p1 = make_float4(co.z, co.w, __uint_as_float(g), __uint_as_float(patch_mask<LANES>(p.x, p.y, co, tile_x0, tile_y0)));
     dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
 }
 
+// The per-patch hit lists of one group of 32 staged records: lane jl offers the mask of record jl (0 = not a
+// candidate); the lanes of patch s get the ballot of that patch's bit.
+template <int LANES>
+__device__ __forceinline__ unsigned patch_hits(uint32_t mk, int warp, int sub)
+{
+    using PT = Patch<LANES>;
+    unsigned m = 0;
+#pragma unroll
+    for (int s = 0; s < PT::NSUB; s++) {
+        const unsigned bs = __ballot_sync(0xffffffffu, (mk >> PT::bit(warp, s)) & 1u);
+        m = (sub == s) ? bs : m;
+    }
+    return m;
+}
+
+template <int LANES>
 __global__ void __launch_bounds__(kBlock, 6)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -108,7 +153,8 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const int tile_y = tile / prm.gx, tile_x = tile - tile_y * prm.gx;
     const int scene = view_scene[view];
     int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
+    pixel_of_thread<LANES>(tile_x, tile_y, px, py);
+    const int sub = lane / LANES;
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
     const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
@@ -126,16 +172,16 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffer
         const int nb = min(batch, todo - r0);
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+            stage_one<LANES>(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
-            if (__all_sync(0xffffffffu, done)) break;  // every pixel of the patch is saturated (or outside)
+            if (__all_sync(0xffffffffu, done)) break;  // every pixel of the warp's region is saturated (or outside)
             const int jl = base + lane;
-            bool hit = false;
-            if (jl < nb) hit = (__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u;
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = base + __ffs(m) - 1;
+            unsigned m = patch_hits<LANES>(jl < nb ? __float_as_uint(s_rec[jl].p1.w) : 0u, warp, sub);
+            // the patches walk their lists side by side; a patch whose list is exhausted idles (act = false)
+            while (LANES == 32 ? (m != 0u) : __any_sync(0xffffffffu, m != 0u)) {
+                const bool act = m != 0u;
+                const int j = base + (act ? __ffs(m) - 1 : 0);
                 m &= m - 1;
                 const float4 p0 = s_rec[j].p0;
                 const float4 p1 = s_rec[j].p1;
@@ -145,7 +191,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
                 // A.4 in predicate form: skip if power > 0 or alpha < 1/255; stop (without compositing) if T would
                 // fall below 1e-4; otherwise composite.  Lanes that do not composite add exact zeros.
-                const bool cand = !done && !(power > 0.0f) && !(a < kAlphaMin);
+                const bool cand = act && !done && !(power > 0.0f) && !(a < kAlphaMin);
                 const bool stop = cand && (test_T < kTEps);
                 const bool comp = cand && !stop;
                 done = done || stop;
@@ -185,44 +231,45 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     }
 }
 
-// Sum 10 per-lane values over the warp with 14 shuffles (recursive halving: at each of the first three steps a lane
-// keeps half of its values and hands the other half to its partner).  On return lane L holds
-//   A  = sum over lanes of a[4*b4 + 2*b3 + b2]   (b4,b3,b2 = bits 4,3,2 of L; all four lanes of a quad agree)
-//   Bv = sum over lanes of b[b4]
-template <bool DEPTH>
-__device__ __forceinline__ void warp_reduce_10(const float (&a)[8], const float (&b)[2], int lane, float& A, float& Bv)
+// Sum 10 per-lane values over each group of LANES lanes by recursive halving: at each of the first three steps a lane
+// keeps half of its values and hands the other half to its partner (14 / 12 / 10 shuffles at LANES = 32 / 16 / 8).
+// With h1, h2, h3 = the lane's bits LANES/2, LANES/4, LANES/8, on return the lane holds
+//   A  = sum over the group of a[4 h1 + 2 h2 + h3]      (all lanes that agree on h1..h3 hold the same sum)
+//   Bv = sum over the group of b[h1]                    (DEPTH = false: b[1] is identically zero, Bv = sum of b[0])
+template <int LANES, bool DEPTH>
+__device__ __forceinline__ void group_reduce_10(const float (&a)[8], const float (&b)[2], int lane, float& A, float& Bv)
 {
     const unsigned full = 0xffffffffu;
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-    float k0 = h16 ? a[4] : a[0], k1 = h16 ? a[5] : a[1], k2 = h16 ? a[6] : a[2], k3 = h16 ? a[7] : a[3];
-    const float s0 = h16 ? a[0] : a[4], s1 = h16 ? a[1] : a[5], s2 = h16 ? a[2] : a[6], s3 = h16 ? a[3] : a[7];
-    // without a depth gradient b[1] is identically zero: every lane keeps b[0] and lane 1 ends with the full sum
-    float bk = DEPTH ? (h16 ? b[1] : b[0]) : b[0];
-    const float bs = DEPTH ? (h16 ? b[0] : b[1]) : b[0];
-    k0 += __shfl_xor_sync(full, s0, 16);
-    k1 += __shfl_xor_sync(full, s1, 16);
-    k2 += __shfl_xor_sync(full, s2, 16);
-    k3 += __shfl_xor_sync(full, s3, 16);
-    bk += __shfl_xor_sync(full, bs, 16);  // DEPTH = false: a plain butterfly, all lanes end with sum b[0]
-    float m0 = h8 ? k2 : k0, m1 = h8 ? k3 : k1;
-    const float t0 = h8 ? k0 : k2, t1 = h8 ? k1 : k3;
-    m0 += __shfl_xor_sync(full, t0, 8);
-    m1 += __shfl_xor_sync(full, t1, 8);
-    bk += __shfl_xor_sync(full, bk, 8);
-    A = h4 ? m1 : m0;
-    const float u = h4 ? m0 : m1;
-    A += __shfl_xor_sync(full, u, 4);
-    bk += __shfl_xor_sync(full, bk, 4);
-    A += __shfl_xor_sync(full, A, 2);
-    bk += __shfl_xor_sync(full, bk, 2);
-    A += __shfl_xor_sync(full, A, 1);
-    bk += __shfl_xor_sync(full, bk, 1);
+    const bool h1 = lane & (LANES / 2), h2 = lane & (LANES / 4), h3 = lane & (LANES / 8);
+    float k0 = h1 ? a[4] : a[0], k1 = h1 ? a[5] : a[1], k2 = h1 ? a[6] : a[2], k3 = h1 ? a[7] : a[3];
+    const float s0 = h1 ? a[0] : a[4], s1 = h1 ? a[1] : a[5], s2 = h1 ? a[2] : a[6], s3 = h1 ? a[3] : a[7];
+    float bk = DEPTH ? (h1 ? b[1] : b[0]) : b[0];
+    const float bs = DEPTH ? (h1 ? b[0] : b[1]) : b[0];
+    k0 += __shfl_xor_sync(full, s0, LANES / 2);
+    k1 += __shfl_xor_sync(full, s1, LANES / 2);
+    k2 += __shfl_xor_sync(full, s2, LANES / 2);
+    k3 += __shfl_xor_sync(full, s3, LANES / 2);
+    bk += __shfl_xor_sync(full, bs, LANES / 2);  // DEPTH = false: a plain butterfly, all lanes end with sum b[0]
+    float m0 = h2 ? k2 : k0, m1 = h2 ? k3 : k1;
+    const float t0 = h2 ? k0 : k2, t1 = h2 ? k1 : k3;
+    m0 += __shfl_xor_sync(full, t0, LANES / 4);
+    m1 += __shfl_xor_sync(full, t1, LANES / 4);
+    bk += __shfl_xor_sync(full, bk, LANES / 4);
+    A = h3 ? m1 : m0;
+    const float u = h3 ? m0 : m1;
+    A += __shfl_xor_sync(full, u, LANES / 8);
+    bk += __shfl_xor_sync(full, bk, LANES / 8);
+#pragma unroll
+    for (int o = LANES / 16; o >= 1; o >>= 1) {
+        A += __shfl_xor_sync(full, A, o);
+        bk += __shfl_xor_sync(full, bk, o);
+    }
     Bv = bk;
 }
 
 // DEPTH: whether a gradient w.r.t. the depth image is given (LGM never uses the depth output, so its training step
 // runs the cheaper DEPTH = false instantiation: one value less to reduce, no depth recursion).
-template <bool DEPTH>
+template <int LANES, bool DEPTH>
 __global__ void __launch_bounds__(kBlock, 5)
 composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -243,7 +290,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const int tile_y = tile / prm.gx, tile_x = tile - tile_y * prm.gx;
     const int scene = view_scene[view];
     int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
+    pixel_of_thread<LANES>(tile_x, tile_y, px, py);
+    const int sub = lane / LANES, sl = lane % LANES;
     const bool inside = px < prm.W && py < prm.H;
     const float pfx = (float)px, pfy = (float)py;
     const float tile_x0 = (float)(tile_x * kTile), tile_y0 = (float)(tile_y * kTile);
@@ -269,8 +317,16 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     }
     const float bgT = -T_final * (__ldg(bg) * dC0 + __ldg(bg + 1) * dC1 + __ldg(bg + 2) * dC2);
 
-    // Only list positions below the largest n_contrib of the tile (of the warp's patch) can contribute.
+    // Only list positions below the largest n_contrib of the tile (of the patch) can contribute.
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+    uint32_t pmax[Patch<LANES>::NSUB];  // per patch of this warp
+    {
+        uint32_t v = last_contributor;
+#pragma unroll
+        for (int o = LANES / 2; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+#pragma unroll
+        for (int s = 0; s < Patch<LANES>::NSUB; s++) pmax[s] = __shfl_sync(0xffffffffu, v, s * LANES);
+    }
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     uint32_t bmax = 0;
@@ -281,27 +337,38 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;  // colour / depth / alpha behind the current Gaussian
     const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
-    // which of the ten reduced sums this lane sends to the gradient row (warp_reduce_10): lanes 0,4,..,28 hold the
-    // eight "a" sums (slots 0..7), lanes 1 and 17 the two "b" sums (slots 8, 9); other lanes send nothing
-    const bool red_is_b = (lane & 15) == 1;
-    const int red_slot = (lane & 3) == 0 ? (lane >> 2) : ((red_is_b && (DEPTH || lane == 1)) ? 8 + (lane >> 4) : -1);
+    // which of the ten reduced sums this lane sends to the gradient row (group_reduce_10): the lanes of a group whose
+    // bits below LANES/8 are zero hold the eight "a" sums (slots 0..7).  The two "b" sums (slots 8, 9) are sent by the
+    // lanes sl = 1 and sl = LANES/2 + 1 where such lanes are free (LANES >= 16), else by a second reduction
+    // instruction from the lanes sl = 0 and sl = LANES/2.
+    const bool a_sender = (sl & (LANES / 8 - 1)) == 0;
+    const int b_lane = LANES >= 16 ? 1 : 0;
+    const bool b_sender = (sl & (LANES / 2 - 1)) == b_lane && (DEPTH || sl == b_lane);
+    const int a_slot = sl / (LANES / 8), b_slot = 8 + sl / (LANES / 2);
 
     for (int r0 = 0; r0 < todo; r0 += batch) {
         __syncthreads();  // the staging buffer is free again
         const int nb = min(batch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
-                      tile_x0, tile_y0);
+            stage_one<LANES>(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity,
+                             depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
-            bool hit = false;
-            // positions >= wmax were never reached by this patch in the forward
-            if (jl < nb && (uint32_t)(todo - 1 - (r0 + jl)) < wmax) hit = (__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u;
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = base + __ffs(m) - 1;
+            // positions >= pmax[s] were never reached by patch s in the forward
+            uint32_t mk = 0;
+            if (jl < nb) {
+                const uint32_t pos_l = (uint32_t)(todo - 1 - (r0 + jl));
+                mk = __float_as_uint(s_rec[jl].p1.w);
+#pragma unroll
+                for (int s = 0; s < Patch<LANES>::NSUB; s++)
+                    if (!(pos_l < pmax[s])) mk &= ~(1u << Patch<LANES>::bit(warp, s));
+            }
+            unsigned m = patch_hits<LANES>(mk, warp, sub);
+            while (LANES == 32 ? (m != 0u) : __any_sync(0xffffffffu, m != 0u)) {
+                const bool act = m != 0u;
+                const int j = base + (act ? __ffs(m) - 1 : 0);
                 m &= m - 1;
                 const uint32_t pos = (uint32_t)(todo - 1 - (r0 + j));
                 const float4 p0 = s_rec[j].p0;
@@ -310,7 +377,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);  // the forward's pinned decisions
                 const float G = expf(power);
                 const float a = fminf(kAlphaMax, LGM_MUL(p1.y, G));
-                const bool valid = (pos < last_contributor) && !(power > 0.0f) && !(a < kAlphaMin);
+                const bool valid = act && (pos < last_contributor) && !(power > 0.0f) && !(a < kAlphaMin);
                 if (!__any_sync(0xffffffffu, valid)) continue;
 
                 float va[8], vb[2];
@@ -356,10 +423,16 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     vb[1] = DEPTH ? w * dD : 0.0f;
                 }
                 float A, Bv;
-                warp_reduce_10<DEPTH>(va, vb, lane, A, Bv);
-                // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
-                if (red_slot >= 0)
-                    atomicAdd(grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow + red_slot, red_is_b ? Bv : A);
+                group_reduce_10<LANES, DEPTH>(va, vb, lane, A, Bv);
+                // ten lanes per patch hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's
+                // gradient row (an idle patch sends nothing)
+                float* row = grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow;
+                if (LANES >= 16) {
+                    if (act && (a_sender || b_sender)) atomicAdd(row + (a_sender ? a_slot : b_slot), a_sender ? A : Bv);
+                } else {
+                    if (act) atomicAdd(row + a_slot, A);
+                    if (act && b_sender) atomicAdd(row + b_slot, Bv);
+                }
             }
         }
     }
@@ -377,6 +450,54 @@ int batch_from_env(const char* name, int dflt)
     return dflt;
 }
 
+// patch size (lanes per patch): LGM_PATCH_LANES = 32 | 16 | 8
+int patch_lanes_from_env()
+{
+    const char* e = getenv("LGM_PATCH_LANES");
+    if (e) {
+        const int v = atoi(e);
+        if (v == 32 || v == 16 || v == 8) return v;
+    }
+    return kPatchLanes;
+}
+
+template <int LANES>
+cudaError_t run_fwd(cudaStream_t stream, unsigned blocks, int smem, const RenderParams& prm, const float* gaussians,
+                    const int32_t* view_scene, const float2* xy, const float4* conic_opacity, const float* depth,
+                    const uint32_t* vals, const uint2* ranges, const float* bg, int clamp_image, int batch, float* image,
+                    float* alpha, float* depth_img, uint32_t* n_contrib)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxBatch * (int)sizeof(Staged));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    composite_fwd_kernel<LANES><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges,
+                                                                  bg, clamp_image, batch, image, alpha, depth_img, n_contrib);
+    return cudaGetLastError();
+}
+
+template <int LANES, bool DEPTH>
+cudaError_t run_bwd(cudaStream_t stream, unsigned blocks, int smem, const RenderParams& prm, const float* gaussians,
+                    const int32_t* view_scene, const float2* xy, const float4* conic_opacity, const float* depth,
+                    const uint32_t* vals, const uint2* ranges, const float* bg, const float* alpha, const uint32_t* n_contrib,
+                    const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth, float* grad_rows, int batch)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<LANES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kMaxBatch * (int)sizeof(Staged));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    composite_bwd_kernel<LANES, DEPTH><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
+                                                                         ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
+                                                                         dL_ddepth, grad_rows, batch);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
@@ -388,16 +509,14 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
     if (blocks == 0) return cudaSuccess;
     const int batch = batch_from_env("LGM_FWD_BATCH", kFwdBatch);
     const int smem = batch * (int)sizeof(Staged);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxBatch * (int)sizeof(Staged));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+#define LGM_FWD(L) run_fwd<L>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, \
+                              bg, clamp_image, batch, image, alpha, depth_img, n_contrib)
+    switch (patch_lanes_from_env()) {
+        case 32: return LGM_FWD(32);
+        case 16: return LGM_FWD(16);
+        default: return LGM_FWD(8);
     }
-    composite_fwd_kernel<<<(unsigned)blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth,
-                                                                     vals, ranges, bg, clamp_image, batch, image, alpha, depth_img, n_contrib);
-    return cudaGetLastError();
+#undef LGM_FWD
 }
 
 cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
@@ -410,25 +529,22 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
     if (blocks == 0) return cudaSuccess;
     const int batch = batch_from_env("LGM_BWD_BATCH", kBwdBatch);
     const int smem = batch * (int)sizeof(Staged);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxBatch * (int)sizeof(Staged));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kMaxBatch * (int)sizeof(Staged));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+#define LGM_BWD(L, D) run_bwd<L, D>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, \
+                                    ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth, grad_rows, batch)
+    const int lanes = patch_lanes_from_env();
+    if (dL_ddepth) {
+        switch (lanes) {
+            case 32: return LGM_BWD(32, true);
+            case 16: return LGM_BWD(16, true);
+            default: return LGM_BWD(8, true);
+        }
     }
-    if (dL_ddepth)
-        composite_bwd_kernel<true><<<(unsigned)blocks, kBlock, smem, stream>>>(
-            prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-            dL_ddepth, grad_rows, batch);
-    else
-        composite_bwd_kernel<false><<<(unsigned)blocks, kBlock, smem, stream>>>(
-            prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-            nullptr, grad_rows, batch);
-    return cudaGetLastError();
+    switch (lanes) {
+        case 32: return LGM_BWD(32, false);
+        case 16: return LGM_BWD(16, false);
+        default: return LGM_BWD(8, false);
+    }
+#undef LGM_BWD
 }
 
 }  // namespace lgm

@@ -597,3 +597,33 @@ def test_rasterizer_with_shs_matches_precomputed_colours(oracle64):
     assert (img - img2).abs().max().item() <= 1e-5
     img.sum().backward()
     assert sh.grad.abs().sum().item() > 0 and torch.isfinite(sh.grad).all() and torch.isfinite(m3.grad).all()
+
+
+def test_patch_sizes_agree(monkeypatch):
+    """The compositing kernels with 8x4 / 4x4 / 4x2-pixel patches (LGM_PATCH_LANES = 32 / 16 / 8): culling granularity
+    only decides which non-contributing pairs are skipped, so the forward outputs are bit-identical and the gradients
+    agree up to fp32 summation order.  Image not a multiple of 16, depth gradient present and absent."""
+    from lgm_b200 import ops
+    B, V, N, S = 2, 3, 6000, 72
+    g0 = make_gaussians(B, N, "trained", seed=23)
+    g0[:, :, 4:7] *= 4.0
+    cv, cvp, _ = make_cameras(B, V, seed=23)
+    t = tan_half(49.1)
+    d_img, d_alpha, d_depth = make_upstream_grads(B, V, S, S, seed=23, with_depth=True)
+    res = {}
+    for lanes in (32, 16, 8):
+        monkeypatch.setenv("LGM_PATCH_LANES", str(lanes))
+        g, vm, pm, bg, img, al, dp, st = _cuda_forward(g0.numpy(), cv, cvp, [0.1, 0.2, 0.3], S, S, t, t)
+        outs = []
+        for dd in (d_depth, None):
+            dg, _ = ops.backward_views(g, vm, pm, bg, st, al, d_img.reshape(B * V, 3, S, S).to(DEV).contiguous(),
+                                       d_alpha.reshape(B * V, 1, S, S).to(DEV).contiguous(),
+                                       None if dd is None else dd.reshape(B * V, 1, S, S).to(DEV).contiguous())
+            outs.append(dg.clone())
+        res[lanes] = (img.clone(), al.clone(), dp.clone(), st.n_contrib.clone(), outs)
+    for lanes in (16, 8):
+        for k in range(4):
+            assert torch.equal(res[32][k], res[lanes][k]), f"forward output {k} differs at LGM_PATCH_LANES={lanes}"
+        for a, b in zip(res[32][4], res[lanes][4]):
+            scale = a.abs().amax(dim=(0, 1), keepdim=True).clamp_min(1e-20)
+            assert ((a - b).abs() / scale).max().item() <= 2e-5, f"gradients differ at LGM_PATCH_LANES={lanes}"
