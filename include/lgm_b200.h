@@ -114,8 +114,12 @@ int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const flo
 
 /* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
  * dL_ddepth may be NULL (= zero gradient w.r.t. the depth image: LGM's losses never use depth; a cheaper kernel
- * instantiation runs).  grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on return it holds the
- * per-view screen-space gradients (dL/dmean2D in [0:2] is what means2D.grad receives upstream).
+ * instantiation runs).  grad_rows [n_views * P, LGM_GRAD_ROW] must be ZERO on entry (K6 accumulates with atomics); on
+ * return it holds, per (view, Gaussian), the MOMENT form of the screen-space gradients:
+ *   [0..4] Sx, Sy, Sxx, Sxy, Syy = sums over the Gaussian's pixels of q d, q d d^T with q = G dL/dalpha and
+ *   d = mean2D - pixel;  [5] dL/dopacity (= sum q);  [6..8] dL/dcolour;  [9] dL/ddepth;  [10..11] unused.
+ * K7 turns the moments into upstream's dL/dmean2D and dL/dconic with per-Gaussian coefficients (conic, opacity);
+ * lgm_screen_gradients does the same into a separate array for callers that want upstream's values (means2D.grad).
  * dL_dgaussians [n_scenes, P, 14]: per-Gaussian gradients summed over the views of each scene; overwritten when
  * accumulate == 0, added to when accumulate != 0 (view chunks of one step).                                  */
 int lgm_backward(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
@@ -133,7 +137,11 @@ int lgm_backward_composite(void* stream, const lgm_render_params* prm, const flo
                            const float* dL_ddepth, float* grad_rows);
 int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
                       const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
-                      const float* grad_rows, float* dL_dgaussians, int32_t accumulate);
+                      const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate);
+/* grad_rows (moment form) -> screen_grads [n_views * P, LGM_GRAD_ROW] in upstream's form: [0..1] dL/dmean2D (what
+ * means2D.grad receives upstream), [2..4] dL/dconic (xx, xy, yy), [5] dL/dopacity, [6..8] dL/dcolour, [9] dL/ddepth. */
+int lgm_screen_gradients(void* stream, const lgm_render_params* prm, const float* conic_opacity, const float* grad_rows,
+                         float* screen_grads);
 
 /* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
 /* Which binning path the calling thread's last lgm_forward_bin took (diagnostics / launch accounting). */

@@ -36,7 +36,8 @@ _SIGNATURES = {
     "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _vp, _vp, _vp, _vp, _sz, _vp, _i32] + [_vp] * 4),
     "lgm_backward": (ctypes.c_int, [_vp, _pp] + [_vp] * 19 + [_i32]),
     "lgm_backward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
-    "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i32]),
+    "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32]),
+    "lgm_screen_gradients": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp]),
     "lgm_last_bin_mode": (ctypes.c_int, []),
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

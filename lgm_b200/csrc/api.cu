@@ -274,16 +274,31 @@ int lgm_backward_composite(void* stream, const lgm_render_params* prm, const flo
 
 int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
                       const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
-                      const float* grad_rows, float* dL_dgaussians, int32_t accumulate)
+                      const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     if (p.n_scenes == 0 || p.P == 0) return LGM_OK;
     LGM_NOTNULL(gaussians); LGM_NOTNULL(scene_view_offsets); LGM_NOTNULL(dL_dgaussians);
-    if (p.n_views > 0) { LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(radii); LGM_NOTNULL(grad_rows); }
+    if (p.n_views > 0) {
+        LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(radii); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(grad_rows);
+    }
     LGM_CUDA(lgm::launch_preprocess_bwd((cudaStream_t)stream, p, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
-                                        grad_rows, dL_dgaussians, accumulate),
+                                        reinterpret_cast<const float4*>(conic_opacity), grad_rows, dL_dgaussians, accumulate),
              "backward_geom");
+    return LGM_OK;
+}
+
+int lgm_screen_gradients(void* stream, const lgm_render_params* prm, const float* conic_opacity, const float* grad_rows,
+                         float* screen_grads)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    if (p.n_views == 0 || p.P == 0) return LGM_OK;
+    LGM_NOTNULL(conic_opacity); LGM_NOTNULL(grad_rows); LGM_NOTNULL(screen_grads);
+    LGM_CUDA(lgm::launch_screen_gradients((cudaStream_t)stream, p, reinterpret_cast<const float4*>(conic_opacity), grad_rows,
+                                          screen_grads),
+             "screen_gradients");
     return LGM_OK;
 }
 
@@ -297,7 +312,7 @@ int lgm_backward(void* stream, const lgm_render_params* prm, const float* gaussi
     if (int rc = lgm_backward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges,
                                         bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth, grad_rows))
         return rc;
-    return lgm_backward_geom(stream, prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii, grad_rows,
+    return lgm_backward_geom(stream, prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii, conic_opacity, grad_rows,
                              dL_dgaussians, accumulate);
 }
 

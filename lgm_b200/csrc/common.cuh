@@ -44,7 +44,10 @@ cudaError_t launch_sh_backward(cudaStream_t stream, int P, int deg, int max_coef
                                float* dL_dmeans);
 cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
-                                  const int32_t* radii, const float* grad_rows, float* dL_dgaussians, int accumulate);
+                                  const int32_t* radii, const float4* conic_opacity, const float* grad_rows,
+                                  float* dL_dgaussians, int accumulate);
+cudaError_t launch_screen_gradients(cudaStream_t stream, const RenderParams& prm, const float4* conic_opacity,
+                                    const float* grad_rows, float* out);
 
 cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n, uint32_t* block_offsets,
                                    unsigned long long* total);

@@ -36,6 +36,18 @@ constexpr float kCullScale = 1.002f;  // safety margins of the alpha >= 1/255 te
 constexpr float kCullPad = 2e-3f;
 constexpr float kCullPix = 0.02f;     // pixels
 
+// exp(x) for the compositing kernels: one multiply and MUFU.EX2 (relative error ~3e-7 at |x| <= 5.5, the range in which
+// alpha can pass the 1/255 test) instead of libdevice's 8-instruction sequence.  Forward and backward use the same
+// function, so the backward re-derives exactly the alpha (and the skip decisions) of the forward; against the oracle
+// the images move by < 1e-6, far inside the 1e-4 bar.  The pinned arithmetic (splat_math.cuh) is untouched: it ends at
+// `power`, everything that feeds radii, tiles and keys is upstream of this.
+__device__ __forceinline__ float exp_fast(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+
 struct __align__(16) Staged {
     float4 p0;    // px, py, conic xx, conic xy
     float4 p1;    // conic yy, opacity, row index (view * P + idx) as bits, patch mask as bits
@@ -187,7 +199,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 const float4 p1 = s_rec[j].p1;
                 const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
                 const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);
-                const float a = fminf(kAlphaMax, LGM_MUL(p1.y, expf(power)));
+                const float a = fminf(kAlphaMax, LGM_MUL(p1.y, exp_fast(power)));
                 const float test_T = LGM_MUL(T, LGM_SUB(1.0f, a));
                 // A.4 in predicate form: skip if power > 0 or alpha < 1/255; stop (without compositing) if T would
                 // fall below 1e-4; otherwise composite.  Lanes that do not composite add exact zeros.
@@ -335,8 +347,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
     const int todo = (int)min(range.y - range.x, bmax);
 
     float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;  // colour / depth / alpha behind the current Gaussian
-    const float ddelx_dx = 0.5f * (float)prm.W, ddely_dy = 0.5f * (float)prm.H;
+    float U = 0.f;  // (colour, depth, alpha) accumulated behind the current Gaussian, dotted with (dC, dD, dA)
     // which of the ten reduced sums this lane sends to the gradient row (group_reduce_10): the lanes of a group whose
     // bits below LANES/8 are zero hold the eight "a" sums (slots 0..7).  The two "b" sums (slots 8, 9) are sent by the
     // lanes sl = 1 and sl = LANES/2 + 1 where such lanes are free (LANES >= 16), else by a second reduction
@@ -375,7 +386,7 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 const float4 p1 = s_rec[j].p1;
                 const float dx = LGM_SUB(p0.x, pfx), dy = LGM_SUB(p0.y, pfy);
                 const float power = pair_power(p0.z, p0.w, p1.x, dx, dy);  // the forward's pinned decisions
-                const float G = expf(power);
+                const float G = exp_fast(power);
                 const float a = fminf(kAlphaMax, LGM_MUL(p1.y, G));
                 const bool valid = act && (pos < last_contributor) && !(power > 0.0f) && !(a < kAlphaMin);
                 if (!__any_sync(0xffffffffu, valid)) continue;
@@ -384,8 +395,10 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 {
                     // Evaluated by every lane, no divergent region: a lane that does not contribute runs with
                     // alpha = 0 and G = 0, which leaves its running state untouched and makes its ten terms exact zeros.
-                    // "Colour behind" recursions in eager form: after a contributor (a, c),  acc <- acc + a (c - acc)
-                    // ( = a c + (1 - a) acc, A.5), likewise depth and alpha; T <- T / (1 - a).
+                    // A.5's "colour behind" recursions  acc <- a c + (1 - a) acc  (colour, depth, alpha) only ever enter
+                    // through their dot product with this pixel's upstream gradient, so ONE scalar is carried:
+                    //   U = acc . dC + acc_depth dD + acc_alpha dA,   U <- U + a (c . dC + depth dD + dA - U),
+                    // and dL/dalpha = (c . dC + depth dD + dA - U) T + bg-term.  T <- T / (1 - a).
                     const float4 cd = s_rec[j].rgbd;
                     const float ae = valid ? a : 0.0f;
                     const float Gv = valid ? G : 0.0f;
@@ -393,30 +406,25 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(1.0f - ae));
                     T *= rcp;
                     const float w = ae * T;
-                    const float e0 = cd.x - acc0, e1 = cd.y - acc1, e2 = cd.z - acc2, eD = cd.w - accD, eA = 1.0f - accA;
-                    float dL_da = e0 * dC0;
-                    dL_da = fmaf(e1, dC1, dL_da);
-                    dL_da = fmaf(e2, dC2, dL_da);
-                    if (DEPTH) dL_da = fmaf(eD, dD, dL_da);
-                    dL_da = fmaf(eA, dA, dL_da);
-                    dL_da = fmaf(dL_da, T, bgT * rcp);
-                    acc0 = fmaf(ae, e0, acc0);
-                    acc1 = fmaf(ae, e1, acc1);
-                    acc2 = fmaf(ae, e2, acc2);
-                    if (DEPTH) accD = fmaf(ae, eD, accD);
-                    accA = fmaf(ae, eA, accA);
-                    const float dL_dG = p1.y * dL_da;
-                    const float gdx = Gv * dx, gdy = Gv * dy;
-                    const float dG_ddelx = -gdx * p0.z - gdy * p0.w;
-                    const float dG_ddely = -gdy * p1.x - gdx * p0.w;
-                    const float h = -0.5f * dL_dG;
-                    const float hgx = h * gdx;
-                    va[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    va[1] = dL_dG * dG_ddely * ddely_dy;
-                    va[2] = hgx * dx;
-                    va[3] = hgx * dy;
-                    va[4] = h * gdy * dy;
-                    va[5] = Gv * dL_da;
+                    float cdot = fmaf(cd.x, dC0, dA);
+                    cdot = fmaf(cd.y, dC1, cdot);
+                    cdot = fmaf(cd.z, dC2, cdot);
+                    if (DEPTH) cdot = fmaf(cd.w, dD, cdot);
+                    const float e = cdot - U;
+                    const float dL_da = fmaf(e, T, bgT * rcp);
+                    U = fmaf(ae, e, U);
+                    // The geometry gradients are linear in the moments of q = G dL/dalpha about the Gaussian's centre
+                    // (dx, dy are centre - pixel, the same origin in every tile), with coefficients that depend on the
+                    // Gaussian only; the row accumulates the moments and preprocess_bwd applies the coefficients
+                    // (moments_to_gradients, splat_math.cuh) — 9 multiplies here instead of 21.
+                    const float q = Gv * dL_da;
+                    const float qx = q * dx, qy = q * dy;
+                    va[0] = qx;
+                    va[1] = qy;
+                    va[2] = qx * dx;
+                    va[3] = qx * dy;
+                    va[4] = qy * dy;
+                    va[5] = q;
                     va[6] = w * dC0;
                     va[7] = w * dC1;
                     vb[0] = w * dC2;

@@ -109,8 +109,8 @@ cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, 
 __global__ void __launch_bounds__(kBlock, 3)
 preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ scene_view_offsets,
-                      const int32_t* __restrict__ radii, const float* __restrict__ grad_rows,
-                      float* __restrict__ dL_dgaussians, int accumulate)
+                      const int32_t* __restrict__ radii, const float4* __restrict__ conic_opacity,
+                      const float* __restrict__ grad_rows, float* __restrict__ dL_dgaussians, int accumulate)
 {
     __shared__ __align__(16) float s_g[kBlock * 14];
     __shared__ float s_m[32];
@@ -140,9 +140,13 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         if (!(radii[gi] > 0)) continue;
         const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
         const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
-        // r0 = (m2d.x, m2d.y, conic.xx, conic.xy)  r1 = (conic.yy, opacity, col.r, col.g)  r2 = (col.b, depth, -, -)
-        preprocess_point_bwd(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, r0.x, r0.y, r0.z,
-                             r0.w, r1.x, r2.y, d, d + 4, d + 7);
+        // r0 = (Sx, Sy, Sxx, Sxy)  r1 = (Syy, S0 = dL/dopacity, col.r, col.g)  r2 = (col.b, depth, -, -): moment form
+        const float4 co = __ldg(conic_opacity + gi);
+        float g2x, g2y, gcx, gcy, gcz;
+        moments_to_gradients((float)prm.W, (float)prm.H, co.x, co.y, co.z, co.w, r0.x, r0.y, r0.z, r0.w, r1.x, &g2x, &g2y, &gcx,
+                             &gcy, &gcz);
+        preprocess_point_bwd(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, g2x, g2y, gcx, gcy,
+                             gcz, r2.y, d, d + 4, d + 7);
         d[3] += r1.y;
         d[11] += r1.z;
         d[12] += r1.w;
@@ -166,12 +170,42 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
 
 cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
-                                  const int32_t* radii, const float* grad_rows, float* dL_dgaussians, int accumulate)
+                                  const int32_t* radii, const float4* conic_opacity, const float* grad_rows,
+                                  float* dL_dgaussians, int accumulate)
 {
     if (prm.P == 0 || prm.n_scenes == 0) return cudaSuccess;
     dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_scenes);
     preprocess_bwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
-                                                       grad_rows, dL_dgaussians, accumulate);
+                                                       conic_opacity, grad_rows, dL_dgaussians, accumulate);
+    return cudaGetLastError();
+}
+
+// Moment rows -> upstream's screen-space gradients (diagnostics, means2D.grad of the Level-1 API, parity tests):
+// out row = (dL/dmean2D.xy, dL/dconic.xx .xy .yy, dL/dopacity, dL/dcolour.rgb, dL/ddepth, 0, 0)
+__global__ void __launch_bounds__(kBlock)
+screen_gradients_kernel(const RenderParams prm, size_t n_rows, const float4* __restrict__ conic_opacity,
+                        const float* __restrict__ grad_rows, float* __restrict__ out)
+{
+    const size_t gi = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (gi >= n_rows) return;
+    const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
+    const float4 r0 = row[0], r1 = row[1], r2 = row[2];
+    const float4 co = conic_opacity[gi];
+    float g2x, g2y, gcx, gcy, gcz;
+    moments_to_gradients((float)prm.W, (float)prm.H, co.x, co.y, co.z, co.w, r0.x, r0.y, r0.z, r0.w, r1.x, &g2x, &g2y, &gcx, &gcy,
+                         &gcz);
+    float4* dst = reinterpret_cast<float4*>(out + gi * kGradRow);
+    dst[0] = make_float4(g2x, g2y, gcx, gcy);
+    dst[1] = make_float4(gcz, r1.y, r1.z, r1.w);
+    dst[2] = make_float4(r2.x, r2.y, 0.f, 0.f);
+}
+
+cudaError_t launch_screen_gradients(cudaStream_t stream, const RenderParams& prm, const float4* conic_opacity,
+                                    const float* grad_rows, float* out)
+{
+    const size_t n_rows = (size_t)prm.n_views * prm.P;
+    if (n_rows == 0) return cudaSuccess;
+    screen_gradients_kernel<<<(unsigned)((n_rows + kBlock - 1) / kBlock), kBlock, 0, stream>>>(prm, n_rows, conic_opacity, grad_rows, out);
     return cudaGetLastError();
 }
 

@@ -214,6 +214,23 @@ LGM_HD float pair_power(float cx, float cy, float cz, float dx, float dy)
 // A.6 preprocess backward for one (view, Gaussian) with radius > 0.  Tolerance-checked (1e-3 rel), not bit-pinned:
 // natural expression form.  g2 = dL/dmean2D (NDC-scaled, 2), gc = dL/dconic (x, y, w slots), gd = dL/ddepth.
 // Accumulates (+=) into dpos[3], dscale[3], drot[4].
+// The compositing backward accumulates, per (view, Gaussian), the moments of q = G dL/dalpha about the Gaussian's
+// centre over its pixels (d = centre - pixel):  Sx = sum q dx, Sy, Sxx = sum q dx dx, Sxy, Syy  (and S0 = sum q, which IS
+// dL/dopacity).  Upstream's per-pixel terms (A.5) are these moments times per-Gaussian coefficients:
+//   dL/dmean2D.x = -(W/2) o (cxx Sx + cxy Sy)     dL/dconic.xx = -o Sxx / 2
+//   dL/dmean2D.y = -(H/2) o (cyy Sy + cxy Sx)     dL/dconic.xy = -o Sxy / 2      dL/dconic.yy = -o Syy / 2
+// with (cxx, cxy, cyy, o) = the Gaussian's conic and opacity.
+LGM_HD void moments_to_gradients(float W, float H, float cxx, float cxy, float cyy, float o, float Sx, float Sy, float Sxx,
+                                 float Sxy, float Syy, float* g2x, float* g2y, float* gcx, float* gcy, float* gcz)
+{
+    const float h = -0.5f * o;
+    *g2x = h * W * (cxx * Sx + cxy * Sy);
+    *g2y = h * H * (cyy * Sy + cxy * Sx);
+    *gcx = h * Sxx;
+    *gcy = h * Sxy;
+    *gcz = h * Syy;
+}
+
 LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
                                  const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
                                  float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot)

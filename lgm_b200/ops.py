@@ -174,7 +174,8 @@ class TooManyInstances(_lib.LgmError):
 
 
 def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth):
-    """Returns (dL_dgaussians [B,P,14], grad_rows [VW*P,12])."""
+    """Returns (dL_dgaussians [B,P,14], grad_rows [VW*P,12]).  grad_rows is in MOMENT form (include/lgm_b200.h,
+    lgm_backward); screen_gradients() converts it to upstream's dL/dmean2D, dL/dconic, ... ."""
     L = _lib.lib()
     dev = gaussians.device
     cfg = st.cfg
@@ -189,11 +190,25 @@ def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha,
         _lib.ptr(d_image), _lib.ptr(d_alpha), _lib.ptr(d_depth), _lib.ptr(grad_rows)), "lgm_backward_composite"))
     _timed("geom_bwd", lambda: _lib.check(L.lgm_backward_geom(
         _stream(), prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(st.scene_view_offsets),
-        _lib.ptr(st.radii), _lib.ptr(grad_rows), _lib.ptr(d_gauss), 0), "lgm_backward_geom"))
+        _lib.ptr(st.radii), _lib.ptr(st.conic_opacity), _lib.ptr(grad_rows), _lib.ptr(d_gauss), 0), "lgm_backward_geom"))
     launch_counter["kernels"] += 2 if st.n_views * st.P else 0
     if st.n_views * st.P == 0:
         d_gauss.zero_()
     return d_gauss, grad_rows
+
+
+def screen_gradients(st: ForwardState, grad_rows):
+    """Moment rows -> upstream's per-(view, Gaussian) screen-space gradients [VW*P,12]: [0:2] dL/dmean2D (what
+    means2D.grad receives upstream), [2:5] dL/dconic, [5] dL/dopacity, [6:9] dL/dcolour, [9] dL/ddepth."""
+    L = _lib.lib()
+    cfg = st.cfg
+    prm = _lib.make_params(st.n_scenes, st.P, st.n_views, cfg.image_height, cfg.image_width, cfg.tanfovx, cfg.tanfovy,
+                           cfg.scale_modifier)
+    out = torch.zeros_like(grad_rows)
+    _lib.check(L.lgm_screen_gradients(_stream(), prm, _lib.ptr(st.conic_opacity), _lib.ptr(grad_rows), _lib.ptr(out)),
+               "lgm_screen_gradients")
+    launch_counter["kernels"] += 1 if st.n_views * st.P else 0
+    return out
 
 
 def _grad_or_zeros(g, like):

@@ -67,7 +67,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         d = d_gauss[0]
         P = d.shape[0]
         d_means2D = torch.zeros(P, 3, device=g.device)
-        d_means2D[:, :2] = rows[:P, 0:2]
+        d_means2D[:, :2] = ops.screen_gradients(st, rows)[:P, 0:2]
         # (means3D, means2D, colors_precomp, opacities, scales, rotations, raster_settings)
         return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], d[:, 4:7], d[:, 7:11], None
 
