@@ -87,7 +87,7 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     w.tile_scratch = off;
     off = align_up(off + lgm::tile_sort_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
     w.direct_scratch = off;
-    off = align_up(off + lgm::direct_bin_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
+    off = align_up(off + lgm::direct_bin_scratch_bytes(p), 256);
     w.total = off;
     return w;
 }

@@ -30,7 +30,7 @@ cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, 
 // direct_bin.cu: count -> scan -> scatter -> per-tile shared-memory sort (no global radix sort); a step whose longest
 // tile exceeds direct_bin_tile_cap() must use the onesweep path
 int direct_bin_tile_cap();
-size_t direct_bin_scratch_bytes(uint32_t n_ranges);
+size_t direct_bin_scratch_bytes(const RenderParams& prm);
 cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                     uint2* ranges, void* scratch, const uint32_t** longest_tile_dev);
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,

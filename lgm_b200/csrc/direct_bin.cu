@@ -4,8 +4,8 @@
 //
 //   D1  count     per (view, Gaussian): +1 per touched tile, aggregated per CTA in shared memory, then one global
 //                 atomic per (CTA, touched tile) into tile_counts[global tile]
-//   D2  scan      exclusive scan of the counts (scan_block_sums_kernel) = every tile's [start, end) in the final list
-//       ranges    ranges[] written from counts + offsets (empty tiles stay (0,0)), non-empty tiles appended to a work
+//   D2  ranges    one CTA per view scans the view's tile counts on top of the totals of the views before it = every
+//                 tile's [start, end) in the final list (empty tiles stay (0,0)); non-empty tiles appended to a work
 //                 list, longest tile recorded
 //   D3  scatter   same enumeration as D1; each CTA reserves a run of every touched tile's segment with one global atomic,
 //                 its instances take the slots of the run (shared-memory atomics) and store (value, depth bits) there —
@@ -93,8 +93,8 @@ constexpr int kEnumMaxTiles = 6144;  // 2 x 4 B per tile of dynamic shared memor
 template <bool SCATTER>
 __global__ void __launch_bounds__(kBlock)
 tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
-                      const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
-                      uint2* __restrict__ pairs)
+                      const float* __restrict__ depth, uint32_t* __restrict__ counts, uint32_t* __restrict__ view_totals,
+                      uint16_t* __restrict__ cta_hist, const uint2* __restrict__ ranges, uint2* __restrict__ pairs)
 {
     extern __shared__ uint32_t s_enum[];
     uint32_t* s_hist = s_enum;                 // [n_tiles] instances of this CTA per tile, then the fill cursor
@@ -102,42 +102,51 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     const int view = blockIdx.y;
     const int first = blockIdx.x * (kBlock * kEnumItems) + threadIdx.x;
     const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
-    for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
-    __syncthreads();
+    // this CTA's histogram travels from the count launch to the scatter launch (<= 2048 per tile: 16 bits)
+    uint16_t* my_hist = cta_hist + ((size_t)view * gridDim.x + blockIdx.x) * prm.n_tiles;
+    if (!SCATTER) {
+        for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
+        __syncthreads();
 #pragma unroll 1
-    for (int k = 0; k < kEnumItems; k++)
-        for_each_touched_tile<false>(prm, radii, xy, depth, view, first + k * kBlock,
-                                     [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); });
-    __syncthreads();
-    for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
-        const uint32_t c = s_hist[i];
-        if (c == 0u) continue;
-        if (SCATTER) {
-            s_base[i] = ranges[tile_base + i].x + atomicSub(&counts[tile_base + i], c) - c;
-            s_hist[i] = 0u;
-        } else {
-            atomicAdd(&counts[tile_base + i], c);
+        for (int k = 0; k < kEnumItems; k++)
+            for_each_touched_tile<false>(prm, radii, xy, depth, view, first + k * kBlock,
+                                         [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); });
+        __syncthreads();
+        uint32_t mine = 0;
+        for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
+            const uint32_t c = s_hist[i];
+            my_hist[i] = (uint16_t)c;
+            if (c) atomicAdd(&counts[tile_base + i], c);
+            mine += c;
         }
-    }
-    if (!SCATTER) return;
-    __syncthreads();
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&view_totals[view], mine);
+    } else {
+        for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
+            const uint32_t c = my_hist[i];
+            if (c) s_base[i] = ranges[tile_base + i].x + atomicSub(&counts[tile_base + i], c) - c;
+            s_hist[i] = 0u;
+        }
+        __syncthreads();
 #pragma unroll 1
-    for (int k = 0; k < kEnumItems; k++)
-        for_each_touched_tile<true>(prm, radii, xy, depth, view, first + k * kBlock,
-                                    [&](uint32_t tl, uint32_t val, uint32_t dbits) {
-                                        pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, dbits);
-                                    });
+        for (int k = 0; k < kEnumItems; k++)
+            for_each_touched_tile<true>(prm, radii, xy, depth, view, first + k * kBlock,
+                                        [&](uint32_t tl, uint32_t val, uint32_t dbits) {
+                                            pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, dbits);
+                                        });
+    }
 }
 
 // the same without the shared-memory stage, for views of more than kEnumMaxTiles tiles
 template <bool SCATTER>
 __global__ void __launch_bounds__(kBlock)
 tile_enumerate_global_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
-                             const float* __restrict__ depth, uint32_t* __restrict__ counts, const uint2* __restrict__ ranges,
-                             uint2* __restrict__ pairs)
+                             const float* __restrict__ depth, uint32_t* __restrict__ counts, uint32_t* __restrict__ view_totals,
+                             const uint2* __restrict__ ranges, uint2* __restrict__ pairs)
 {
     const int view = blockIdx.y;
     const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    uint32_t mine = 0;
     for_each_touched_tile<SCATTER>(prm, radii, xy, depth, view, blockIdx.x * kBlock + threadIdx.x,
                                    [&](uint32_t tl, uint32_t val, uint32_t dbits) {
                                        const uint32_t gt = tile_base + tl;
@@ -146,44 +155,69 @@ tile_enumerate_global_kernel(const RenderParams prm, const int32_t* __restrict__
                                            pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
                                        } else {
                                            atomicAdd(&counts[gt], 1u);
+                                           mine++;
                                        }
                                    });
+    if (!SCATTER) {
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&view_totals[view], mine);
+    }
 }
+
+// whether the per-CTA shared-memory stage is used (LGM_ENUM_GLOBAL: test hook for the large-view variant)
+bool enumerate_in_smem(const RenderParams& prm) { return prm.n_tiles <= kEnumMaxTiles && getenv("LGM_ENUM_GLOBAL") == nullptr; }
+uint32_t enum_ctas_per_view(const RenderParams& prm) { return (uint32_t)((prm.P + kBlock * kEnumItems - 1) / (kBlock * kEnumItems)); }
 
 template <bool SCATTER>
 cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
-                                  const float* depth, uint32_t* counts, const uint2* ranges, uint2* pairs)
+                                  const float* depth, uint32_t* counts, uint32_t* view_totals, uint16_t* cta_hist,
+                                  const uint2* ranges, uint2* pairs)
 {
-    const bool force_global = getenv("LGM_ENUM_GLOBAL") != nullptr;  // test hook for the large-view variant
-    if (prm.n_tiles <= kEnumMaxTiles && !force_global) {
-        dim3 grid((prm.P + kBlock * kEnumItems - 1) / (kBlock * kEnumItems), prm.n_views);
-        tile_enumerate_kernel<SCATTER><<<grid, kBlock, (size_t)prm.n_tiles * 8, stream>>>(prm, radii, xy, depth, counts, ranges, pairs);
+    if (enumerate_in_smem(prm)) {
+        dim3 grid(enum_ctas_per_view(prm), prm.n_views);
+        tile_enumerate_kernel<SCATTER><<<grid, kBlock, (size_t)prm.n_tiles * 8, stream>>>(prm, radii, xy, depth, counts, view_totals,
+                                                                                          cta_hist, ranges, pairs);
     } else {
         dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
-        tile_enumerate_global_kernel<SCATTER><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, ranges, pairs);
+        tile_enumerate_global_kernel<SCATTER><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, view_totals, ranges, pairs);
     }
     return cudaGetLastError();
 }
 
-// ranges from counts + offsets; non-empty tiles -> work list (warp-aggregated append); head[0] = list length,
-// head[1] = work cursor (zeroed by the caller), head[2] = longest tile
+// D2.  One CTA per view: the view's first slot is the sum of the totals of the views before it, the tiles of the view
+// are scanned in chunks of 256.  Writes ranges[] (empty tiles stay (0,0)), appends the non-empty tiles to the work list
+// (warp-aggregated) and records the longest tile.  head[0] = list length, head[1] = work cursor, head[2] = longest tile.
 __global__ void __launch_bounds__(kBlock)
-tile_ranges_from_counts_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t n_ranges,
-                               uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
+tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ view_totals, int n_tiles,
+                        uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
 {
-    const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const uint32_t n = t < n_ranges ? counts[t] : 0u;
-    if (t < n_ranges) ranges[t] = n ? make_uint2(offsets[t], offsets[t] + n) : make_uint2(0u, 0u);
-    const unsigned m = __ballot_sync(0xffffffffu, n != 0u);
-    if (m == 0u) return;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&head[0], (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (n) list[base + __popc(m & ((1u << lane) - 1u))] = t;
-    const uint32_t mx = __reduce_max_sync(0xffffffffu, n);
-    if (lane == leader) atomicMax(&head[2], mx);
+    __shared__ uint32_t s_warp[8];
+    const int view = blockIdx.x, t = threadIdx.x, lane = t & 31;
+    uint32_t part = 0;
+    for (int v = t; v < view; v += kBlock) part += view_totals[v];
+    uint32_t carry;
+    block_excl_scan_256(part, s_warp, &carry);
+    uint32_t longest = 0;
+    for (int i0 = 0; i0 < n_tiles; i0 += kBlock) {
+        const int i = i0 + t;
+        const uint32_t gt = (uint32_t)view * (uint32_t)n_tiles + (uint32_t)i;
+        const uint32_t n = i < n_tiles ? counts[gt] : 0u;
+        uint32_t tot;
+        const uint32_t start = carry + block_excl_scan_256(n, s_warp, &tot);
+        carry += tot;
+        if (i < n_tiles) ranges[gt] = n ? make_uint2(start, start + n) : make_uint2(0u, 0u);
+        longest = max(longest, n);
+        const unsigned m = __ballot_sync(0xffffffffu, n != 0u);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&head[0], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (n) list[base + __popc(m & ((1u << lane) - 1u))] = gt;
+        }
+    }
+    longest = __reduce_max_sync(0xffffffffu, longest);
+    if (lane == 0 && longest) atomicMax(&head[2], longest);
 }
 
 // D4.  Persistent CTAs pull tiles from the work list.
@@ -297,28 +331,42 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
 
 int direct_bin_tile_cap() { return kSortCap; }
 
-// small arrays of the direct path: counts [n_ranges], offsets [n_ranges], list [n_ranges], head [64 u32],
-// total [1 u64 + pad]
-size_t direct_bin_scratch_bytes(uint32_t n_ranges) { return ((size_t)n_ranges * 3 + 64 + 16) * sizeof(uint32_t); }
+// scratch of the direct path: head [64 u32] | view totals [n_views, padded to 64] | counts [n_ranges] | list [n_ranges] |
+// per-CTA histograms u16 [n_views x CTAs per view x n_tiles] (shared-memory variant only)
+struct DirectScratch {
+    uint32_t *head, *view_totals, *counts, *list;
+    uint16_t* cta_hist;
+    size_t zero_bytes, total_bytes;
+};
+static DirectScratch direct_scratch(const RenderParams& prm, void* scratch)
+{
+    const size_t n_ranges = (size_t)prm.n_views * prm.n_tiles;
+    const size_t nv = ((size_t)prm.n_views + 63) / 64 * 64;
+    DirectScratch d;
+    d.head = static_cast<uint32_t*>(scratch);
+    d.view_totals = d.head + 64;
+    d.counts = d.view_totals + nv;
+    d.list = d.counts + n_ranges;
+    d.cta_hist = reinterpret_cast<uint16_t*>(d.list + n_ranges);
+    d.zero_bytes = (64 + nv + n_ranges) * sizeof(uint32_t);  // head, view totals, counts
+    const size_t hist = prm.n_tiles <= kEnumMaxTiles ? (size_t)prm.n_views * enum_ctas_per_view(prm) * prm.n_tiles * sizeof(uint16_t) : 0;
+    d.total_bytes = (64 + nv + 2 * n_ranges) * sizeof(uint32_t) + hist + 256;
+    return d;
+}
 
-static inline uint32_t* db_counts(void* scratch) { return static_cast<uint32_t*>(scratch) + 64 + 16; }
+size_t direct_bin_scratch_bytes(const RenderParams& prm) { return direct_scratch(prm, nullptr).total_bytes; }
 
-// D1 + D2: after this, head[2] (device) holds the longest tile.  `scratch` as direct_bin_scratch_bytes.
+// D1 + D2: after this, *longest_tile_dev (device) holds the longest tile.  `scratch` as direct_bin_scratch_bytes.
 cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                     uint2* ranges, void* scratch, const uint32_t** longest_tile_dev)
 {
-    const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
-    uint32_t* head = static_cast<uint32_t*>(scratch);
-    unsigned long long* total = reinterpret_cast<unsigned long long*>(head + 64);
-    uint32_t* counts = db_counts(scratch);
-    uint32_t* offsets = counts + n_ranges;
-    uint32_t* list = offsets + n_ranges;
-    cudaError_t err = cudaMemsetAsync(scratch, 0, ((size_t)n_ranges + 64 + 16) * sizeof(uint32_t), stream);  // head, total, counts
+    const DirectScratch d = direct_scratch(prm, scratch);
+    cudaError_t err = cudaMemsetAsync(scratch, 0, d.zero_bytes, stream);
     if (err != cudaSuccess) return err;
-    if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, counts, nullptr, nullptr)) != cudaSuccess) return err;
-    if ((err = launch_scan_block_sums(stream, counts, n_ranges, offsets, total)) != cudaSuccess) return err;
-    tile_ranges_from_counts_kernel<<<(n_ranges + kBlock - 1) / kBlock, kBlock, 0, stream>>>(counts, offsets, n_ranges, ranges, list, head);
-    *longest_tile_dev = head + 2;
+    if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, d.counts, d.view_totals, d.cta_hist, nullptr, nullptr)) != cudaSuccess)
+        return err;
+    tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(d.counts, d.view_totals, prm.n_tiles, ranges, d.list, d.head);
+    *longest_tile_dev = d.head + 2;
     return cudaGetLastError();
 }
 
@@ -328,9 +376,7 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
                                    uint64_t* keys_sorted, void* scratch)
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
-    uint32_t* head = static_cast<uint32_t*>(scratch);
-    uint32_t* counts = db_counts(scratch);
-    const uint32_t* list = counts + 2 * (size_t)n_ranges;
+    const DirectScratch d = direct_scratch(prm, scratch);
     static int n_sm = 0;
     if (!n_sm) {
         cudaError_t e = cudaFuncSetAttribute(tile_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
@@ -339,10 +385,11 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, counts, ranges, static_cast<uint2*>(pairs));
+    cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, d.cta_hist, ranges,
+                                                  static_cast<uint2*>(pairs));
     if (err != cudaSuccess) return err;
     const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
-    tile_bucket_sort_kernel<<<n_cta, kSortThreads, kSortSmem, stream>>>(static_cast<const uint2*>(pairs), ranges, list, head,
+    tile_bucket_sort_kernel<<<n_cta, kSortThreads, kSortSmem, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, d.head,
                                                                         vals_sorted, keys_sorted);
     return cudaGetLastError();
 }

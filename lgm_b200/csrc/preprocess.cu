@@ -141,12 +141,8 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
         const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
         // r0 = (Sx, Sy, Sxx, Sxy)  r1 = (Syy, S0 = dL/dopacity, col.r, col.g)  r2 = (col.b, depth, -, -): moment form
-        const float4 co = __ldg(conic_opacity + gi);
-        float g2x, g2y, gcx, gcy, gcz;
-        moments_to_gradients((float)prm.W, (float)prm.H, co.x, co.y, co.z, co.w, r0.x, r0.y, r0.z, r0.w, r1.x, &g2x, &g2y, &gcx,
-                             &gcy, &gcz);
-        preprocess_point_bwd(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, g2x, g2y, gcx, gcy,
-                             gcz, r2.y, d, d + 4, d + 7);
+        preprocess_point_bwd_moments(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, (float)prm.W,
+                                     (float)prm.H, g[3], r0.x, r0.y, r0.z, r0.w, r1.x, r2.y, d, d + 4, d + 7);
         d[3] += r1.y;
         d[11] += r1.z;
         d[12] += r1.w;

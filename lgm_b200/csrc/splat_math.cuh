@@ -231,9 +231,13 @@ LGM_HD void moments_to_gradients(float W, float H, float cxx, float cxy, float c
     *gcz = h * Syy;
 }
 
-LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
-                                 const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
-                                 float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot)
+// moments = false: (g2x, g2y) = dL/dmean2D, (gcx, gcy, gcz) = dL/dconic as upstream passes them.
+// moments = true : the same five arguments carry (Sx, Sy, Sxx, Sxy, Syy) and are converted here, with the conic
+// re-derived from the 2D covariance this function computes anyway (W, H = image size, opacity = the Gaussian's).
+LGM_HD void preprocess_point_bwd_core(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
+                                      const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
+                                      float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot,
+                                      bool moments, float W, float H, float opacity)
 {
     const float x = pos[0], y = pos[1], z = pos[2];
     const float pvx = affine_row(mv, 0, x, y, z), pvy = affine_row(mv, 1, x, y, z), pvz = affine_row(mv, 2, x, y, z);
@@ -245,6 +249,10 @@ LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const flo
     const float yg = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
     const float a = abc[0], b = abc[1], c = abc[2];
     const float denom = a * c - b * b;
+    if (moments) {
+        const float di = 1.0f / denom;  // the forward's conic = (c, -b, a) / det
+        moments_to_gradients(W, H, c * di, -b * di, a * di, opacity, g2x, g2y, gcx, gcy, gcz, &g2x, &g2y, &gcx, &gcy, &gcz);
+    }
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
     const float denom2inv = 1.0f / ((denom * denom) + kWEps);
     float g6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -323,6 +331,23 @@ LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const flo
     drot[2] += 2.f * qx * (LGM_DMT(1, 0) + LGM_DMT(0, 1)) + 2.f * r * (LGM_DMT(2, 0) - LGM_DMT(0, 2)) + 2.f * qz * (LGM_DMT(1, 2) + LGM_DMT(2, 1)) - 4.f * qy * (LGM_DMT(2, 2) + LGM_DMT(0, 0));
     drot[3] += 2.f * r * (LGM_DMT(0, 1) - LGM_DMT(1, 0)) + 2.f * qx * (LGM_DMT(2, 0) + LGM_DMT(0, 2)) + 2.f * qy * (LGM_DMT(1, 2) + LGM_DMT(2, 1)) - 4.f * qz * (LGM_DMT(1, 1) + LGM_DMT(0, 0));
 #undef LGM_DMT
+}
+
+LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
+                                 const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
+                                 float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot)
+{
+    preprocess_point_bwd_core(pos, scale, rot, mod, mv, mp, tanx, tany, fx, fy, g2x, g2y, gcx, gcy, gcz, gd, dpos, dscale, drot,
+                              false, 0.f, 0.f, 0.f);
+}
+
+LGM_HD void preprocess_point_bwd_moments(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
+                                         const float* mp, float tanx, float tany, float fx, float fy, float W, float H,
+                                         float opacity, float Sx, float Sy, float Sxx, float Sxy, float Syy, float gd,
+                                         float* dpos, float* dscale, float* drot)
+{
+    preprocess_point_bwd_core(pos, scale, rot, mod, mv, mp, tanx, tany, fx, fy, Sx, Sy, Sxx, Sxy, Syy, gd, dpos, dscale, drot,
+                              true, W, H, opacity);
 }
 
 }  // namespace lgm
