@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true", help="e2e: autograd's mse_loss instead of lgm_b200.mse_image_alpha_loss")
     ap.add_argument("--sort-sweep", action="store_true", help="also time every onesweep launch shape (LGM_SORT_VARIANT)")
     ap.add_argument("--loop-baseline", action="store_true",
                     help="also time the reference's per-view driver loop (core/gs.py:42-93) on the same kernels")
@@ -228,6 +229,7 @@ def run_native(args):
 
     copy_stream = torch.cuda.Stream(device=dev)
     mse_sum = torch.nn.functional.mse_loss
+    from lgm_b200 import mse_image_alpha_loss
 
     def step_e2e():
         main = torch.cuda.current_stream()
@@ -242,11 +244,51 @@ def run_native(args):
         main.wait_stream(copy_stream)
         gt_i.record_stream(main)
         gt_m.record_stream(main)
-        # loss of /root/reference/core/models.py:153 (MSE image + MSE alpha), normalised over the whole job
-        loss = mse_sum(out["image"], gt_i, reduction="sum") / (n_views_total * 3 * S * S) + \
-            mse_sum(out["alpha"], gt_m, reduction="sum") / (n_views_total * S * S)
+        # loss of /root/reference/core/models.py:153 (MSE image + MSE alpha), normalised over the whole job; the
+        # package's fused form (lgm_b200.mse_image_alpha_loss) unless --torch-loss
+        if args.torch_loss:
+            loss = mse_sum(out["image"], gt_i, reduction="sum") / (n_views_total * 3 * S * S) + \
+                mse_sum(out["alpha"], gt_m, reduction="sum") / (n_views_total * S * S)
+        else:
+            loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
+                                        w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
         loss.backward()
         return float(loss.item())  # D2H read of the step's result
+
+    def issue_copies():
+        """All inputs of one step, host -> device on the copy stream; returns the device tensors and an event."""
+        with torch.cuda.stream(copy_stream):
+            t = [x.to(dev, non_blocking=True) for x in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host)]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return t, ev
+
+    pending = {"next": None}
+
+    def step_e2e_prefetch():
+        """The same step as step_e2e with the usual data-loader overlap: every step issues the copy of the NEXT step's
+        inputs and consumes the set copied while the previous step computed (reported beside `e2e`, not as `e2e`)."""
+        main = torch.cuda.current_stream()
+        if pending["next"] is None:
+            pending["next"] = issue_copies()
+        (gd, cvd, cvpd, cpd, gt_i, gt_m), ev = pending["next"]
+        main.wait_event(ev)
+        copy_stream.wait_stream(main)  # the next set's buffers may reuse memory the main stream has just released
+        pending["next"] = issue_copies()
+        for t in (gd, cvd, cvpd, cpd, gt_i, gt_m):
+            t.record_stream(main)
+        g = gd.requires_grad_(True)
+        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src)
+        loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
+                                    w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
+        loss.backward()
+        return float(loss.item())
+
+    def step_copies_only():
+        t, ev = issue_copies()
+        torch.cuda.current_stream().wait_event(ev)
+        for x in t:
+            x.record_stream(torch.cuda.current_stream())
 
     def barrier():
         torch.cuda.synchronize()
@@ -282,11 +324,19 @@ def run_native(args):
 
     e2e = None
     if not args.no_e2e:
-        ms_e, _ = timed(step_e2e, max(2, args.steps // 2), 2)
+        ms_e, _ = timed(step_e2e, max(3, args.steps), 3)
         h2d = sum(t.numel() * t.element_size() for t in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host))
+        ms_p, _ = timed(step_e2e_prefetch, max(3, args.steps), 3)
+        ms_c, _ = timed(step_copies_only, 3, 2)
         e2e = {"value": n_views_total / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 8,
-               "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss -> backward -> loss.item()"}
+               "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss "
+                       f"({'torch autograd' if args.torch_loss else 'lgm_b200.mse_image_alpha_loss'}) -> backward -> loss.item(); "
+                       "the ground truth is copied on a side stream while the same step renders",
+               # context: the copies alone, and the step with the next step's inputs prefetched during this one
+               "h2d_alone_ms": ms_c, "h2d_alone_gbs": h2d / (ms_c * 1e-3) / 1e9,
+               "prefetched_inputs": {"value": n_views_total / (ms_p * 1e-3), "ms_per_step": ms_p,
+                                     "what": "each step issues the copy of the next step's inputs and consumes the set copied during the previous step"}}
 
     # ---- stage breakdown + roofline of the HBM-bound group, measured live with CUDA events (rank 0) ----
     stages, roofline, extra = None, None, {}

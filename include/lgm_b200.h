@@ -153,6 +153,17 @@ int lgm_last_bin_mode(void);
 
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
+/* The supervision right after the path: /root/reference/core/models.py:153,
+ *   loss = mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks),
+ * and its gradient in one pass:  *loss = w_image sum (image - gt_image)^2 + w_alpha sum (alpha - gt_alpha)^2 (double),
+ * d_image = 2 s w_image (image - gt_image), d_alpha = 2 s w_alpha (alpha - gt_alpha) — the dL_dimage / dL_dalpha inputs
+ * of lgm_backward; s = *grad_scale (a DEVICE float: autograd's incoming dL/dloss), 1 when grad_scale is NULL.
+ * w = 1 / element count gives the reference's mean reduction.  loss, d_image and d_alpha may each be NULL (output not
+ * wanted).  All pointers 16-byte aligned. */
+int lgm_mse_loss_grad(void* stream, const float* image, const float* gt_image, float* d_image, int64_t n_image,
+                      float w_image, const float* alpha, const float* gt_alpha, float* d_alpha, int64_t n_alpha, float w_alpha,
+                      double* loss, const float* grad_scale);
+
 /* Colours from spherical harmonics — the `shs` argument of GaussianRasterizer.forward
  * (diff_gaussian_rasterization/__init__.py: shs / sh_degree / campos; upstream computeColorFromSH in
  * cuda_rasterizer/forward.cu and its backward in backward.cu).  LGM itself passes colors_precomp

@@ -325,6 +325,22 @@ int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const f
     return LGM_OK;
 }
 
+int lgm_mse_loss_grad(void* stream, const float* image, const float* gt_image, float* d_image, int64_t n_image,
+                      float w_image, const float* alpha, const float* gt_alpha, float* d_alpha, int64_t n_alpha, float w_alpha,
+                      double* loss, const float* grad_scale)
+{
+    if (n_image < 0 || n_alpha < 0) return fail(LGM_ERR_BAD_SHAPE, "negative element count");
+    if (n_image > 0) { LGM_NOTNULL(image); LGM_NOTNULL(gt_image); }
+    if (n_alpha > 0) { LGM_NOTNULL(alpha); LGM_NOTNULL(gt_alpha); }
+    const uintptr_t bits = (uintptr_t)image | (uintptr_t)gt_image | (uintptr_t)d_image | (uintptr_t)alpha | (uintptr_t)gt_alpha |
+                           (uintptr_t)d_alpha;
+    if (bits & 15u) return fail(LGM_ERR_BAD_SHAPE, "mse_loss_grad: pointers must be 16-byte aligned");
+    LGM_CUDA(lgm::launch_mse_loss_grad((cudaStream_t)stream, image, gt_image, d_image, (size_t)n_image, w_image, alpha, gt_alpha,
+                                       d_alpha, (size_t)n_alpha, w_alpha, loss, grad_scale),
+             "mse_loss_grad");
+    return LGM_OK;
+}
+
 static int sh_shape_ok(int32_t n_points, int32_t degree, int32_t max_coeffs)
 {
     if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");

@@ -36,6 +36,10 @@ cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
                                    uint64_t* keys_sorted, void* scratch);
+// loss.cu: MSE(image) + MSE(alpha) and its gradient in one pass (core/models.py:153)
+cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
+                                 float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,
+                                 float w_alpha, double* loss, const float* grad_scale);
 // sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
 cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
                               const float* shs, float* colors, uint8_t* clamped);

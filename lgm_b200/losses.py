@@ -1,0 +1,51 @@
+"""The supervision immediately after the render path: /root/reference/core/models.py:153
+
+    loss_mse = F.mse_loss(pred_images, gt_images) + F.mse_loss(pred_alphas, gt_masks)
+
+as one launch for the loss and one for the gradients w.r.t. the rendered image / alpha, written straight into the
+tensors the compositing backward reads (lgm_mse_loss_grad, lgm_b200/csrc/loss.cu) — instead of autograd's chain of
+elementwise and reduction launches over the images.  No CPU path.
+"""
+import torch
+
+from . import _lib, ops
+
+
+class _MSEImageAlpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_images, pred_alphas, gt_images, gt_masks, w_image, w_alpha):
+        for name, t in (("pred_images", pred_images), ("pred_alphas", pred_alphas), ("gt_images", gt_images), ("gt_masks", gt_masks)):
+            if not t.is_cuda:
+                raise _lib.LgmError(f"{name} must be a CUDA tensor (lgm_b200 has no CPU path)")
+        if pred_images.shape != gt_images.shape or pred_alphas.shape != gt_masks.shape:
+            raise _lib.LgmError("prediction and ground-truth shapes differ")
+        x, a = pred_images.contiguous().float(), pred_alphas.contiguous().float()
+        gx, ga = gt_images.contiguous().float(), gt_masks.contiguous().float()
+        loss = torch.empty(1, dtype=torch.float64, device=x.device)
+        ctx.wi = 1.0 / max(x.numel(), 1) if w_image is None else float(w_image)
+        ctx.wa = 1.0 / max(a.numel(), 1) if w_alpha is None else float(w_alpha)
+        _lib.check(_lib.lib().lgm_mse_loss_grad(ops._stream(), _lib.ptr(x), _lib.ptr(gx), None, x.numel(), ctx.wi,
+                                                _lib.ptr(a), _lib.ptr(ga), None, a.numel(), ctx.wa, _lib.ptr(loss), None),
+                   "lgm_mse_loss_grad")
+        ops.launch_counter["kernels"] += 1
+        ctx.save_for_backward(x, a, gx, ga)
+        return loss[0].float()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x, a, gx, ga = ctx.saved_tensors
+        if grad_loss is None:
+            return None, None, None, None, None, None
+        d_x, d_a = torch.empty_like(x), torch.empty_like(a)
+        scale = grad_loss.reshape(1).float().contiguous()  # stays on the device: no host sync to look at its value
+        _lib.check(_lib.lib().lgm_mse_loss_grad(ops._stream(), _lib.ptr(x), _lib.ptr(gx), _lib.ptr(d_x), x.numel(), ctx.wi,
+                                                _lib.ptr(a), _lib.ptr(ga), _lib.ptr(d_a), a.numel(), ctx.wa, None,
+                                                _lib.ptr(scale)), "lgm_mse_loss_grad")
+        ops.launch_counter["kernels"] += 1
+        return d_x, d_a, None, None, None, None
+
+
+def mse_image_alpha_loss(pred_images, pred_alphas, gt_images, gt_masks, w_image=None, w_alpha=None):
+    """mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks) (mean reduction by default; w_image / w_alpha
+    override the per-element weights, e.g. 1 / global element count when the views are sharded over ranks)."""
+    return _MSEImageAlpha.apply(pred_images, pred_alphas, gt_images, gt_masks, w_image, w_alpha)

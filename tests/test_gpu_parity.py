@@ -627,3 +627,26 @@ def test_patch_sizes_agree(monkeypatch):
         for a, b in zip(res[32][4], res[lanes][4]):
             scale = a.abs().amax(dim=(0, 1), keepdim=True).clamp_min(1e-20)
             assert ((a - b).abs() / scale).max().item() <= 2e-5, f"gradients differ at LGM_PATCH_LANES={lanes}"
+
+
+def test_fused_mse_loss_matches_torch():
+    """lgm_b200.mse_image_alpha_loss = F.mse_loss(image) + F.mse_loss(alpha) of /root/reference/core/models.py:153: value
+    and gradients, odd element counts (scalar tail), a non-unit incoming gradient, explicit weights."""
+    import torch.nn.functional as F
+    from lgm_b200 import mse_image_alpha_loss
+    gen = torch.Generator().manual_seed(3)
+    for shape_i, shape_a in (((2, 3, 3, 37, 41), (2, 3, 1, 37, 41)), ((1, 4, 3, 64, 64), (1, 4, 1, 64, 64))):
+        x = torch.rand(shape_i, generator=gen).to(DEV).requires_grad_(True)
+        a = torch.rand(shape_a, generator=gen).to(DEV).requires_grad_(True)
+        gx, ga = torch.rand(shape_i, generator=gen).to(DEV), (torch.rand(shape_a, generator=gen) > 0.5).float().to(DEV)
+        ref = F.mse_loss(x.double(), gx.double()) + F.mse_loss(a.double(), ga.double())
+        gxr, gar = torch.autograd.grad(3.0 * ref, [x, a])
+        loss = mse_image_alpha_loss(x, a, gx, ga)
+        gx2, ga2 = torch.autograd.grad(3.0 * loss, [x, a])
+        assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+        assert (gx2 - gxr).abs().max().item() <= 1e-6 * gxr.abs().max().item()
+        assert (ga2 - gar).abs().max().item() <= 1e-6 * gar.abs().max().item()
+        # explicit weights (views sharded over ranks: normalise by the global element count)
+        loss_w = mse_image_alpha_loss(x, a, gx, ga, w_image=0.5 / x.numel(), w_alpha=0.25 / a.numel())
+        ref_w = 0.5 * F.mse_loss(x.double(), gx.double()) + 0.25 * F.mse_loss(a.double(), ga.double())
+        assert abs(loss_w.item() - ref_w.item()) <= 1e-6 * abs(ref_w.item())

@@ -119,3 +119,10 @@ def test_shard_views_scene_indices():
         assert bool((scene[1:] >= scene[:-1]).all())
         got.append(vm)
     assert torch.equal(torch.cat(got), cv.reshape(B * V, 16))
+
+
+def test_fused_loss_refuses_cpu_tensors():
+    from lgm_b200 import mse_image_alpha_loss
+    x, a = torch.zeros(1, 2, 3, 8, 8), torch.zeros(1, 2, 1, 8, 8)
+    with pytest.raises(LgmError, match="no CPU path"):
+        mse_image_alpha_loss(x, a, x.clone(), a.clone())
