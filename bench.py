@@ -327,7 +327,7 @@ def run_native(args):
         ms_e, _ = timed(step_e2e, max(3, args.steps), 3)
         h2d = sum(t.numel() * t.element_size() for t in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host))
         ms_p, _ = timed(step_e2e_prefetch, max(3, args.steps), 3)
-        ms_c, _ = timed(step_copies_only, 3, 2)
+        ms_c, _ = timed(step_copies_only, 5, 3)
         e2e = {"value": n_views_total / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 8,
                "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss "
@@ -427,8 +427,10 @@ def run_native(args):
         grp_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + (6 * 24 + 8) * Lr + 8 * Lr + 8 * n_local * n_tiles
         if bin_mode == "direct":
             impl_bytes = n_local * (80 * P_ + 2 * 12 * P_ + 4 * P_) + 20 * Lr + 20 * n_local * n_tiles
-            # dram__bytes_read.sum + dram__bytes_write.sum of K1 + D1..D4 from the ncu --set full capture, per instance
-            traffic = None
+            # dram__bytes_read.sum + dram__bytes_write.sum of K1 + D1..D4 from the ncu --set full capture
+            # (profiles/r01_summary.md): 59.7 B per (view, Gaussian) pair (K1 31.4, count 12.3, scatter's geometry reads 16.0)
+            # and 21.7 B per instance (scatter 10.2, tile sort 11.6)
+            traffic = int(59.7 * n_local * P_ + 21.7 * Lr)
         else:
             impl_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
             traffic = int(n_local * 100 * P_ + 12 * Lr + (npass * 23.6 + 8.0) * Lr + 8 * Lr)
@@ -439,7 +441,11 @@ def run_native(args):
                     "traffic": traffic, "traffic_source": "profiles/r01_summary.md (ncu --set full, dram bytes per launch)",
                     "peak_source": peak_src, "algorithmic_bytes": int(grp_bytes), "implemented_bytes": int(impl_bytes),
                     "achieved_implemented": impl_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
-                    "ms": t_grp, "definition": "SURVEY.md 8d: (80P+20P) per view + (12 + 6*24+8 + 8) per instance + 8 per tile"}
+                    "frac_implemented": impl_bytes / (t_grp * 1e-3) / 1e9 / peak if t_grp > 0 else None,
+                    "ms": t_grp, "definition": "SURVEY.md 8d: (80P+20P) per view + (12 + 6*24+8 + 8) per instance + 8 per tile",
+                    "note": ("SURVEY 8d's algorithmic bytes assume a 6-pass LSD radix sort of the instance list (152 B per instance); "
+                             "the direct path orders each tile in shared memory and moves ~20 B per instance, so frac can exceed 1 — "
+                             "implemented_bytes / traffic give the bytes this implementation needs / moves") if bin_mode == "direct" else None}
         lens = (st.ranges[:, 1] - st.ranges[:, 0]).long()
         pair_evals = int(lens.sum()) * 256
         extra = {

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Writes profiles/<prefix>_sass_<kernel>.txt (cuobjdump -sass of liblgm_b200.so, one file per kernel, first
+instantiation of templated kernels unless listed in KEEP) and profiles/<prefix>_sass_opcode_histograms.txt.
+
+    python scripts/dump_sass.py r01
+"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "lgm_b200", "liblgm_b200.so")
+KEEP = {  # demangled-name substring -> file tag
+    "preprocess_fwd_kernel": "preprocess_fwd_kernel", "preprocess_bwd_kernel": "preprocess_bwd_kernel",
+    "scan_block_sums_kernel": "scan_block_sums_kernel", "emit_kernel": "emit_kernel", "histogram_kernel": "histogram_kernel",
+    "onesweep_kernel<512, 8, 2, false>": "onesweep_kernel", "tile_ranges_kernel": "tile_ranges_kernel",
+    "tile_enumerate_kernel<false>": "tile_count_kernel", "tile_enumerate_kernel<true>": "tile_scatter_kernel",
+    "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel": "tile_bucket_sort_kernel",
+    "composite_fwd_kernel<32>": "composite_fwd_kernel", "composite_bwd_kernel<32, false>": "composite_bwd_kernel",
+    "sh_forward_kernel": "sh_forward_kernel", "sh_backward_kernel": "sh_backward_kernel", "mse_loss_grad_kernel": "mse_loss_grad_kernel",
+}
+
+
+def main():
+    prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    out = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
+    blocks = re.split(r"\n\s*Function : ", out)[1:]
+    names = [b.split("\n", 1)[0].strip() for b in blocks]
+    dem = subprocess.run(["cu++filt"] + names, capture_output=True, text=True, check=True).stdout.splitlines()
+    hist_lines = []
+    done = set()
+    for name, d, b in zip(names, dem, blocks):
+        d_norm = d.replace("(int)", "").replace("(bool)0", "false").replace("(bool)1", "true")
+        for key, tag in KEEP.items():
+            if key in d_norm and tag not in done:
+                done.add(tag)
+                with open(os.path.join(ROOT, "profiles", f"{prefix}_sass_{tag}.txt"), "w") as f:
+                    f.write(f"// {d}\n// cuobjdump -sass lgm_b200/liblgm_b200.so (sm_100a)\n" + b)
+                ops = collections.Counter()
+                for line in b.splitlines():
+                    m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+                    if m:
+                        ops[m.group(1).split(".")[0]] += 1
+                total = sum(ops.values())
+                hist_lines.append(f"== {tag}  ({d[:100]})  {total} SASS instructions\n   " +
+                                  "  ".join(f"{k}:{v}" for k, v in ops.most_common(24)) + "\n")
+    with open(os.path.join(ROOT, "profiles", f"{prefix}_sass_opcode_histograms.txt"), "w") as f:
+        f.write("Static SASS opcode counts per kernel (cuobjdump -sass, sm_100a).  No UTC*MMA / HMMA / UTMALDG: the path has no\n"
+                "dense contraction and its staging is an indexed gather (see DESIGN.md §4).\n\n" + "\n".join(hist_lines))
+    missing = set(KEEP.values()) - done
+    print("written:", sorted(done))
+    if missing:
+        print("NOT FOUND:", sorted(missing))
+
+
+if __name__ == "__main__":
+    main()
