@@ -153,6 +153,12 @@ int lgm_last_bin_mode(void);
 
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
+/* The step right before the path: /root/reference/core/models.py:40-44,107-115 — raw splatter image
+ * x [n_rows,14] -> Gaussians [n_rows,14]: pos = clamp(x[0:3],-1,1), opacity = sigmoid(x[3]), scale = 0.1 softplus(x[4:7]),
+ * rotation = normalize(x[7:11]), rgb = 0.5 tanh(x[11:14]) + 0.5; and its backward (dL_dgaussians -> dL_dx). */
+int lgm_activate_forward(void* stream, int64_t n_rows, const float* x, float* gaussians);
+int lgm_activate_backward(void* stream, int64_t n_rows, const float* x, const float* dL_dgaussians, float* dL_dx);
+
 /* The supervision right after the path: /root/reference/core/models.py:153,
  *   loss = mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks),
  * and its gradient in one pass:  *loss = w_image sum (image - gt_image)^2 + w_alpha sum (alpha - gt_alpha)^2 (double),

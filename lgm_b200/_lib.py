@@ -40,6 +40,8 @@ _SIGNATURES = {
     "lgm_screen_gradients": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp]),
     "lgm_last_bin_mode": (ctypes.c_int, []),
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "lgm_activate_forward": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    "lgm_activate_backward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "lgm_mse_loss_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp]),
     "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sh_backward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

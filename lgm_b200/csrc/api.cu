@@ -341,6 +341,24 @@ int lgm_mse_loss_grad(void* stream, const float* image, const float* gt_image, f
     return LGM_OK;
 }
 
+int lgm_activate_forward(void* stream, int64_t n_rows, const float* x, float* gaussians)
+{
+    if (n_rows < 0) return fail(LGM_ERR_BAD_SHAPE, "n_rows < 0");
+    if (n_rows == 0) return LGM_OK;
+    LGM_NOTNULL(x); LGM_NOTNULL(gaussians);
+    LGM_CUDA(lgm::launch_activate_fwd((cudaStream_t)stream, (size_t)n_rows, x, gaussians), "activate_forward");
+    return LGM_OK;
+}
+
+int lgm_activate_backward(void* stream, int64_t n_rows, const float* x, const float* dL_dgaussians, float* dL_dx)
+{
+    if (n_rows < 0) return fail(LGM_ERR_BAD_SHAPE, "n_rows < 0");
+    if (n_rows == 0) return LGM_OK;
+    LGM_NOTNULL(x); LGM_NOTNULL(dL_dgaussians); LGM_NOTNULL(dL_dx);
+    LGM_CUDA(lgm::launch_activate_bwd((cudaStream_t)stream, (size_t)n_rows, x, dL_dgaussians, dL_dx), "activate_backward");
+    return LGM_OK;
+}
+
 static int sh_shape_ok(int32_t n_points, int32_t degree, int32_t max_coeffs)
 {
     if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");

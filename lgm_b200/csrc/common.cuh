@@ -40,6 +40,9 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
 cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
                                  float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,
                                  float w_alpha, double* loss, const float* grad_scale);
+// activations.cu: raw splatter image [.,14] -> Gaussians (core/models.py:40-44,107-115), forward and backward
+cudaError_t launch_activate_fwd(cudaStream_t stream, size_t n_rows, const float* x, float* g);
+cudaError_t launch_activate_bwd(cudaStream_t stream, size_t n_rows, const float* x, const float* dg, float* dx);
 // sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
 cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
                               const float* shs, float* colors, uint8_t* clamped);

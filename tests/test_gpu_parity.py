@@ -650,3 +650,33 @@ def test_fused_mse_loss_matches_torch():
         loss_w = mse_image_alpha_loss(x, a, gx, ga, w_image=0.5 / x.numel(), w_alpha=0.25 / a.numel())
         ref_w = 0.5 * F.mse_loss(x.double(), gx.double()) + 0.25 * F.mse_loss(a.double(), ga.double())
         assert abs(loss_w.item() - ref_w.item()) <= 1e-6 * abs(ref_w.item())
+
+
+def test_fused_activations_match_torch():
+    """lgm_b200.activate_gaussians = the five activations + cat of /root/reference/core/models.py:40-44,107-115, forward
+    and backward, including the clamp's edges, softplus' threshold and a zero quaternion."""
+    import torch.nn.functional as F
+    from lgm_b200 import activate_gaussians
+    gen = torch.Generator().manual_seed(11)
+    x = (3.0 * torch.randn(2, 5000, 14, generator=gen))
+    x[0, 0, 0:3] = torch.tensor([-1.0, 1.0, 1.5])      # clamp edges (gradient passes at +-1) and outside
+    x[0, 1, 4:7] = torch.tensor([19.5, 20.5, 40.0])    # softplus threshold
+    x[0, 2, 7:11] = 0.0                                # zero quaternion: normalize's eps clamp
+    x[0, 3, 11:14] = torch.tensor([-12.0, 0.0, 12.0])  # saturated tanh
+    w = torch.randn(2, 5000, 14, generator=gen)
+
+    def ref(t):
+        return torch.cat([t[..., 0:3].clamp(-1, 1), torch.sigmoid(t[..., 3:4]), 0.1 * F.softplus(t[..., 4:7]),
+                          F.normalize(t[..., 7:11], dim=-1), 0.5 * torch.tanh(t[..., 11:]) + 0.5], dim=-1)
+
+    xr = x.double().to(DEV).requires_grad_(True)
+    yr = ref(xr)
+    (gr,) = torch.autograd.grad((yr * w.double().to(DEV)).sum(), xr)
+    xg = x.to(DEV).requires_grad_(True)
+    yg = activate_gaussians(xg)
+    (gg,) = torch.autograd.grad((yg * w.to(DEV)).sum(), xg)
+    assert (yg.double() - yr).abs().max().item() <= 2e-6
+    keep = torch.ones_like(gr, dtype=torch.bool)
+    keep[0, 2, 7:11] = False  # at |q| = 0 torch's normalize backward is 0/0-free but eps-scaled; compare separately
+    assert ((gg.double() - gr).abs()[keep] / (1.0 + gr.abs()[keep])).max().item() <= 1e-5
+    assert torch.isfinite(gg).all()

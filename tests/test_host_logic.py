@@ -126,3 +126,9 @@ def test_fused_loss_refuses_cpu_tensors():
     x, a = torch.zeros(1, 2, 3, 8, 8), torch.zeros(1, 2, 1, 8, 8)
     with pytest.raises(LgmError, match="no CPU path"):
         mse_image_alpha_loss(x, a, x.clone(), a.clone())
+
+
+def test_fused_activations_refuse_cpu_and_bad_shapes():
+    from lgm_b200 import activate_gaussians
+    with pytest.raises(LgmError, match="no CPU path"):
+        activate_gaussians(torch.zeros(1, 4, 14))
