@@ -83,9 +83,9 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
  * The list order is upstream's: by tile, then depth bits, ties in emit order (ascending value).  Three internal
  * paths produce it bit for bit (lgm_last_bin_mode tells which ran; environment LGM_BIN_MODE=direct|onesweep|hybrid
  * forces one):
- *   direct   (default when every tile fits the per-tile shared-memory sort) count -> scan -> scatter -> per-tile
- *            sort; costs one extra 4-byte device->host readback (the longest tile) inside this call;
- *   onesweep a stable LSD onesweep radix sort over the (compressed) 64-bit keys (heavy tiles);
+ *   direct   (default when every tile fits the per-tile shared-memory sort: <= 20,480 instances) count -> scan ->
+ *            scatter -> per-tile sort; costs one extra 4-byte device->host readback (the longest tile) in this call;
+ *   onesweep a stable LSD onesweep radix sort over the (compressed) 64-bit keys (tiles beyond that);
  *   hybrid   onesweep over the (view|tile) bits, then a per-tile radix sort of the depth bits.
  * want_sorted_keys == 0 lets direct / hybrid skip writing keys_sorted (its contents are then unspecified);
  * vals_sorted and ranges, all the renderer consumes, are always final. */

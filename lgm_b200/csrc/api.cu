@@ -95,7 +95,7 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
 // the direct path is tried when the MEAN tile holds at most this many instances (a longer mean makes a tile above
 // the shared-memory capacity near certain, and the count pass would be wasted)
-constexpr uint64_t kDirectMaxMeanTile = 2048;
+constexpr uint64_t kDirectMaxMeanTile = 12288;
 
 }  // namespace
 
@@ -194,7 +194,7 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
         if ((int)longest <= lgm::direct_bin_tile_cap()) {
             LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
                                                  reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
-                                                 want_sorted_keys ? keys_sorted : nullptr, ws + w.direct_scratch),
+                                                 want_sorted_keys ? keys_sorted : nullptr, ws + w.direct_scratch, longest),
                      "forward_bin: direct sort");
             g_last_bin_mode = LGM_BIN_DIRECT;
             return LGM_OK;

@@ -35,7 +35,7 @@ cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm
                                     uint2* ranges, void* scratch, const uint32_t** longest_tile_dev);
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
-                                   uint64_t* keys_sorted, void* scratch);
+                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile);
 // loss.cu: MSE(image) + MSE(alpha) and its gradient in one pass (core/models.py:153)
 cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
                                  float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,

@@ -21,8 +21,9 @@
 // D4 is a bucket sort: keys are mapped monotonically to ~n/2 buckets by (depth - min) * nb / (range + 1), counted and
 // grouped with shared-memory atomics (two sweeps), and each element finds its final slot by counting the smaller keys
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
-// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  A tile longer than kSortCap cannot be staged
-// in shared memory: the caller (api.cu) reads the longest tile back and uses the onesweep path for such a step.
+// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Two size classes (M: <= 5,632 instances,
+// 3 CTAs per SM; L: <= 20,480, one 1024-thread CTA per SM).  A longer tile cannot be staged in shared memory: the caller
+// (api.cu) reads the longest tile back and uses the onesweep path for such a step.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -31,10 +32,12 @@
 namespace lgm {
 namespace {
 
-constexpr int kSortThreads = 512;
-constexpr int kSortCap = 5632;      // elements of one tile staged in shared memory (11 per thread)
-constexpr int kMaxBuckets = 2048;
-constexpr size_t kSortSmem = (size_t)kSortCap * 8 + (size_t)kSortCap * 2 + (size_t)(kMaxBuckets + 1) * 4 + 32 * 4;
+// Two size classes of the per-tile sort.  M: tiles of up to 5,632 instances, 512 threads, 63 KB of shared memory, 3 CTAs
+// per SM — the trained-scene case.  L: up to 20,480 instances, 1024 threads, 216 KB, one CTA per SM — untrained
+// Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
+constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
+constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
+constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 32 * 4; }
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
 // Calls f(tile index inside the view, value, depth bits) once per (Gaussian, touched tile) for the Gaussian `idx` of
@@ -185,10 +188,11 @@ cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, 
 
 // D2.  One CTA per view: the view's first slot is the sum of the totals of the views before it, the tiles of the view
 // are scanned in chunks of 256.  Writes ranges[] (empty tiles stay (0,0)), appends the non-empty tiles to the work list
-// (warp-aggregated) and records the longest tile.  head[0] = list length, head[1] = work cursor, head[2] = longest tile.
+// (warp-aggregated) and records the longest tile.  Tiles of the M class (<= kSortCapM) fill the list from the front, longer
+// ones from the back.  head[0] / head[3] = M / L list length, head[1] / head[4] = their work cursors, head[2] = longest.
 __global__ void __launch_bounds__(kBlock)
 tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ view_totals, int n_tiles,
-                        uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
+                        uint32_t n_ranges, uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
 {
     __shared__ uint32_t s_warp[8];
     const int view = blockIdx.x, t = threadIdx.x, lane = t & 31;
@@ -206,40 +210,54 @@ tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __r
         carry += tot;
         if (i < n_tiles) ranges[gt] = n ? make_uint2(start, start + n) : make_uint2(0u, 0u);
         longest = max(longest, n);
-        const unsigned m = __ballot_sync(0xffffffffu, n != 0u);
+        const bool is_m = n != 0u && n <= (uint32_t)kSortCapM, is_l = n > (uint32_t)kSortCapM;
+        const unsigned m = __ballot_sync(0xffffffffu, is_m);
         if (m) {
             const int leader = __ffs(m) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&head[0], (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (n) list[base + __popc(m & ((1u << lane) - 1u))] = gt;
+            if (is_m) list[base + __popc(m & ((1u << lane) - 1u))] = gt;
+        }
+        const unsigned ml = __ballot_sync(0xffffffffu, is_l);
+        if (ml) {
+            const int leader = __ffs(ml) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&head[3], (uint32_t)__popc(ml));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_l) list[n_ranges - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = gt;
         }
     }
     longest = __reduce_max_sync(0xffffffffu, longest);
     if (lane == 0 && longest) atomicMax(&head[2], longest);
 }
 
-// D4.  Persistent CTAs pull tiles from the work list.
-__global__ void __launch_bounds__(kSortThreads, 3)
+// D4.  Persistent CTAs pull tiles from a work list: list[item * list_step] for item < *n_list_ptr, items handed out
+// through *cursor.
+template <int T, int CAP, int LG_MAXB, int MIN_BLOCKS>
+__global__ void __launch_bounds__(T, MIN_BLOCKS)
 tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ list,
-                        uint32_t* __restrict__ head, uint32_t* __restrict__ vals_sorted, uint64_t* __restrict__ keys_sorted)
+                        int list_step, const uint32_t* __restrict__ n_list_ptr, uint32_t* __restrict__ cursor,
+                        uint32_t* __restrict__ vals_sorted, uint64_t* __restrict__ keys_sorted)
 {
+    constexpr int kSortCap = CAP, kMaxBuckets = 1 << LG_MAXB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);                                // [kSortCap] depth << 32 | value
     uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSortCap * 8);      // [kSortCap] bucket-grouped indices
     uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 10);    // [kMaxBuckets + 1]
     uint32_t* s_red = bucket + kMaxBuckets + 1;                                          // [32]
     __shared__ uint32_t s_item;
-    constexpr int T = kSortThreads, kWarps = T / 32;
+    constexpr int kWarps = T / 32;
+    static_assert(CAP < 65536 && (kWarps & (kWarps - 1)) == 0 && kWarps <= 32, "16-bit indices, power-of-two warps");
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t n_list = head[0];
+    const uint32_t n_list = *n_list_ptr;
 
     while (true) {
-        if (t == 0) s_item = atomicAdd(&head[1], 1u);
+        if (t == 0) s_item = atomicAdd(cursor, 1u);
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_list) break;
-        const uint32_t tile = list[item];
+        const uint32_t tile = list[(ptrdiff_t)item * list_step];
         const uint2 range = ranges[tile];
         const int n = (int)(range.y - range.x);
         const uint2* src = pairs + range.x;
@@ -248,9 +266,9 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
             continue;
         }
 
-        // number of buckets: a power of two in [n/2, n), 32..kMaxBuckets
+        // number of buckets: a power of two in [n/2, n), 32..kMaxBuckets (n up to 5 kMaxBuckets in the L class)
         int lg_nb = 32 - __clz((unsigned)max(n - 1, 1)) - 1;
-        lg_nb = min(max(lg_nb, 5), 11);
+        lg_nb = min(max(lg_nb, 5), LG_MAXB);
         const int nb = 1 << lg_nb;
 
         // sweep 0: stage, min / max of the depth bits
@@ -328,7 +346,7 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
 
 }  // namespace
 
-int direct_bin_tile_cap() { return kSortCap; }
+int direct_bin_tile_cap() { return kSortCapL; }
 
 // scratch of the direct path: head [64 u32] | view totals [n_views, padded to 64] | counts [n_ranges] | list [n_ranges]
 struct DirectScratch {
@@ -360,21 +378,27 @@ cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm
     if (err != cudaSuccess) return err;
     if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, d.counts, d.view_totals, nullptr, nullptr)) != cudaSuccess)
         return err;
-    tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(d.counts, d.view_totals, prm.n_tiles, ranges, d.list, d.head);
+    tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(d.counts, d.view_totals, prm.n_tiles,
+                                                                (uint32_t)prm.n_views * (uint32_t)prm.n_tiles, ranges, d.list, d.head);
     *longest_tile_dev = d.head + 2;
     return cudaGetLastError();
 }
 
-// D3 + D4.  pairs: L x 8 B of workspace.  keys_sorted may be null (keys not wanted).
+// D3 + D4.  pairs: L x 8 B of workspace.  keys_sorted may be null (keys not wanted).  longest_tile: the value read back
+// after launch_direct_bin_count (decides whether the L-class launch is needed).
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
-                                   uint64_t* keys_sorted, void* scratch)
+                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile)
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
     const DirectScratch d = direct_scratch(prm, scratch);
+    auto* sort_m = tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3>;
+    auto* sort_l = tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1>;
+    constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_l = sort_smem(kSortCapL, kLgBucketsL);
     static int n_sm = 0;
     if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(tile_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+        cudaError_t e = cudaFuncSetAttribute(sort_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -383,9 +407,16 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
     cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, ranges,
                                                   static_cast<uint2*>(pairs));
     if (err != cudaSuccess) return err;
+    // the long tiles first: they are the critical path of the tail
+    if (longest_tile > (uint32_t)kSortCapM) {
+        const uint32_t n_cta = (uint32_t)min((unsigned)n_sm, n_ranges);
+        sort_l<<<n_cta, kSortThreadsL, smem_l, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list + (n_ranges - 1), -1,
+                                                        d.head + 3, d.head + 4, vals_sorted, keys_sorted);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
     const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
-    tile_bucket_sort_kernel<<<n_cta, kSortThreads, kSortSmem, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, d.head,
-                                                                        vals_sorted, keys_sorted);
+    sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head, d.head + 1,
+                                                    vals_sorted, keys_sorted);
     return cudaGetLastError();
 }
 

@@ -496,9 +496,10 @@ def _same_binning(a, b):
 def test_binning_modes_are_bit_identical(monkeypatch):
     """The three binning paths of lgm_forward_bin — direct (count / scatter / per-tile shared-memory sort, direct_bin.cu),
     onesweep (one LSD sort of the 64-bit keys) and hybrid (onesweep on the tile bits + per-tile radix sort) — give the
-    same sorted keys / values / ranges / image, light and heavy tiles alike; direct hands a step whose longest tile
-    exceeds its shared-memory capacity to onesweep."""
-    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 30000, 64)):
+    same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632 and L-class
+    tiles <= 20,480 instances); direct hands a step whose longest tile exceeds its shared-memory capacity to onesweep."""
+    seen = set()
+    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 20000, 64), ("init", 60000, 64)):
         g = make_gaussians(2, N, kind, seed=17).numpy()
         cv, cvp, _ = make_cameras(2, 2, seed=17)
         res = {m: _bin_result(monkeypatch, m, g, cv, cvp, S) for m in ("onesweep", "hybrid", "direct", "auto")}
@@ -506,10 +507,11 @@ def test_binning_modes_are_bit_identical(monkeypatch):
         for m in ("hybrid", "direct", "auto"):
             assert _same_binning(res["onesweep"], res[m]), f"{kind} N={N}: mode {m} differs from onesweep"
         longest = res["onesweep"]["longest"]
-        assert res["direct"]["ran"] == ("direct" if longest <= 5632 else "onesweep"), (longest, res["direct"]["ran"])
+        assert res["direct"]["ran"] == ("direct" if longest <= 20480 else "onesweep"), (longest, res["direct"]["ran"])
         if kind == "trained":
             assert res["auto"]["ran"] == "direct"
-    assert longest > 5632  # the last case exercised the hand-over
+        seen.add("M" if longest <= 5632 else ("L" if longest <= 20480 else "handover"))
+    assert seen == {"M", "L", "handover"}, seen  # every size class and the hand-over were exercised
 
 
 def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
