@@ -37,7 +37,7 @@ namespace {
 // Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
 constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
 constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
-constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 32 * 4; }
+constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
 // Calls f(tile index inside the view, value, depth bits) once per (Gaussian, touched tile) for the Gaussian `idx` of
@@ -245,7 +245,7 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
     uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);                                // [kSortCap] depth << 32 | value
     uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSortCap * 8);      // [kSortCap] bucket-grouped indices
     uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 10);    // [kMaxBuckets + 1]
-    uint32_t* s_red = bucket + kMaxBuckets + 1;                                          // [32]
+    uint32_t* s_red = bucket + kMaxBuckets + 1;                                          // [64]: min and max per warp
     __shared__ uint32_t s_item;
     constexpr int kWarps = T / 32;
     static_assert(CAP < 65536 && (kWarps & (kWarps - 1)) == 0 && kWarps <= 32, "16-bit indices, power-of-two warps");
