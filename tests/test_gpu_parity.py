@@ -498,8 +498,8 @@ def test_binning_modes_are_bit_identical(monkeypatch):
     onesweep (one LSD sort of the 64-bit keys) and hybrid (onesweep on the tile bits + per-tile radix sort) — give the
     same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632 and L-class
     tiles <= 20,480 instances); direct hands a step whose longest tile exceeds its shared-memory capacity to onesweep."""
-    seen = set()
-    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 20000, 64), ("init", 60000, 64)):
+    seen, lens = set(), []
+    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 60000, 64), ("init", 60000, 32)):
         g = make_gaussians(2, N, kind, seed=17).numpy()
         cv, cvp, _ = make_cameras(2, 2, seed=17)
         res = {m: _bin_result(monkeypatch, m, g, cv, cvp, S) for m in ("onesweep", "hybrid", "direct", "auto")}
@@ -511,7 +511,8 @@ def test_binning_modes_are_bit_identical(monkeypatch):
         if kind == "trained":
             assert res["auto"]["ran"] == "direct"
         seen.add("M" if longest <= 5632 else ("L" if longest <= 20480 else "handover"))
-    assert seen == {"M", "L", "handover"}, seen  # every size class and the hand-over were exercised
+        lens.append(longest)
+    assert seen == {"M", "L", "handover"}, (seen, lens)  # every size class and the hand-over were exercised
 
 
 def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
