@@ -120,14 +120,21 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     const float* src = gaussians + ((size_t)scene * prm.P + base) * 14;
     stage_rows(s_g, src, n);
     __syncthreads();
-    float g[14];
-    float d[14];
+    // Carried through the view loop: position, opacity, the view-independent 3D covariance; accumulated: dL/dpos,
+    // dL/dopacity, dL/drgb and g6 = dL/dcov3D (mapped to scale / rotation once, after the loop — linear in g6).
+    float pos[3] = {0.f, 0.f, 0.f}, opacity = 0.f, cov6[6];
+    float d[14], g6[6];
 #pragma unroll
     for (int k = 0; k < 14; k++) d[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) g6[k] = cov6[k] = 0.f;
     const bool active = (int)threadIdx.x < n;
     if (active) {
-#pragma unroll
-        for (int k = 0; k < 14; k++) g[k] = s_g[threadIdx.x * 14 + k];
+        const float* g = s_g + threadIdx.x * 14;
+        float M[9];
+        pos[0] = g[0]; pos[1] = g[1]; pos[2] = g[2];
+        opacity = g[3];
+        cov3d_from_scale_rot(g[4], g[5], g[6], prm.mod, g[7], g[8], g[9], g[10], cov6, M);
     }
     const int v0 = scene_view_offsets[scene], v1 = scene_view_offsets[scene + 1];
     for (int v = v0; v < v1; v++) {
@@ -141,13 +148,14 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
         const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
         // r0 = (Sx, Sy, Sxx, Sxy)  r1 = (Syy, S0 = dL/dopacity, col.r, col.g)  r2 = (col.b, depth, -, -): moment form
-        preprocess_point_bwd_moments(g, g + 4, g + 7, prm.mod, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, (float)prm.W,
-                                     (float)prm.H, g[3], r0.x, r0.y, r0.z, r0.w, r1.x, r2.y, d, d + 4, d + 7);
+        preprocess_point_bwd_view(pos, cov6, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, r0.x, r0.y, r0.z, r0.w, r1.x, r2.y,
+                                  d, g6, /*moments=*/true, (float)prm.W, (float)prm.H, opacity);
         d[3] += r1.y;
         d[11] += r1.z;
         d[12] += r1.w;
         d[13] += r2.x;
     }
+    if (active) preprocess_point_bwd_finish(s_g + threadIdx.x * 14 + 4, s_g + threadIdx.x * 14 + 7, prm.mod, g6, d + 4, d + 7);
     // transpose through shared memory for coalesced stores of the 14-float rows
     __syncthreads();
     if (active) {

@@ -231,18 +231,20 @@ LGM_HD void moments_to_gradients(float W, float H, float cxx, float cxy, float c
     *gcz = h * Syy;
 }
 
+// Preprocess backward, split so that a caller summing over the views of a scene (K7) pays the view-independent part
+// once: `_view` is everything that depends on the camera — (i) conic -> cov2D -> cov3D gradient g6 and the mean through
+// the EWA Jacobian, (ii) projection, (iii) depth — and ACCUMULATES dL/dpos and g6 = dL/dcov3D; `_finish` maps the summed
+// g6 to scale / rotation ((v): linear in g6 for a fixed scale and rotation).
 // moments = false: (g2x, g2y) = dL/dmean2D, (gcx, gcy, gcz) = dL/dconic as upstream passes them.
 // moments = true : the same five arguments carry (Sx, Sy, Sxx, Sxy, Syy) and are converted here, with the conic
 // re-derived from the 2D covariance this function computes anyway (W, H = image size, opacity = the Gaussian's).
-LGM_HD void preprocess_point_bwd_core(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
-                                      const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
-                                      float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot,
-                                      bool moments, float W, float H, float opacity)
+LGM_HD void preprocess_point_bwd_view(const float* pos, const float* cov6, const float* mv, const float* mp, float tanx,
+                                      float tany, float fx, float fy, float g2x, float g2y, float gcx, float gcy, float gcz,
+                                      float gd, float* dpos, float* g6acc, bool moments, float W, float H, float opacity)
 {
     const float x = pos[0], y = pos[1], z = pos[2];
     const float pvx = affine_row(mv, 0, x, y, z), pvy = affine_row(mv, 1, x, y, z), pvz = affine_row(mv, 2, x, y, z);
-    float cov6[6], M[9], abc[3], Tm[6], t[3], txtz, tytz;
-    cov3d_from_scale_rot(scale[0], scale[1], scale[2], mod, rot[0], rot[1], rot[2], rot[3], cov6, M);
+    float abc[3], Tm[6], t[3], txtz, tytz;
     cov2d_ewa(pvx, pvy, pvz, fx, fy, tanx, tany, cov6, mv, abc, Tm, t, &txtz, &tytz);
     const float limx = 1.3f * tanx, limy = 1.3f * tany;
     const float xg = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
@@ -303,6 +305,15 @@ LGM_HD void preprocess_point_bwd_core(const float* pos, const float* scale, cons
     dm1 += (mv[6] - mv[7] * mul3) * gd;
     dm2 += (mv[10] - mv[11] * mul3) * gd;
     dpos[0] += dm0; dpos[1] += dm1; dpos[2] += dm2;
+#pragma unroll
+    for (int k = 0; k < 6; k++) g6acc[k] += g6[k];
+}
+
+LGM_HD void preprocess_point_bwd_finish(const float* scale, const float* rot, float mod, const float* g6, float* dscale,
+                                        float* drot)
+{
+    float cov6[6], M[9];
+    cov3d_from_scale_rot(scale[0], scale[1], scale[2], mod, rot[0], rot[1], rot[2], rot[3], cov6, M);
     // (v) cov3D -> scale / rotation.  dA = 2 * Gsym * (Rq S)
     const float Gs[9] = {g6[0], 0.5f * g6[1], 0.5f * g6[2], 0.5f * g6[1], g6[3], 0.5f * g6[4], 0.5f * g6[2], 0.5f * g6[4], g6[5]};
     float dA[9];
@@ -331,6 +342,18 @@ LGM_HD void preprocess_point_bwd_core(const float* pos, const float* scale, cons
     drot[2] += 2.f * qx * (LGM_DMT(1, 0) + LGM_DMT(0, 1)) + 2.f * r * (LGM_DMT(2, 0) - LGM_DMT(0, 2)) + 2.f * qz * (LGM_DMT(1, 2) + LGM_DMT(2, 1)) - 4.f * qy * (LGM_DMT(2, 2) + LGM_DMT(0, 0));
     drot[3] += 2.f * r * (LGM_DMT(0, 1) - LGM_DMT(1, 0)) + 2.f * qx * (LGM_DMT(2, 0) + LGM_DMT(0, 2)) + 2.f * qy * (LGM_DMT(1, 2) + LGM_DMT(2, 1)) - 4.f * qz * (LGM_DMT(1, 1) + LGM_DMT(0, 0));
 #undef LGM_DMT
+}
+
+LGM_HD void preprocess_point_bwd_core(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
+                                      const float* mp, float tanx, float tany, float fx, float fy, float g2x, float g2y,
+                                      float gcx, float gcy, float gcz, float gd, float* dpos, float* dscale, float* drot,
+                                      bool moments, float W, float H, float opacity)
+{
+    float cov6[6], M[9], g6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    cov3d_from_scale_rot(scale[0], scale[1], scale[2], mod, rot[0], rot[1], rot[2], rot[3], cov6, M);
+    preprocess_point_bwd_view(pos, cov6, mv, mp, tanx, tany, fx, fy, g2x, g2y, gcx, gcy, gcz, gd, dpos, g6, moments, W,
+                              H, opacity);
+    preprocess_point_bwd_finish(scale, rot, mod, g6, dscale, drot);
 }
 
 LGM_HD void preprocess_point_bwd(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
