@@ -499,7 +499,7 @@ def test_binning_modes_are_bit_identical(monkeypatch):
     same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632 and L-class
     tiles <= 20,480 instances); direct hands a step whose longest tile exceeds its shared-memory capacity to onesweep."""
     seen, lens = set(), []
-    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 60000, 64), ("init", 60000, 32)):
+    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 60000, 64), ("init", 120000, 32)):
         g = make_gaussians(2, N, kind, seed=17).numpy()
         cv, cvp, _ = make_cameras(2, 2, seed=17)
         res = {m: _bin_result(monkeypatch, m, g, cv, cvp, S) for m in ("onesweep", "hybrid", "direct", "auto")}
