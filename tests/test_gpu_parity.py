@@ -683,3 +683,26 @@ def test_fused_activations_match_torch():
     keep[0, 2, 7:11] = False  # at |q| = 0 torch's normalize backward is 0/0-free but eps-scaled; compare separately
     assert ((gg.double() - gr).abs()[keep] / (1.0 + gr.abs()[keep])).max().item() <= 1e-5
     assert torch.isfinite(gg).all()
+
+
+def test_forward_only_orbit_is_one_batched_call():
+    """SURVEY.md 8f N3 (infer.py:113-145 / gui.py): an orbit of many views of one object under torch.no_grad() is ONE
+    batched render call that keeps no backward state, with scale_modifier != 1, and equals the same views rendered
+    with autograd enabled."""
+    from lgm_b200 import GaussianRenderer, default_options, ops
+    opt = default_options(output_size=96)
+    r = GaussianRenderer(opt, device=DEV)
+    g = make_gaussians(1, 8000, "trained", seed=31).to(DEV)
+    g[:, :, 4:7] *= 4.0
+    cv, cvp, cp = make_cameras(1, 60, seed=31)
+    k0 = ops.launch_counter["kernels"]
+    with torch.no_grad():
+        out = r.render(g, cv.to(DEV), cvp.to(DEV), cp.to(DEV), scale_modifier=0.7)
+    n_launch = ops.launch_counter["kernels"] - k0
+    assert out["image"].shape == (1, 60, 3, 96, 96) and not out["image"].requires_grad
+    assert n_launch <= 12, n_launch  # one set of launches for all 60 views, not one per view
+    g2 = g.clone().requires_grad_(True)
+    ref = r.render(g2, cv.to(DEV), cvp.to(DEV), cp.to(DEV), scale_modifier=0.7)
+    for k in ("image", "alpha", "depth"):
+        assert torch.equal(out[k], ref[k])
+    assert float(out["alpha"].max()) > 0.5
