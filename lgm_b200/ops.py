@@ -79,11 +79,14 @@ def _check_cuda_f32(t, name, shape_tail=None):
 class ForwardState:
     """Everything the backward needs (the analogue of upstream's geomBuffer / binningBuffer / imgBuffer)."""
     __slots__ = ("cfg", "n_scenes", "P", "n_views", "view_scene", "scene_view_offsets", "depth", "radii", "xy",
-                 "conic_opacity", "vals", "ranges", "n_contrib", "num_rendered", "keys", "tiles_touched")
+                 "conic_opacity", "vals", "ranges", "n_contrib", "num_rendered", "keys", "tiles_touched", "grad_rows")
 
 
-def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg: ViewConfig):
-    """All views in one set of launches.  Returns (image [VW,3,H,W], alpha [VW,1,H,W], depth [VW,1,H,W], state)."""
+def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg: ViewConfig,
+                  prepare_backward=False):
+    """All views in one set of launches.  Returns (image [VW,3,H,W], alpha [VW,1,H,W], depth [VW,1,H,W], state).
+    prepare_backward: also allocate and zero the backward's gradient rows now — the fill then runs on the GPU while
+    the host waits for the instance count, instead of at the head of the backward."""
     L = _lib.lib()
     _check_cuda_f32(gaussians, "gaussians", (14,))
     _check_cuda_f32(view_mats, "view_mats", (16,))
@@ -114,6 +117,13 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.tiles_touched), _lib.ptr(block_sums),
         _lib.ptr(block_offsets), _lib.ptr(total)), "lgm_forward_geom"))
     launch_counter["kernels"] += 2 if npair else 0
+    # work that does not depend on the instance count is queued before the host waits for it
+    st.grad_rows = torch.zeros(max(npair, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev) if prepare_backward else None
+    image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
+    alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
+    depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
+    st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
+    st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
     # The ONE host<->device synchronisation of the step (upstream: one per view): the instance count sizes the
     # sort buffers.
     n_inst = int(total.item())
@@ -124,12 +134,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     _lib.check(L.lgm_bin_workspace_bytes(prm, n_inst, ws_bytes), "lgm_bin_workspace_bytes")
     keys = torch.empty(max(n_inst, 1), dtype=torch.int64, device=dev)
     st.vals = torch.empty(max(n_inst, 1), dtype=torch.int32, device=dev)
-    st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
     workspace = torch.empty(max(int(ws_bytes.value), 1), dtype=torch.uint8, device=dev)
-    image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
-    alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
-    depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
-    st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
     # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)
     _timed("bin", lambda: _lib.check(L.lgm_forward_bin(
         s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, _lib.ptr(keys),
@@ -181,7 +186,10 @@ def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha,
     cfg = st.cfg
     prm = _lib.make_params(st.n_scenes, st.P, st.n_views, cfg.image_height, cfg.image_width, cfg.tanfovx, cfg.tanfovy,
                            cfg.scale_modifier)
-    grad_rows = torch.zeros(max(st.n_views * st.P, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev)
+    grad_rows = getattr(st, "grad_rows", None)  # zeroed during the forward when the caller announced a backward
+    st.grad_rows = None                          # used once: a second backward over the same state gets fresh rows
+    if grad_rows is None:
+        grad_rows = torch.zeros(max(st.n_views * st.P, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev)
     d_gauss = torch.empty_like(gaussians)
     # (lgm_backward is these two calls back to back)
     _timed("composite_bwd", lambda: _lib.check(L.lgm_backward_composite(
@@ -223,7 +231,7 @@ class _RenderViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg):
         image, alpha, depth_img, st = forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg,
-                                                    cfg)
+                                                    cfg, prepare_backward=ctx.needs_input_grad[0])
         ctx.st = st
         ctx.set_materialize_grads(False)  # an unused output (depth, in LGM) arrives as None, not as a zero image
         ctx.save_for_backward(gaussians, view_mats, proj_mats, bg, alpha)
