@@ -9,8 +9,9 @@ A step = one pass of the hot path over one batch of synthetic input: GaussianRen
 (forward), then backward from given upstream gradients to dL/d[B,N,14] (clamp mask included), as
 /root/reference/core/models.py:141 + main.py:102 drive it.  Workload at N = 1 ("zero123g", BASELINE.json configs[2],
 the configuration the north_star target is quoted on): 8 scenes x 26 views, 98,304 Gaussians per scene, 320^2,
-fovy 60.  At N GPUs the step has 8N scenes (weak scaling): the B*V views are partitioned across ranks, Gaussians are
-broadcast from rank 0, per-Gaussian gradients are combined with one NCCL all-reduce.
+fovy 60.  At N GPUs the step has 8N scenes (weak scaling): the B*V views are partitioned across ranks; rank 0 produces the
+Gaussians and wants their gradient, so every rank is sent the scenes it renders and returns its block of
+the gradient (lgm_b200.dist, producer_only: NCCL scatter + gather; all-reduce / all-gather when every rank needs it).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job views/s with inputs resident in HBM; `e2e` = the same metric
 with, every step, the step's inputs (Gaussians, cameras, ground-truth images and masks) copied from pinned host
@@ -231,9 +232,9 @@ def run_native(args):
     def step_resident():
         if forward_only:
             with torch.no_grad():
-                return renderer.render(g_dev, cv_dev, cvp_dev, cp_dev, bg_color=bg, broadcast_src=src)["image"]
+                return renderer.render(g_dev, cv_dev, cvp_dev, cp_dev, bg_color=bg, broadcast_src=src, producer_only=True)["image"]
         g = g_dev.detach().requires_grad_(True)
-        out = renderer.render(g, cv_dev, cvp_dev, cp_dev, bg_color=bg, broadcast_src=src)
+        out = renderer.render(g, cv_dev, cvp_dev, cp_dev, bg_color=bg, broadcast_src=src, producer_only=True)
         torch.autograd.backward([out["image"], out["alpha"]], [d_img, d_alpha])
         return g.grad
 
@@ -250,7 +251,7 @@ def run_native(args):
         copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             gt_i, gt_m = gt_img_host.to(dev, non_blocking=True), gt_mask_host.to(dev, non_blocking=True)
-        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src)
+        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
         main.wait_stream(copy_stream)
         gt_i.record_stream(main)
         gt_m.record_stream(main)
@@ -288,7 +289,7 @@ def run_native(args):
         for t in (gd, cvd, cvpd, cpd, gt_i, gt_m):
             t.record_stream(main)
         g = gd.requires_grad_(True)
-        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src)
+        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
         loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
                                     w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
         loss.backward()
@@ -533,7 +534,7 @@ def run_native(args):
             "config": {"workload": f"{args.workload}: {cfgname}; per GPU {Bg} scenes x {V} views = {Bg * V} views/step, "
                                    f"{args.kind}-like Gaussians (SURVEY.md 8d), step = {B} scenes view-sharded over {world} GPU(s)",
                        "global_views": n_views_total, "gaussians_per_scene": N, "image": f"{S}x{S}",
-                       "parallelism": f"view-sharded x{world}" + (", broadcast + NCCL all-reduce of [B,N,14] grads" if world > 1 else ""),
+                       "parallelism": f"view-sharded x{world}" + (", Gaussians scattered from rank 0 (each rank receives the scenes it renders), [B,N,14] gradient blocks gathered to rank 0 (NCCL)" if world > 1 else ""),
                        "l2": (f"per-step working set {working_set / 1e6:.0f} MB + instances: L2 flushed (256 MB write) between the "
                               "timed steps, each step timed on its own") if flush_l2 else
                              (f"per-step working set ({working_set / 1e9:.1f} GB of geometry, gradient rows and images, plus the "

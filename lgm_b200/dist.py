@@ -29,14 +29,29 @@ def scene_blocks(n_scenes, views_per_scene, world_size):
 class _ReplicatedInput(torch.autograd.Function):
     """Identity in forward (optionally a broadcast from `src`); sum of the ranks' gradients in backward, so the
     collective sits in the autograd graph of `gaussians` exactly once per step.  The sum is an all-reduce in general;
-    when every rank owns whole scenes (`block` scenes each) it is an all-gather of the owned blocks."""
+    when every rank owns whole scenes (`block` scenes each) it is an all-gather of the owned blocks.
+
+    producer_only (needs `src` and whole-scene blocks): the Gaussians exist on `src` alone and only `src` wants their
+    gradient.  Then every rank is SENT just the scenes it renders (scatter; the other rows of its tensor are never read)
+    and returns just its block of the gradient to `src` (gather) — 1/world of the bytes of broadcast + all-gather on
+    every rank but `src`.  On the other ranks the returned gradient holds their own block only."""
 
     @staticmethod
-    def forward(ctx, x, group, src, block):
-        ctx.group, ctx.block = group, block
-        if src is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-            x = x.contiguous().clone()
-            dist.broadcast(x, src=src, group=group)
+    def forward(ctx, x, group, src, block, producer_only):
+        ctx.group, ctx.block, ctx.src = group, block, src
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        ctx.producer_only = bool(producer_only and multi and src is not None and block is not None and
+                                 x.shape[0] == block * dist.get_world_size(group))
+        if src is not None and multi:
+            rank = dist.get_rank(group)
+            if ctx.producer_only:
+                x_in = x.detach().contiguous()
+                x = torch.empty_like(x_in)  # only this rank's scenes are filled in — and only they are read
+                dist.scatter(x[rank * block:(rank + 1) * block], scatter_list=list(x_in.split(block)) if rank == src else None,
+                             src=src, group=group)
+            else:
+                x = x.contiguous().clone()
+                dist.broadcast(x, src=src, group=group)
         return x.view_as(x)
 
     @staticmethod
@@ -44,18 +59,24 @@ class _ReplicatedInput(torch.autograd.Function):
         g = g.contiguous()
         if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
             world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
-            if ctx.block is not None and g.shape[0] == ctx.block * world:
+            if ctx.producer_only:
+                mine = g[rank * ctx.block:(rank + 1) * ctx.block].contiguous()
+                out = torch.empty_like(g) if rank == ctx.src else None
+                dist.gather(mine, gather_list=list(out.split(ctx.block)) if rank == ctx.src else None, dst=ctx.src,
+                            group=ctx.group)
+                g = out if rank == ctx.src else g
+            elif ctx.block is not None and g.shape[0] == ctx.block * world:
                 out = torch.empty_like(g)
                 dist.all_gather_into_tensor(out, g[rank * ctx.block:(rank + 1) * ctx.block].contiguous(), group=ctx.group)
                 g = out
             else:
                 g = g.clone()
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None, None, None
+        return g, None, None, None, None
 
 
-def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None, scenes_per_rank=None):
-    return _ReplicatedInput.apply(gaussians, group, broadcast_src, scenes_per_rank)
+def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None, scenes_per_rank=None, producer_only=False):
+    return _ReplicatedInput.apply(gaussians, group, broadcast_src, scenes_per_rank, producer_only)
 
 
 def shard_views(cam_view, cam_view_proj, cam_pos, rank=None, world_size=None):
@@ -81,19 +102,22 @@ class ShardedGaussianRenderer:
     render() returns this rank's views only: image [n_local,3,H,W], alpha, depth [n_local,1,H,W] and the (begin,end)
     block of the flattened B*V index space.  Back-propagating any loss on them yields, on EVERY rank, the gradient
     of the sum of all ranks' losses w.r.t. `gaussians` (one collective: all-reduce, or all-gather when every rank
-    owns whole scenes)."""
+    owns whole scenes).  With `broadcast_src` and `producer_only=True` the Gaussians are taken from rank `broadcast_src`
+    alone and the summed gradient is delivered to that rank alone (scatter + gather instead of broadcast + all-gather
+    when every rank owns whole scenes)."""
 
     def __init__(self, opt, device="cuda", group=None):
         from .renderer import GaussianRenderer
         self.inner = GaussianRenderer(opt, device=device)
         self.group = group
 
-    def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1, broadcast_src=None):
+    def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1, broadcast_src=None,
+               producer_only=False):
         from . import ops
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         g = replicate_for_view_sharding(gaussians.contiguous().float(), self.group, broadcast_src,
-                                        scene_blocks(cam_view.shape[0], cam_view.shape[1], world))
+                                        scene_blocks(cam_view.shape[0], cam_view.shape[1], world), producer_only)
         vm, pm, _cp, scene, (b, e) = shard_views(cam_view, cam_view_proj, cam_pos, rank, world)
         S = int(self.inner.opt.output_size)
         bg = (self.inner.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
