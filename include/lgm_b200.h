@@ -77,6 +77,13 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
                      float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
                      uint64_t* total_instances);
 
+/* The same with upstream's cov3D_precomp: cov3d [n_scenes, P, 6] (xx, xy, xz, yy, yz, zz) replaces the covariance built
+ * from the scale / rotation columns of `gaussians` (which are then ignored); NULL = lgm_forward_geom. */
+int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                           const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                           float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                           uint64_t* total_instances, const float* cov3d);
+
 /* K2 emit + K3 sort + K4 ranges.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
  * n_instances = the value forward_geom left in total_instances.  keys_sorted u64[L] (view*tiles+tile << 32 |
  * depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges uint2[n_views * tiles] = [start,end).
@@ -138,6 +145,13 @@ int lgm_backward_composite(void* stream, const lgm_render_params* prm, const flo
 int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
                       const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
                       const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate);
+/* K7 for a forward that used cov3D_precomp: the gradient stops at the covariance — dL_dcov3d [n_scenes, P, 6] (upstream's
+ * dL_dcov3D layout: off-diagonal entries carry both symmetric halves) is written (added to when accumulate != 0), the
+ * scale / rotation columns of dL_dgaussians are zero.  cov3d == NULL and dL_dcov3d == NULL = lgm_backward_geom. */
+int lgm_backward_geom_cov3d(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                            const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
+                            const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate,
+                            const float* cov3d, float* dL_dcov3d);
 /* grad_rows (moment form) -> screen_grads [n_views * P, LGM_GRAD_ROW] in upstream's form: [0..1] dL/dmean2D (what
  * means2D.grad receives upstream), [2..4] dL/dconic (xx, xy, yy), [5] dL/dopacity, [6..8] dL/dcolour, [9] dL/ddepth. */
 int lgm_screen_gradients(void* stream, const lgm_render_params* prm, const float* conic_opacity, const float* grad_rows,

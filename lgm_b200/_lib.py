@@ -31,6 +31,8 @@ _SIGNATURES = {
     "lgm_num_block_sums": (_i64, [_i32, _i32]),
     "lgm_bin_workspace_bytes": (ctypes.c_int, [_pp, _i64, ctypes.POINTER(_sz)]),
     "lgm_forward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 12),
+    "lgm_forward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 13),
+    "lgm_backward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32, _vp, _vp]),
     "lgm_forward_bin": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _i32]),
     "lgm_forward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32] + [_vp] * 4),
     "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _vp, _vp, _vp, _vp, _sz, _vp, _i32] + [_vp] * 4),

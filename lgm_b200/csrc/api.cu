@@ -124,6 +124,15 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
                      float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
                      uint64_t* total_instances)
 {
+    return lgm_forward_geom_cov3d(stream, prm, gaussians, view_mats, proj_mats, view_scene, depth, radii, xy, conic_opacity,
+                                  tiles_touched, block_sums, block_offsets, total_instances, nullptr);
+}
+
+int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                           const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                           float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                           uint64_t* total_instances, const float* cov3d)
+{
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     LGM_NOTNULL(total_instances);
@@ -137,7 +146,7 @@ int lgm_forward_geom(void* stream, const lgm_render_params* prm, const float* ga
     LGM_NOTNULL(block_sums); LGM_NOTNULL(block_offsets);
     LGM_CUDA(lgm::launch_preprocess_fwd(s, p, gaussians, view_mats, proj_mats, view_scene, depth, radii,
                                         reinterpret_cast<float2*>(xy), reinterpret_cast<float4*>(conic_opacity),
-                                        tiles_touched, block_sums),
+                                        tiles_touched, block_sums, cov3d),
              "forward_geom: preprocess");
     const int64_t nsum = lgm_num_block_sums(p.P, p.n_views);
     LGM_CUDA(lgm::launch_scan_block_sums(s, block_sums, (uint32_t)nsum, block_offsets,
@@ -276,6 +285,16 @@ int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* g
                       const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
                       const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate)
 {
+    return lgm_backward_geom_cov3d(stream, prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii, conic_opacity,
+                                   grad_rows, dL_dgaussians, accumulate, nullptr, nullptr);
+}
+
+int lgm_backward_geom_cov3d(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                            const float* proj_mats, const int32_t* scene_view_offsets, const int32_t* radii,
+                            const float* conic_opacity, const float* grad_rows, float* dL_dgaussians, int32_t accumulate,
+                            const float* cov3d, float* dL_dcov3d)
+{
+    if ((cov3d == nullptr) != (dL_dcov3d == nullptr)) return fail(LGM_ERR_NULL_POINTER, "cov3d and dL_dcov3d go together");
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     if (p.n_scenes == 0 || p.P == 0) return LGM_OK;
@@ -284,7 +303,8 @@ int lgm_backward_geom(void* stream, const lgm_render_params* prm, const float* g
         LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(radii); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(grad_rows);
     }
     LGM_CUDA(lgm::launch_preprocess_bwd((cudaStream_t)stream, p, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
-                                        reinterpret_cast<const float4*>(conic_opacity), grad_rows, dL_dgaussians, accumulate),
+                                        reinterpret_cast<const float4*>(conic_opacity), grad_rows, dL_dgaussians, accumulate,
+                                        cov3d, dL_dcov3d),
              "backward_geom");
     return LGM_OK;
 }

@@ -30,7 +30,7 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ view_scene,
                       float* __restrict__ depth, int32_t* __restrict__ radii, float2* __restrict__ xy,
                       float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched,
-                      uint32_t* __restrict__ block_sums)
+                      uint32_t* __restrict__ block_sums, const float* __restrict__ cov3d)
 {
     __shared__ __align__(16) float s_g[kBlock * 14];
     __shared__ float s_mv[16], s_mp[16];
@@ -47,8 +47,10 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     uint32_t tiles = 0;
     if ((int)threadIdx.x < n) {
         const float* g = s_g + threadIdx.x * 14;
+        // cov3d (upstream's cov3D_precomp, [n_scenes, P, 6]) replaces the covariance built from scale / rotation
         const Geom o = preprocess_point(g, g + 4, g + 7, prm.mod, s_mv, s_mp, prm.W, prm.H, prm.tanx, prm.tany, prm.fx,
-                                        prm.fy, prm.gx, prm.gy);
+                                        prm.fy, prm.gx, prm.gy,
+                                        cov3d ? cov3d + ((size_t)scene * prm.P + base + threadIdx.x) * 6 : nullptr);
         const size_t gi = (size_t)view * prm.P + base + threadIdx.x;
         depth[gi] = o.depth;
         radii[gi] = o.radius;
@@ -75,12 +77,12 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
 cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* view_scene,
                                   float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
-                                  uint32_t* tiles_touched, uint32_t* block_sums)
+                                  uint32_t* tiles_touched, uint32_t* block_sums, const float* cov3d)
 {
     if (prm.P == 0 || prm.n_views == 0) return cudaSuccess;
     dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
     preprocess_fwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, view_scene, depth, radii, xy,
-                                                       conic_opacity, tiles_touched, block_sums);
+                                                       conic_opacity, tiles_touched, block_sums, cov3d);
     return cudaGetLastError();
 }
 
@@ -110,7 +112,8 @@ __global__ void __launch_bounds__(kBlock, 3)
 preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ scene_view_offsets,
                       const int32_t* __restrict__ radii, const float4* __restrict__ conic_opacity,
-                      const float* __restrict__ grad_rows, float* __restrict__ dL_dgaussians, int accumulate)
+                      const float* __restrict__ grad_rows, float* __restrict__ dL_dgaussians, int accumulate,
+                      const float* __restrict__ cov3d, float* __restrict__ dL_dcov3d)
 {
     __shared__ __align__(16) float s_g[kBlock * 14];
     __shared__ float s_m[32];
@@ -134,7 +137,13 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         float M[9];
         pos[0] = g[0]; pos[1] = g[1]; pos[2] = g[2];
         opacity = g[3];
-        cov3d_from_scale_rot(g[4], g[5], g[6], prm.mod, g[7], g[8], g[9], g[10], cov6, M);
+        if (cov3d) {
+            const float* c = cov3d + ((size_t)scene * prm.P + base + threadIdx.x) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov6[k] = c[k];
+        } else {
+            cov3d_from_scale_rot(g[4], g[5], g[6], prm.mod, g[7], g[8], g[9], g[10], cov6, M);
+        }
     }
     const int v0 = scene_view_offsets[scene], v1 = scene_view_offsets[scene + 1];
     for (int v = v0; v < v1; v++) {
@@ -155,7 +164,16 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         d[12] += r1.w;
         d[13] += r2.x;
     }
-    if (active) preprocess_point_bwd_finish(s_g + threadIdx.x * 14 + 4, s_g + threadIdx.x * 14 + 7, prm.mod, g6, d + 4, d + 7);
+    if (active) {
+        if (cov3d) {
+            // cov3D_precomp: the gradient stops at the covariance (upstream's dL_dcov3D); scale / rotation get none
+            float* o = dL_dcov3d + ((size_t)scene * prm.P + base + threadIdx.x) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) o[k] = accumulate ? o[k] + g6[k] : g6[k];
+        } else {
+            preprocess_point_bwd_finish(s_g + threadIdx.x * 14 + 4, s_g + threadIdx.x * 14 + 7, prm.mod, g6, d + 4, d + 7);
+        }
+    }
     // transpose through shared memory for coalesced stores of the 14-float rows
     __syncthreads();
     if (active) {
@@ -175,12 +193,12 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
 cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* scene_view_offsets,
                                   const int32_t* radii, const float4* conic_opacity, const float* grad_rows,
-                                  float* dL_dgaussians, int accumulate)
+                                  float* dL_dgaussians, int accumulate, const float* cov3d, float* dL_dcov3d)
 {
     if (prm.P == 0 || prm.n_scenes == 0) return cudaSuccess;
     dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_scenes);
     preprocess_bwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, scene_view_offsets, radii,
-                                                       conic_opacity, grad_rows, dL_dgaussians, accumulate);
+                                                       conic_opacity, grad_rows, dL_dgaussians, accumulate, cov3d, dL_dcov3d);
     return cudaGetLastError();
 }
 

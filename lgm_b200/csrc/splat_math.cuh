@@ -169,8 +169,11 @@ LGM_HD void tile_rect(float px, float py, int radius, int gx, int gy, int& x0, i
 
 // A.1 for one (view, Gaussian).  g = the 14 floats of /root/reference/core/gs.py:45-49 minus colour:
 // pos(3) opacity(1) scale(3) rot(4).  Returns a zeroed Geom (radius 0) when culled.
+// cov6_in (optional): a precomputed 3D covariance (xx, xy, xz, yy, yz, zz) — upstream's cov3D_precomp — used instead of
+// the one built from scale / rotation / mod.
 LGM_HD Geom preprocess_point(const float* pos, const float* scale, const float* rot, float mod, const float* mv,
-                             const float* mp, int W, int H, float tanx, float tany, float fx, float fy, int gx, int gy)
+                             const float* mp, int W, int H, float tanx, float tany, float fx, float fy, int gx, int gy,
+                             const float* cov6_in = nullptr)
 {
     Geom o;
     o.depth = 0.f; o.radius = 0; o.px = o.py = 0.f; o.cx = o.cy = o.cz = 0.f;
@@ -182,7 +185,12 @@ LGM_HD Geom preprocess_point(const float* pos, const float* scale, const float* 
     const float pw = LGM_DIV(1.0f, LGM_ADD(hw, kWEps));
     const float projx = LGM_MUL(hx, pw), projy = LGM_MUL(hy, pw);
     float cov6[6], M[9], abc[3], Tm[6], t[3], txtz, tytz;
-    cov3d_from_scale_rot(scale[0], scale[1], scale[2], mod, rot[0], rot[1], rot[2], rot[3], cov6, M);
+    if (cov6_in) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov6[k] = cov6_in[k];
+    } else {
+        cov3d_from_scale_rot(scale[0], scale[1], scale[2], mod, rot[0], rot[1], rot[2], rot[3], cov6, M);
+    }
     cov2d_ewa(pvx, pvy, pvz, fx, fy, tanx, tany, cov6, mv, abc, Tm, t, &txtz, &tytz);
     const float a = abc[0], b = abc[1], c = abc[2];
     const float det = LGM_FMA(a, c, -LGM_MUL(b, b));

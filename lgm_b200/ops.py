@@ -83,10 +83,11 @@ class ForwardState:
 
 
 def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg: ViewConfig,
-                  prepare_backward=False):
+                  prepare_backward=False, cov3d=None):
     """All views in one set of launches.  Returns (image [VW,3,H,W], alpha [VW,1,H,W], depth [VW,1,H,W], state).
     prepare_backward: also allocate and zero the backward's gradient rows now — the fill then runs on the GPU while
-    the host waits for the instance count, instead of at the head of the backward."""
+    the host waits for the instance count, instead of at the head of the backward.
+    cov3d [B,P,6]: upstream's cov3D_precomp — replaces the covariance built from the scale / rotation columns."""
     L = _lib.lib()
     _check_cuda_f32(gaussians, "gaussians", (14,))
     _check_cuda_f32(view_mats, "view_mats", (16,))
@@ -112,10 +113,14 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     block_offsets = torch.empty(max(nsum, 1), dtype=torch.int32, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
     s = _stream()
-    _timed("geom", lambda: _lib.check(L.lgm_forward_geom(
+    if cov3d is not None:
+        _check_cuda_f32(cov3d, "cov3d", (6,))
+        if cov3d.numel() != B * P * 6:
+            raise _lib.LgmError(f"cov3d must hold n_scenes * P * 6 values, got {tuple(cov3d.shape)}")
+    _timed("geom", lambda: _lib.check(L.lgm_forward_geom_cov3d(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(view_scene), _lib.ptr(st.depth),
         _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.tiles_touched), _lib.ptr(block_sums),
-        _lib.ptr(block_offsets), _lib.ptr(total)), "lgm_forward_geom"))
+        _lib.ptr(block_offsets), _lib.ptr(total), _lib.ptr(cov3d)), "lgm_forward_geom"))
     launch_counter["kernels"] += 2 if npair else 0
     # work that does not depend on the instance count is queued before the host waits for it
     st.grad_rows = torch.zeros(max(npair, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev) if prepare_backward else None
@@ -178,9 +183,10 @@ class TooManyInstances(_lib.LgmError):
         self.n_instances = n
 
 
-def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth):
+def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth, cov3d=None):
     """Returns (dL_dgaussians [B,P,14], grad_rows [VW*P,12]).  grad_rows is in MOMENT form (include/lgm_b200.h,
-    lgm_backward); screen_gradients() converts it to upstream's dL/dmean2D, dL/dconic, ... ."""
+    lgm_backward); screen_gradients() converts it to upstream's dL/dmean2D, dL/dconic, ... .
+    With cov3d (the forward's cov3D_precomp) returns (dL_dgaussians, grad_rows, dL_dcov3d [B,P,6])."""
     L = _lib.lib()
     dev = gaussians.device
     cfg = st.cfg
@@ -196,12 +202,16 @@ def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha,
         _stream(), prm, _lib.ptr(gaussians), _lib.ptr(st.view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity),
         _lib.ptr(st.depth), _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), _lib.ptr(alpha), _lib.ptr(st.n_contrib),
         _lib.ptr(d_image), _lib.ptr(d_alpha), _lib.ptr(d_depth), _lib.ptr(grad_rows)), "lgm_backward_composite"))
-    _timed("geom_bwd", lambda: _lib.check(L.lgm_backward_geom(
+    d_cov = None if cov3d is None else torch.zeros(gaussians.shape[0], gaussians.shape[1], 6, dtype=torch.float32, device=dev)
+    _timed("geom_bwd", lambda: _lib.check(L.lgm_backward_geom_cov3d(
         _stream(), prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(st.scene_view_offsets),
-        _lib.ptr(st.radii), _lib.ptr(st.conic_opacity), _lib.ptr(grad_rows), _lib.ptr(d_gauss), 0), "lgm_backward_geom"))
+        _lib.ptr(st.radii), _lib.ptr(st.conic_opacity), _lib.ptr(grad_rows), _lib.ptr(d_gauss), 0, _lib.ptr(cov3d),
+        _lib.ptr(d_cov)), "lgm_backward_geom"))
     launch_counter["kernels"] += 2 if st.n_views * st.P else 0
     if st.n_views * st.P == 0:
         d_gauss.zero_()
+    if cov3d is not None:
+        return d_gauss, grad_rows, d_cov
     return d_gauss, grad_rows
 
 

@@ -3,9 +3,10 @@
 (color, radii, depth, alpha) and error behaviour (SURVEY.md §8b level 1) — backed by the batched sm_100a kernels
 with n_views = 1.
 
-`shs` (spherical-harmonics colours, not on LGM's path — core/gs.py:79-80 passes colors_precomp) is served by the
-sh.cu kernels, whose output enters the renderer exactly like colors_precomp.  `cov3D_precomp` is not on LGM's path
-and is not implemented (NotImplementedError, never a silent fallback).
+Not on LGM's path (core/gs.py:79-84 passes colors_precomp, scales and rotations) but served for API completeness:
+`shs` (spherical-harmonics colours) by the sh.cu kernels, whose output enters the renderer exactly like
+colors_precomp, and `cov3D_precomp` [P,6] by the covariance inputs of the preprocess kernels (the gradient then
+stops at the covariance, as upstream's dL_dcov3D).
 """
 from typing import NamedTuple
 
@@ -35,10 +36,15 @@ class _RasterizeGaussians(torch.autograd.Function):
     rotations, cov3Ds_precomp, raster_settings."""
 
     @staticmethod
-    def forward(ctx, means3D, means2D, colors_precomp, opacities, scales, rotations, raster_settings):
+    def forward(ctx, means3D, means2D, colors_precomp, opacities, scales, rotations, cov3D_precomp, raster_settings):
         rs = raster_settings
         dev = means3D.device
         P = means3D.shape[0]
+        if cov3D_precomp is not None:  # the scale / rotation columns are ignored by the kernels
+            scales, rotations = means3D.new_zeros(P, 3), means3D.new_zeros(P, 4)
+            ctx.cov3d = cov3D_precomp.float().reshape(1, P, 6).contiguous()
+        else:
+            ctx.cov3d = None
         g = torch.cat([means3D.float(), opacities.float().reshape(P, 1), scales.float(), rotations.float(),
                        colors_precomp.float()], dim=-1).reshape(1, P, 14).contiguous()
         cfg = ops.ViewConfig(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
@@ -48,7 +54,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         bg = rs.bg.to(dev).float().reshape(3).contiguous()
         view_scene = torch.zeros(1, dtype=torch.int32, device=dev)
         offsets = torch.tensor([0, 1], dtype=torch.int32, device=dev)
-        image, alpha, depth, st = ops.forward_views(g, vm, pm, view_scene, offsets, bg, cfg)
+        image, alpha, depth, st = ops.forward_views(g, vm, pm, view_scene, offsets, bg, cfg, cov3d=ctx.cov3d)
         ctx.st = st
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(g, vm, pm, bg, alpha)
@@ -62,14 +68,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         st = ctx.st
         H, W = st.cfg.image_height, st.cfg.image_width
         z = lambda t, c: (torch.zeros(1, c, H, W, device=g.device) if t is None else t.reshape(1, c, H, W).contiguous().float())
-        d_gauss, rows = ops.backward_views(g, vm, pm, bg, st, alpha, z(grad_color, 3), z(grad_alpha, 1),
-                                           None if grad_depth is None else z(grad_depth, 1))
+        res = ops.backward_views(g, vm, pm, bg, st, alpha, z(grad_color, 3), z(grad_alpha, 1),
+                                 None if grad_depth is None else z(grad_depth, 1), cov3d=ctx.cov3d)
+        d_gauss, rows = res[0], res[1]
         d = d_gauss[0]
         P = d.shape[0]
         d_means2D = torch.zeros(P, 3, device=g.device)
         d_means2D[:, :2] = ops.screen_gradients(st, rows)[:P, 0:2]
-        # (means3D, means2D, colors_precomp, opacities, scales, rotations, raster_settings)
-        return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], d[:, 4:7], d[:, 7:11], None
+        # (means3D, means2D, colors_precomp, opacities, scales, rotations, cov3D_precomp, raster_settings)
+        if ctx.cov3d is not None:
+            return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], None, None, res[2][0], None
+        return d[:, 0:3], d_means2D, d[:, 11:14], d[:, 3:4], d[:, 4:7], d[:, 7:11], None, None
 
 
 class _SHToColor(torch.autograd.Function):
@@ -130,9 +139,8 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        if cov3D_precomp is not None:
-            raise NotImplementedError("lgm_b200: cov3D_precomp is not on LGM's path and is not implemented; "
-                                      "pass scales and rotations")
+        if cov3D_precomp is not None and (cov3D_precomp.dim() != 2 or cov3D_precomp.shape != (means3D.shape[0], 6)):
+            raise _lib.LgmError("cov3D_precomp must have dimensions (num_points, 6)")
         if means3D.dim() != 2 or means3D.shape[1] != 3:
             raise _lib.LgmError("means3D must have dimensions (num_points, 3)")
         if not means3D.is_cuda:
@@ -140,5 +148,5 @@ class GaussianRasterizer(nn.Module):
         if shs is not None:
             rs = self.raster_settings
             colors_precomp = _SHToColor.apply(means3D, shs, rs.campos.to(means3D.device), int(rs.sh_degree))
-        return _RasterizeGaussians.apply(means3D, means2D, colors_precomp, opacities, scales, rotations,
+        return _RasterizeGaussians.apply(means3D, means2D, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                          self.raster_settings)

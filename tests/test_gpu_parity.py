@@ -706,3 +706,50 @@ def test_forward_only_orbit_is_one_batched_call():
     for k in ("image", "alpha", "depth"):
         assert torch.equal(out[k], ref[k])
     assert float(out["alpha"].max()) > 0.5
+
+
+def test_rasterizer_with_cov3d_precomp(oracle32):
+    """GaussianRasterizer(cov3D_precomp=...): (a) with the oracle's bit-pinned covariance the forward is bit-identical
+    to the scales / rotations call; (b) the gradient stops at the covariance — chained through a differentiable torch
+    cov3D(scales, rotations) it reproduces the scale / rotation gradients of the direct call."""
+    from lgm_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    N, S = 2500, 80
+    g = make_gaussians(1, N, "trained", seed=41)[0]
+    g[:, 4:7] *= 5.0
+    cv, cvp, cp = make_cameras(1, 1, seed=41)
+    t = tan_half(49.1)
+    rs = GaussianRasterizationSettings(image_height=S, image_width=S, tanfovx=t, tanfovy=t, bg=torch.tensor([0.2, 0.3, 0.4], device=DEV),
+                                       scale_modifier=1.0, viewmatrix=cv[0, 0].to(DEV), projmatrix=cvp[0, 0].to(DEV), sh_degree=0,
+                                       campos=cp[0, 0].to(DEV), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    leaf = lambda x: x.clone().to(DEV).contiguous().requires_grad_(True)
+    m3, op, sc, ro, col = leaf(g[:, 0:3]), leaf(g[:, 3:4]), leaf(g[:, 4:7]), leaf(g[:, 7:11]), leaf(g[:, 11:14])
+    img, radii, depth, alpha = rast(m3, torch.zeros_like(m3), op, colors_precomp=col, scales=sc, rotations=ro)
+    w_img = torch.randn(3, S, S, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (img * w_img).sum().backward()
+    # (a) the oracle's covariance (same pinned arithmetic as the kernel's cov3d_from_scale_rot)
+    means, scales, rots, opac, cols = split14(g.numpy())
+    pre = oracle32.preprocess(means, scales, rots, opac, cv[0, 0].numpy(), cvp[0, 0].numpy(), S, S, t, t, 1.0)
+    cov = torch.tensor(pre["cov3d"], dtype=torch.float32, device=DEV)
+    img_c, radii_c, depth_c, alpha_c = rast(m3.detach(), torch.zeros_like(m3), op.detach(), colors_precomp=col.detach(),
+                                            cov3D_precomp=cov)
+    assert torch.equal(img, img_c) and torch.equal(radii, radii_c) and torch.equal(alpha, alpha_c) and torch.equal(depth, depth_c)
+    # (b) differentiable covariance in torch: Sigma = (S R)^T (S R) with upstream's rotation layout (Appendix A.1)
+    sc2, ro2 = leaf(g[:, 4:7]), leaf(g[:, 7:11])
+    r, x, y, z = ro2[:, 0], ro2[:, 1], ro2[:, 2], ro2[:, 3]
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                      2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                      2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+    Mm = sc2[:, :, None] * Rm                       # M = S R
+    Sig = Mm.transpose(1, 2) @ Mm
+    cov_t = torch.stack([Sig[:, 0, 0], Sig[:, 0, 1], Sig[:, 0, 2], Sig[:, 1, 1], Sig[:, 1, 2], Sig[:, 2, 2]], -1)
+    vis = radii > 0  # the oracle leaves the covariance of culled Gaussians at zero
+    assert int(vis.sum()) > 1000
+    assert (cov_t.detach() - cov)[vis].abs().max().item() <= 1e-6 * cov.abs().max().item()
+    m3b, opb, colb = leaf(g[:, 0:3]), leaf(g[:, 3:4]), leaf(g[:, 11:14])
+    img_b, *_ = rast(m3b, torch.zeros_like(m3b), opb, colors_precomp=colb, cov3D_precomp=cov_t)
+    (img_b * w_img).sum().backward()
+    for name, a, b in (("means3D", m3.grad, m3b.grad), ("opacity", op.grad, opb.grad), ("colors", col.grad, colb.grad),
+                       ("scales", sc.grad, sc2.grad), ("rotations", ro.grad, ro2.grad)):
+        scale = a.abs().max().item()
+        assert scale > 0 and (a - b).abs().max().item() <= 2e-4 * scale, (name, (a - b).abs().max().item(), scale)

@@ -44,8 +44,10 @@ def test_argument_exclusivity_errors():
         r(m, m2, o, colors_precomp=c, scales=s, rotations=q, cov3D_precomp=torch.zeros(P, 6))
     with pytest.raises(LgmError, match="no CPU path"):  # shs is served (sh.cu), but only on the GPU
         r(m, m2, o, shs=torch.zeros(P, 1, 3), scales=s, rotations=q)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(LgmError, match="no CPU path"):  # cov3D_precomp is served, but only on the GPU
         r(m, m2, o, colors_precomp=c, cov3D_precomp=torch.zeros(P, 6))
+    with pytest.raises(LgmError, match="num_points, 6"):
+        r(m, m2, o, colors_precomp=c, cov3D_precomp=torch.zeros(P, 9))
     with pytest.raises(LgmError, match="num_points, 3"):
         r(torch.zeros(P, 4), m2, o, colors_precomp=c, scales=s, rotations=q)
 
