@@ -728,7 +728,7 @@ def test_rasterizer_with_cov3d_precomp(oracle32):
     w_img = torch.randn(3, S, S, generator=torch.Generator().manual_seed(1)).to(DEV)
     (img * w_img).sum().backward()
     # (a) the oracle's covariance (same pinned arithmetic as the kernel's cov3d_from_scale_rot)
-    means, scales, rots, opac, cols = split14(g.numpy())
+    means, opac, scales, rots, cols = split14(g.numpy())
     pre = oracle32.preprocess(means, scales, rots, opac, cv[0, 0].numpy(), cvp[0, 0].numpy(), S, S, t, t, 1.0)
     cov = torch.tensor(pre["cov3d"], dtype=torch.float32, device=DEV)
     img_c, radii_c, depth_c, alpha_c = rast(m3.detach(), torch.zeros_like(m3), op.detach(), colors_precomp=col.detach(),
