@@ -740,7 +740,7 @@ def test_rasterizer_with_cov3d_precomp(oracle32):
     Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
                       2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
                       2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
-    Mm = sc2[:, :, None] * Rm                       # M = S R
+    Mm = sc2[:, :, None] * Rm.transpose(1, 2)       # M = S R; the triples above are GLM columns, i.e. Rm is R^T
     Sig = Mm.transpose(1, 2) @ Mm
     cov_t = torch.stack([Sig[:, 0, 0], Sig[:, 0, 1], Sig[:, 0, 2], Sig[:, 1, 1], Sig[:, 1, 2], Sig[:, 2, 2]], -1)
     vis = radii > 0  # the oracle leaves the covariance of culled Gaussians at zero
