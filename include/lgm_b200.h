@@ -184,6 +184,15 @@ int lgm_mse_loss_grad(void* stream, const float* image, const float* gt_image, f
                       float w_image, const float* alpha, const float* gt_alpha, float* d_alpha, int64_t n_alpha, float w_alpha,
                       double* loss, const float* grad_scale);
 
+/* The LPIPS input preparation of /root/reference/core/models.py:155-163:
+ *   F.interpolate(images.view(-1, 3, S, S) * 2 - 1, (256, 256), mode='bilinear', align_corners=False)
+ * y [n_planes, h_out, w_out] = mul * bilinear_resize(x [n_planes, h_in, w_in]) + add (mul = 2, add = -1 there), and its
+ * backward dx = mul * resize^T(dy) (dx is overwritten).  n_planes <= 65535 per call. */
+int lgm_resize_bilinear_forward(void* stream, const float* x, float* y, int64_t n_planes, int32_t h_in, int32_t w_in,
+                                int32_t h_out, int32_t w_out, float mul, float add);
+int lgm_resize_bilinear_backward(void* stream, const float* dy, float* dx, int64_t n_planes, int32_t h_in, int32_t w_in,
+                                 int32_t h_out, int32_t w_out, float mul);
+
 /* Colours from spherical harmonics — the `shs` argument of GaussianRasterizer.forward
  * (diff_gaussian_rasterization/__init__.py: shs / sh_degree / campos; upstream computeColorFromSH in
  * cuda_rasterizer/forward.cu and its backward in backward.cu).  LGM itself passes colors_precomp

@@ -9,8 +9,8 @@ CPU or PyTorch fallback — a missing library or a non-CUDA tensor raises.
 from ._lib import LgmError
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 from .activations import activate_gaussians
-from .losses import mse_image_alpha_loss
+from .losses import lpips_input, mse_image_alpha_loss
 from .renderer import GaussianRenderer, default_options
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "GaussianRenderer", "default_options", "LgmError",
-           "mse_image_alpha_loss", "activate_gaussians"]
+           "mse_image_alpha_loss", "lpips_input", "activate_gaussians"]

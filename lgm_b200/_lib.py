@@ -45,6 +45,8 @@ _SIGNATURES = {
     "lgm_activate_forward": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "lgm_activate_backward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "lgm_mse_loss_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp]),
+    "lgm_resize_bilinear_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float, ctypes.c_float]),
+    "lgm_resize_bilinear_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float]),
     "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sh_backward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sort_input_is_tmp": (ctypes.c_int, [_i32]),

@@ -379,6 +379,36 @@ int lgm_activate_backward(void* stream, int64_t n_rows, const float* x, const fl
     return LGM_OK;
 }
 
+static int resize_shape_ok(int64_t n_planes, int32_t h_in, int32_t w_in, int32_t h_out, int32_t w_out)
+{
+    if (n_planes < 0 || n_planes > 65535) return fail(LGM_ERR_BAD_SHAPE, "n_planes must be 0..65535");
+    if (h_in < 1 || w_in < 1 || h_out < 0 || w_out < 0) return fail(LGM_ERR_BAD_SHAPE, "bad image size");
+    return LGM_OK;
+}
+
+int lgm_resize_bilinear_forward(void* stream, const float* x, float* y, int64_t n_planes, int32_t h_in, int32_t w_in,
+                                int32_t h_out, int32_t w_out, float mul, float add)
+{
+    if (int rc = resize_shape_ok(n_planes, h_in, w_in, h_out, w_out)) return rc;
+    if (n_planes == 0 || h_out == 0 || w_out == 0) return LGM_OK;
+    LGM_NOTNULL(x); LGM_NOTNULL(y);
+    LGM_CUDA(lgm::launch_resize_bilinear_fwd((cudaStream_t)stream, x, y, (int)n_planes, h_in, w_in, h_out, w_out, mul, add),
+             "resize_bilinear_forward");
+    return LGM_OK;
+}
+
+int lgm_resize_bilinear_backward(void* stream, const float* dy, float* dx, int64_t n_planes, int32_t h_in, int32_t w_in,
+                                 int32_t h_out, int32_t w_out, float mul)
+{
+    if (int rc = resize_shape_ok(n_planes, h_in, w_in, h_out, w_out)) return rc;
+    if (n_planes == 0) return LGM_OK;
+    LGM_NOTNULL(dx);
+    if (h_out > 0 && w_out > 0) LGM_NOTNULL(dy);
+    LGM_CUDA(lgm::launch_resize_bilinear_bwd((cudaStream_t)stream, dy, dx, (int)n_planes, h_in, w_in, h_out, w_out, mul),
+             "resize_bilinear_backward");
+    return LGM_OK;
+}
+
 static int sh_shape_ok(int32_t n_points, int32_t degree, int32_t max_coeffs)
 {
     if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");

@@ -43,6 +43,11 @@ cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const 
 // activations.cu: raw splatter image [.,14] -> Gaussians (core/models.py:40-44,107-115), forward and backward
 cudaError_t launch_activate_fwd(cudaStream_t stream, size_t n_rows, const float* x, float* g);
 cudaError_t launch_activate_bwd(cudaStream_t stream, size_t n_rows, const float* x, const float* dg, float* dx);
+// resize.cu: y = mul * bilinear_resize(x) + add (F.interpolate, align_corners = False) and its backward
+cudaError_t launch_resize_bilinear_fwd(cudaStream_t stream, const float* x, float* y, int n_planes, int h_in, int w_in, int h_out,
+                                       int w_out, float mul, float add);
+cudaError_t launch_resize_bilinear_bwd(cudaStream_t stream, const float* dy, float* dx, int n_planes, int h_in, int w_in, int h_out,
+                                       int w_out, float mul);
 // sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
 cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
                               const float* shs, float* colors, uint8_t* clamped);

@@ -49,3 +49,46 @@ def mse_image_alpha_loss(pred_images, pred_alphas, gt_images, gt_masks, w_image=
     """mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks) (mean reduction by default; w_image / w_alpha
     override the per-element weights, e.g. 1 / global element count when the views are sharded over ranks)."""
     return _MSEImageAlpha.apply(pred_images, pred_alphas, gt_images, gt_masks, w_image, w_alpha)
+
+
+class _ResizeBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, mul, add):
+        if not x.is_cuda:
+            raise _lib.LgmError("images must be a CUDA tensor (lgm_b200 has no CPU path)")
+        if x.dim() < 2:
+            raise _lib.LgmError("images must end in (H, W)")
+        xc = x.contiguous().float()
+        h_in, w_in = xc.shape[-2], xc.shape[-1]
+        h_out, w_out = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+        planes = xc.numel() // max(h_in * w_in, 1)
+        y = torch.empty(*xc.shape[:-2], h_out, w_out, dtype=torch.float32, device=xc.device)
+        L = _lib.lib()
+        for p0 in range(0, planes, 65535):  # grid.y limit
+            n = min(65535, planes - p0)
+            _lib.check(L.lgm_resize_bilinear_forward(ops._stream(), xc.data_ptr() + 4 * p0 * h_in * w_in,
+                                                     y.data_ptr() + 4 * p0 * h_out * w_out, n, h_in, w_in, h_out, w_out,
+                                                     float(mul), float(add)), "lgm_resize_bilinear_forward")
+            ops.launch_counter["kernels"] += 1
+        ctx.geom = (planes, h_in, w_in, h_out, w_out, float(mul), tuple(xc.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        planes, h_in, w_in, h_out, w_out, mul, shape = ctx.geom
+        dyc = dy.contiguous().float()
+        dx = torch.empty(shape, dtype=torch.float32, device=dyc.device)
+        L = _lib.lib()
+        for p0 in range(0, planes, 65535):
+            n = min(65535, planes - p0)
+            _lib.check(L.lgm_resize_bilinear_backward(ops._stream(), dyc.data_ptr() + 4 * p0 * h_out * w_out,
+                                                      dx.data_ptr() + 4 * p0 * h_in * w_in, n, h_in, w_in, h_out, w_out, mul),
+                       "lgm_resize_bilinear_backward")
+            ops.launch_counter["kernels"] += 1
+        return dx, None, None, None
+
+
+def lpips_input(images, size=256):
+    """F.interpolate(images * 2 - 1, (size, size), mode='bilinear', align_corners=False) for images [..., H, W] — the
+    LPIPS input preparation of /root/reference/core/models.py:155-163 (the LPIPS network itself stays the caller's)."""
+    return _ResizeBilinear.apply(images, size, 2.0, -1.0)

@@ -755,3 +755,23 @@ def test_rasterizer_with_cov3d_precomp(oracle32):
         # order of the fp32 reductions: <= 1e-3 in relative L2 and 2e-3 of the tensor's scale entry-wise
         scale, rel = a.abs().max().item(), ((a - b).norm() / a.norm()).item()
         assert scale > 0 and rel <= 1e-3 and (a - b).abs().max().item() <= 2e-3 * scale, (name, rel, (a - b).abs().max().item(), scale)
+
+
+def test_lpips_input_matches_interpolate():
+    """lgm_b200.lpips_input = F.interpolate(x * 2 - 1, (256, 256), mode='bilinear', align_corners=False) of
+    /root/reference/core/models.py:155-163, forward and backward, down- and up-sampling, non-square."""
+    import torch.nn.functional as F
+    from lgm_b200 import lpips_input
+    gen = torch.Generator().manual_seed(5)
+    for shape, size in (((2, 3, 3, 320, 320), 256), ((5, 3, 96, 72), (128, 100)), ((1, 1, 7, 5), 3)):
+        x = torch.rand(shape, generator=gen).to(DEV).requires_grad_(True)
+        flat = x.reshape(-1, 1, shape[-2], shape[-1])
+        out_hw = (size, size) if isinstance(size, int) else size
+        ref = F.interpolate(flat * 2 - 1, out_hw, mode="bilinear", align_corners=False)
+        w = torch.randn(ref.shape, generator=gen).to(DEV)
+        (gr,) = torch.autograd.grad((ref * w).sum(), x)
+        y = lpips_input(x, size)
+        assert y.shape == (*shape[:-2], *out_hw)
+        (gg,) = torch.autograd.grad((y.reshape(ref.shape) * w).sum(), x)
+        assert (y.reshape(ref.shape) - ref).abs().max().item() <= 2e-6
+        assert (gg - gr).abs().max().item() <= 1e-5 * max(1.0, gr.abs().max().item())
