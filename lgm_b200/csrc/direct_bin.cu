@@ -40,20 +40,13 @@ constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
-// Enumerates the (Gaussian, touched tile) instances of the 32 Gaussians held by a warp (`idx` of `view` per lane; every
-// lane of the warp must make this call together), in one of two ways:
-//  * Gaussian-major (small footprints, the trained-scene case): f(tile, value, depth bits) once per instance — by the
-//    owning lane for footprints of up to kCoopAreaD tiles, by the whole warp (lanes across the rect) above;
-//  * tile-major, when the warp's footprints together cover their bounding rect at least kTileMajorFill times
-//    (untrained Gaussians: hundreds of tiles each): the warp walks the tiles of the bounding rect and calls
-//    fw(tile, ballot of the lanes touching it, this lane touches it, value, depth bits) with all lanes converged, so that
-//    the instances of one tile are handled — counted with one atomic, stored to consecutive slots — together.
-constexpr uint32_t kTileMajorFill = 4;
-
-template <bool WITH_DEPTH, typename F, typename FW>
+// Calls f(tile index inside the view, value, depth bits) once per (Gaussian, touched tile) for the Gaussian `idx` of
+// `view` held by this thread; footprints above kCoopAreaD tiles are enumerated by the whole warp (lanes across the
+// rect), so every lane of the warp must make this call together.
+template <bool WITH_DEPTH, typename F>
 __device__ __forceinline__ void for_each_touched_tile(const RenderParams& prm, const int32_t* __restrict__ radii,
                                                       const float2* __restrict__ xy, const float* __restrict__ depth,
-                                                      int view, int idx, F&& f, FW&& fw)
+                                                      int view, int idx, F&& f)
 {
     const size_t gi = (size_t)view * prm.P + idx;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -69,22 +62,6 @@ __device__ __forceinline__ void for_each_touched_tile(const RenderParams& prm, c
     uint32_t dbits = 0;
     if (WITH_DEPTH && area) dbits = __float_as_uint(depth[gi]);
     const uint32_t val = (uint32_t)gi;
-    const uint32_t warp_area = __reduce_add_sync(0xffffffffu, area);
-    if (warp_area > 32u * kCoopAreaD) {
-        const int ux0 = __reduce_min_sync(0xffffffffu, area ? x0 : 0x7fffffff), uy0 = __reduce_min_sync(0xffffffffu, area ? y0 : 0x7fffffff);
-        const int ux1 = __reduce_max_sync(0xffffffffu, area ? x1 : 0), uy1 = __reduce_max_sync(0xffffffffu, area ? y1 : 0);
-        if (warp_area >= kTileMajorFill * (uint32_t)((ux1 - ux0) * (uy1 - uy0))) {
-            for (int ty = uy0; ty < uy1; ty++) {
-                const bool row = area != 0u && ty >= y0 && ty < y1;
-                for (int tx = ux0; tx < ux1; tx++) {
-                    const bool hit = row && tx >= x0 && tx < x1;
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m) fw((uint32_t)(ty * prm.gx + tx), m, hit, val, dbits);
-                }
-            }
-            return;
-        }
-    }
     const bool big = area > kCoopAreaD;
     if (area != 0 && !big) {
         for (int y = y0; y < y1; y++)
@@ -132,14 +109,10 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     // recounting was measured slower: 0.63 vs 0.53 ms — the recount sweep also warms L1 with the rows the scatter reads)
     for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int k = 0; k < kEnumItems; k++)
-        for_each_touched_tile<false>(
-            prm, radii, xy, depth, view, first + k * kBlock, [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); },
-            [&](uint32_t tl, unsigned m, bool, uint32_t, uint32_t) {
-                if (lane == __ffs(m) - 1) atomicAdd(&s_hist[tl], (uint32_t)__popc(m));
-            });
+        for_each_touched_tile<false>(prm, radii, xy, depth, view, first + k * kBlock,
+                                     [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); });
     __syncthreads();
     if (!SCATTER) {
         uint32_t mine = 0;
@@ -159,19 +132,10 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < kEnumItems; k++)
-            for_each_touched_tile<true>(
-                prm, radii, xy, depth, view, first + k * kBlock,
-                [&](uint32_t tl, uint32_t val, uint32_t dbits) {
-                    pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, dbits);
-                },
-                [&](uint32_t tl, unsigned m, bool hit, uint32_t val, uint32_t dbits) {
-                    // the lanes touching this tile take consecutive slots of the CTA's run: one coalesced store
-                    const int leader = __ffs(m) - 1;
-                    uint32_t old = 0;
-                    if (lane == leader) old = atomicAdd(&s_hist[tl], (uint32_t)__popc(m));
-                    old = __shfl_sync(0xffffffffu, old, leader);
-                    if (hit) pairs[s_base[tl] + old + __popc(m & ((1u << lane) - 1u))] = make_uint2(val, dbits);
-                });
+            for_each_touched_tile<true>(prm, radii, xy, depth, view, first + k * kBlock,
+                                        [&](uint32_t tl, uint32_t val, uint32_t dbits) {
+                                            pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, dbits);
+                                        });
     }
 }
 
@@ -185,19 +149,16 @@ tile_enumerate_global_kernel(const RenderParams prm, const int32_t* __restrict__
     const int view = blockIdx.y;
     const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
     uint32_t mine = 0;
-    auto one = [&](uint32_t tl, uint32_t val, uint32_t dbits) {
-        const uint32_t gt = tile_base + tl;
-        if (SCATTER) {
-            const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
-            pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
-        } else {
-            atomicAdd(&counts[gt], 1u);
-            mine++;
-        }
-    };
-    for_each_touched_tile<SCATTER>(prm, radii, xy, depth, view, blockIdx.x * kBlock + threadIdx.x, one,
-                                   [&](uint32_t tl, unsigned, bool hit, uint32_t val, uint32_t dbits) {
-                                       if (hit) one(tl, val, dbits);
+    for_each_touched_tile<SCATTER>(prm, radii, xy, depth, view, blockIdx.x * kBlock + threadIdx.x,
+                                   [&](uint32_t tl, uint32_t val, uint32_t dbits) {
+                                       const uint32_t gt = tile_base + tl;
+                                       if (SCATTER) {
+                                           const uint32_t slot = atomicSub(&counts[gt], 1u) - 1u;
+                                           pairs[ranges[gt].x + slot] = make_uint2(val, dbits);
+                                       } else {
+                                           atomicAdd(&counts[gt], 1u);
+                                           mine++;
+                                       }
                                    });
     if (!SCATTER) {
         mine = __reduce_add_sync(0xffffffffu, mine);
