@@ -55,8 +55,11 @@ typedef struct lgm_render_params {
     float scale_modifier;
 } lgm_render_params;
 
-#define LGM_GRAD_ROW 12 /* floats per (view, Gaussian) gradient row: mean2D 2, conic 3, opacity 1, rgb 3, depth 1, pad 2 */
+#define LGM_GRAD_ROW 12 /* floats per (view, Gaussian) gradient row (moment form, see lgm_backward): 5 moments,
+                           opacity 1, rgb 3, depth 1, pad 2 */
 
+/* 2: moment-form gradient rows (lgm_backward_geom takes conic_opacity), want_sorted_keys, direct binning. */
+#define LGM_ABI_VERSION 2
 int lgm_abi_version(void);
 const char* lgm_last_error_string(void);
 

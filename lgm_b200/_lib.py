@@ -21,6 +21,7 @@ class LgmError(RuntimeError):
 
 
 _lib = None
+ABI_VERSION = 2  # include/lgm_b200.h LGM_ABI_VERSION
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _pp = ctypes.POINTER(RenderParams)
 
@@ -68,6 +69,9 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        if l.lgm_abi_version() != ABI_VERSION:  # a stale build: the argument lists below would not match
+            raise LgmError(f"{LIB_PATH} has ABI version {l.lgm_abi_version()}, this package needs {ABI_VERSION}: "
+                           "rebuild with `python -m lgm_b200.build --force`")
         _lib = l
     return _lib
 

@@ -101,7 +101,7 @@ constexpr uint64_t kDirectMaxMeanTile = 12288;
 
 extern "C" {
 
-int lgm_abi_version(void) { return 1; }
+int lgm_abi_version(void) { return LGM_ABI_VERSION; }
 int lgm_last_bin_mode(void) { return g_last_bin_mode; }
 const char* lgm_last_error_string(void) { return g_err; }
 
