@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--forward-only", action="store_true", help="time render() under torch.no_grad() (implied by --workload orbit)")
+    ap.add_argument("--no-peer-gradients", action="store_true",
+                    help="N > 1: return the gradient blocks with an NCCL gather instead of K7 writing into the producer's peer-mapped buffer")
     ap.add_argument("--torch-loss", action="store_true", help="e2e: autograd's mse_loss instead of lgm_b200.mse_image_alpha_loss")
     ap.add_argument("--sort-sweep", action="store_true", help="also time every onesweep launch shape (LGM_SORT_VARIANT)")
     ap.add_argument("--loop-baseline", action="store_true",
@@ -204,7 +206,7 @@ def run_native(args):
     Bg, V, N, S, fovy, cfgname = WORKLOADS[args.workload]
     B = Bg * world
     opt = default_options(output_size=S, fovy=fovy)
-    renderer = ShardedGaussianRenderer(opt, device=dev)
+    renderer = ShardedGaussianRenderer(opt, device=dev, peer_gradients=not args.no_peer_gradients)
     # host-side (pinned) copies of the step's inputs; device-resident copies for the HBM-resident `value`
     g_host = make_gaussians(B, N, args.kind, seed=1234).pin_memory()
     cv, cvp, cp = make_cameras(B, V, fovy=fovy, seed=1234)
@@ -534,7 +536,7 @@ def run_native(args):
             "config": {"workload": f"{args.workload}: {cfgname}; per GPU {Bg} scenes x {V} views = {Bg * V} views/step, "
                                    f"{args.kind}-like Gaussians (SURVEY.md 8d), step = {B} scenes view-sharded over {world} GPU(s)",
                        "global_views": n_views_total, "gaussians_per_scene": N, "image": f"{S}x{S}",
-                       "parallelism": f"view-sharded x{world}" + (", Gaussians scattered from rank 0 (each rank receives the scenes it renders), [B,N,14] gradient blocks gathered to rank 0 (NCCL)" if world > 1 else ""),
+                       "parallelism": f"view-sharded x{world}" + (f", rank 0 produces the Gaussians and receives their gradient: {getattr(renderer, 'exchange', '?')}" if world > 1 else ""),
                        "l2": (f"per-step working set {working_set / 1e6:.0f} MB + instances: L2 flushed (256 MB write) between the "
                               "timed steps, each step timed on its own") if flush_l2 else
                              (f"per-step working set ({working_set / 1e9:.1f} GB of geometry, gradient rows and images, plus the "

@@ -26,57 +26,95 @@ def scene_blocks(n_scenes, views_per_scene, world_size):
     return per // views_per_scene
 
 
+_symm_cache = {}
+
+
+def _producer_buffer(shape, device, group, src):
+    """A [B,N,14] float32 buffer in SYMMETRIC memory (torch.distributed._symmetric_memory: every rank's copy is mapped
+    into every process of the node over NVLink) and this process's view of rank `src`'s copy.  Cached per shape.
+    Returns (handle, local buffer, view of src's buffer) or None when symmetric memory is not available."""
+    key = (tuple(shape), str(device), id(group), src)
+    hit = _symm_cache.get(key)
+    if hit is None:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            try:  # needed by some releases, deprecated (a no-op) in others
+                symm_mem.enable_symm_mem_for_group(grp.group_name)
+            except Exception:
+                pass
+            local = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(local, grp)
+            peer = hdl.get_buffer(src, tuple(shape), torch.float32)
+            hit = (hdl, local, peer)
+        except Exception as e:  # no symmetric memory on this system / backend: the caller uses the NCCL gather
+            hit = (None, None, repr(e))
+        _symm_cache[key] = hit
+    return None if hit[0] is None else hit
+
+
 class _ReplicatedInput(torch.autograd.Function):
     """Identity in forward (optionally a broadcast from `src`); sum of the ranks' gradients in backward, so the
     collective sits in the autograd graph of `gaussians` exactly once per step.  The sum is an all-reduce in general;
     when every rank owns whole scenes (`block` scenes each) it is an all-gather of the owned blocks.
 
     producer_only (needs `src` and whole-scene blocks): the Gaussians exist on `src` alone and only `src` wants their
-    gradient.  Then every rank is SENT just the scenes it renders (scatter; the other rows of its tensor are never read)
-    and returns just its block of the gradient to `src` (gather) — 1/world of the bytes of broadcast + all-gather on
-    every rank but `src`.  On the other ranks the returned gradient holds their own block only."""
+    gradient.  Then every rank is SENT just the scenes it renders (scatter) — the function returns that block,
+    [block,N,14] — and returns just its block of the gradient to `src`: with a gather, or, when a peer-memory sink is
+    in use (ShardedGaussianRenderer(peer_gradients=True)), not at all — the preprocess-backward kernel has already
+    written the block into `src`'s buffer over NVLink, and the backward here is a device-side barrier.  On the other
+    ranks the input receives no gradient."""
 
     @staticmethod
-    def forward(ctx, x, group, src, block, producer_only):
-        ctx.group, ctx.block, ctx.src = group, block, src
+    def forward(ctx, x, group, src, block, producer_only, peer):
+        ctx.group, ctx.block, ctx.src, ctx.peer = group, block, src, peer
         multi = dist.is_initialized() and dist.get_world_size(group) > 1
         ctx.producer_only = bool(producer_only and multi and src is not None and block is not None and
                                  x.shape[0] == block * dist.get_world_size(group))
+        ctx.full_shape = tuple(x.shape)
         if src is not None and multi:
             rank = dist.get_rank(group)
             if ctx.producer_only:
                 x_in = x.detach().contiguous()
-                x = torch.empty_like(x_in)  # only this rank's scenes are filled in — and only they are read
-                dist.scatter(x[rank * block:(rank + 1) * block], scatter_list=list(x_in.split(block)) if rank == src else None,
-                             src=src, group=group)
-            else:
-                x = x.contiguous().clone()
-                dist.broadcast(x, src=src, group=group)
+                x = torch.empty((block,) + tuple(x_in.shape[1:]), dtype=x_in.dtype, device=x_in.device)
+                dist.scatter(x, scatter_list=list(x_in.split(block)) if rank == src else None, src=src, group=group)
+                return x
+            x = x.contiguous().clone()
+            dist.broadcast(x, src=src, group=group)
         return x.view_as(x)
 
     @staticmethod
     def backward(ctx, g):
-        g = g.contiguous()
         if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
             world, rank = dist.get_world_size(ctx.group), dist.get_rank(ctx.group)
+            if ctx.producer_only and ctx.peer is not None:
+                hdl, local, peer = ctx.peer
+                sink = peer[rank * ctx.block:(rank + 1) * ctx.block]
+                # Normally g IS this rank's block of src's buffer, written by K7 through the peer mapping: nothing to
+                # send.  (A render that had to split its views into chunks sums the chunk gradients locally: copy.)
+                if g.data_ptr() != sink.data_ptr():
+                    sink.copy_(g)
+                hdl.barrier(channel=0)  # all blocks have landed before src reads them
+                return (local if rank == ctx.src else None), None, None, None, None, None
+            g = g.contiguous()
             if ctx.producer_only:
-                mine = g[rank * ctx.block:(rank + 1) * ctx.block].contiguous()
-                out = torch.empty_like(g) if rank == ctx.src else None
-                dist.gather(mine, gather_list=list(out.split(ctx.block)) if rank == ctx.src else None, dst=ctx.src,
+                out = torch.empty(ctx.full_shape, dtype=g.dtype, device=g.device) if rank == ctx.src else None
+                dist.gather(g, gather_list=list(out.split(ctx.block)) if rank == ctx.src else None, dst=ctx.src,
                             group=ctx.group)
-                g = out if rank == ctx.src else g
-            elif ctx.block is not None and g.shape[0] == ctx.block * world:
+                return (out if rank == ctx.src else None), None, None, None, None, None
+            if ctx.block is not None and g.shape[0] == ctx.block * world:
                 out = torch.empty_like(g)
                 dist.all_gather_into_tensor(out, g[rank * ctx.block:(rank + 1) * ctx.block].contiguous(), group=ctx.group)
                 g = out
             else:
                 g = g.clone()
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None, None, None, None
+        return g, None, None, None, None, None
 
 
-def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None, scenes_per_rank=None, producer_only=False):
-    return _ReplicatedInput.apply(gaussians, group, broadcast_src, scenes_per_rank, producer_only)
+def replicate_for_view_sharding(gaussians, group=None, broadcast_src=None, scenes_per_rank=None, producer_only=False,
+                                peer=None):
+    return _ReplicatedInput.apply(gaussians, group, broadcast_src, scenes_per_rank, producer_only, peer)
 
 
 def shard_views(cam_view, cam_view_proj, cam_pos, rank=None, world_size=None):
@@ -104,24 +142,44 @@ class ShardedGaussianRenderer:
     of the sum of all ranks' losses w.r.t. `gaussians` (one collective: all-reduce, or all-gather when every rank
     owns whole scenes).  With `broadcast_src` and `producer_only=True` the Gaussians are taken from rank `broadcast_src`
     alone and the summed gradient is delivered to that rank alone (scatter + gather instead of broadcast + all-gather
-    when every rank owns whole scenes)."""
+    when every rank owns whole scenes).
 
-    def __init__(self, opt, device="cuda", group=None):
+    peer_gradients=True (with producer_only): the gather is fused into the preprocess-backward kernel — every rank's
+    K7 writes its block of dL/dgaussians directly into the producer's buffer through symmetric (peer-mapped) memory, so
+    the transfer over NVLink overlaps the kernel, and the step ends with a device-side barrier instead of a collective.
+    The gradient the producer receives is then a view of a communication buffer that the next step with the same shape
+    overwrites — consume it (optimizer step, copy) before rendering again."""
+
+    def __init__(self, opt, device="cuda", group=None, peer_gradients=False):
         from .renderer import GaussianRenderer
         self.inner = GaussianRenderer(opt, device=device)
         self.group = group
+        self.peer_gradients = peer_gradients
 
     def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1, broadcast_src=None,
                producer_only=False):
         from . import ops
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        g = replicate_for_view_sharding(gaussians.contiguous().float(), self.group, broadcast_src,
-                                        scene_blocks(cam_view.shape[0], cam_view.shape[1], world), producer_only)
+        block = scene_blocks(cam_view.shape[0], cam_view.shape[1], world)
+        blockwise = bool(producer_only and world > 1 and broadcast_src is not None and block is not None)
+        peer, sink = None, None
+        if blockwise and self.peer_gradients and gaussians.is_cuda and torch.is_grad_enabled():
+            peer = _producer_buffer(tuple(gaussians.shape), gaussians.device, self.group, broadcast_src)
+            if peer is not None:
+                sink = peer[2][rank * block:(rank + 1) * block]
+        # how the gradient travels back (for reports)
+        self.exchange = ("none (single rank)" if world == 1 else
+                         "scatter + K7 writes into the producer's peer-mapped buffer, device barrier" if sink is not None else
+                         "scatter + gather to the producer" if blockwise else
+                         "all-gather of per-scene blocks" if block is not None else "all-reduce")
+        g = replicate_for_view_sharding(gaussians.contiguous().float(), self.group, broadcast_src, block, producer_only, peer)
         vm, pm, _cp, scene, (b, e) = shard_views(cam_view, cam_view_proj, cam_pos, rank, world)
+        if blockwise:
+            scene = scene - rank * block  # g holds this rank's scenes only
         S = int(self.inner.opt.output_size)
         bg = (self.inner.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
         cfg = ops.ViewConfig(S, S, float(self.inner.tan_half_fov), float(self.inner.tan_half_fov), float(scale_modifier),
                              clamp_image=True)  # core/gs.py:87, fused
-        image, alpha, depth, _ = ops.render_views(g, vm.to(g.device), pm.to(g.device), scene, bg, cfg)
+        image, alpha, depth, _ = ops.render_views(g, vm.to(g.device), pm.to(g.device), scene, bg, cfg, grad_sink=sink)
         return {"image": image, "alpha": alpha, "depth": depth, "views": (b, e)}

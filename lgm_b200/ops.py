@@ -183,10 +183,12 @@ class TooManyInstances(_lib.LgmError):
         self.n_instances = n
 
 
-def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth, cov3d=None):
+def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha, d_image, d_alpha, d_depth, cov3d=None,
+                   d_gauss_out=None):
     """Returns (dL_dgaussians [B,P,14], grad_rows [VW*P,12]).  grad_rows is in MOMENT form (include/lgm_b200.h,
     lgm_backward); screen_gradients() converts it to upstream's dL/dmean2D, dL/dconic, ... .
-    With cov3d (the forward's cov3D_precomp) returns (dL_dgaussians, grad_rows, dL_dcov3d [B,P,6])."""
+    With cov3d (the forward's cov3D_precomp) returns (dL_dgaussians, grad_rows, dL_dcov3d [B,P,6]).
+    d_gauss_out: where K7 writes dL_dgaussians instead of a fresh tensor — e.g. a peer GPU's memory (lgm_b200.dist)."""
     L = _lib.lib()
     dev = gaussians.device
     cfg = st.cfg
@@ -196,7 +198,10 @@ def backward_views(gaussians, view_mats, proj_mats, bg, st: ForwardState, alpha,
     st.grad_rows = None                          # used once: a second backward over the same state gets fresh rows
     if grad_rows is None:
         grad_rows = torch.zeros(max(st.n_views * st.P, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev)
-    d_gauss = torch.empty_like(gaussians)
+    if d_gauss_out is not None and (d_gauss_out.shape != gaussians.shape or d_gauss_out.dtype != torch.float32 or
+                                    not d_gauss_out.is_contiguous()):
+        raise _lib.LgmError("d_gauss_out must be a contiguous float32 tensor of the shape of gaussians")
+    d_gauss = torch.empty_like(gaussians) if d_gauss_out is None else d_gauss_out
     # (lgm_backward is these two calls back to back)
     _timed("composite_bwd", lambda: _lib.check(L.lgm_backward_composite(
         _stream(), prm, _lib.ptr(gaussians), _lib.ptr(st.view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity),
@@ -239,10 +244,11 @@ class _RenderViews(torch.autograd.Function):
     """image, alpha, depth, radii = f(gaussians [B,P,14]); gradients flow to gaussians only."""
 
     @staticmethod
-    def forward(ctx, gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg):
+    def forward(ctx, gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg, grad_sink=None):
         image, alpha, depth_img, st = forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg,
                                                     cfg, prepare_backward=ctx.needs_input_grad[0])
         ctx.st = st
+        ctx.grad_sink = grad_sink  # optional destination of dL/dgaussians (not an autograd input: no gradient)
         ctx.set_materialize_grads(False)  # an unused output (depth, in LGM) arrives as None, not as a zero image
         ctx.save_for_backward(gaussians, view_mats, proj_mats, bg, alpha)
         radii = st.radii.view(st.n_views, st.P)
@@ -256,8 +262,9 @@ class _RenderViews(torch.autograd.Function):
         d_image = _grad_or_zeros(d_image, alpha.expand(-1, 3, -1, -1))
         d_alpha = _grad_or_zeros(d_alpha, alpha)
         d_depth = None if d_depth is None else d_depth.contiguous().float()  # None -> NULL: no depth gradient
-        d_gauss, _ = backward_views(gaussians, view_mats, proj_mats, bg, st, alpha, d_image, d_alpha, d_depth)
-        return d_gauss, None, None, None, None, None, None
+        d_gauss, _ = backward_views(gaussians, view_mats, proj_mats, bg, st, alpha, d_image, d_alpha, d_depth,
+                                    d_gauss_out=ctx.grad_sink)
+        return d_gauss, None, None, None, None, None, None, None
 
 
 def _scene_offsets(view_scene_cpu, n_scenes):
@@ -283,12 +290,13 @@ def _device_view_maps(local_scene, n_scenes, device):
 
 
 def render_views(gaussians, view_mats, proj_mats, view_scene_cpu, bg, cfg: ViewConfig,
-                 max_views_per_call: Optional[int] = None):
+                 max_views_per_call: Optional[int] = None, grad_sink=None):
     """Differentiable rendering of VW views of B scenes.
 
     gaussians [B,P,14] cuda fp32; view_mats / proj_mats [VW,16]; view_scene_cpu: CPU int tensor [VW], non-decreasing
     (views of a scene contiguous).  Splits the views into chunks when one call would exceed the library limits
     (pairs, instances); autograd sums the chunk gradients.  Returns image, alpha, depth, radii [VW,P].
+    grad_sink [B,P,14]: where the backward writes dL/dgaussians (used when the whole call is one chunk; see lgm_b200.dist).
     """
     VW = view_mats.shape[0]
     B, P = gaussians.shape[0], gaussians.shape[1]
@@ -307,9 +315,10 @@ def render_views(gaussians, view_mats, proj_mats, view_scene_cpu, bg, cfg: ViewC
         local_scene = (vs - b0).int()
         try:
             scene_dev, offsets_dev = _device_view_maps(local_scene, b1 - b0, gaussians.device)
+            whole = (b0, b1) == (0, B) and (v0, v1) == (0, VW)
             o = _RenderViews.apply(
                 gaussians[b0:b1] if (b0, b1) != (0, B) else gaussians, view_mats[v0:v1], proj_mats[v0:v1],
-                scene_dev, offsets_dev, bg, cfg)
+                scene_dev, offsets_dev, bg, cfg, grad_sink if whole else None)
         except TooManyInstances as e:
             if v1 - v0 <= 1:
                 raise
