@@ -39,10 +39,13 @@ def _producer_buffer(shape, device, group, src):
         try:
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else dist.group.WORLD
-            try:  # needed by some releases, deprecated (a no-op) in others
-                symm_mem.enable_symm_mem_for_group(grp.group_name)
-            except Exception:
-                pass
+            import warnings
+            with warnings.catch_warnings():  # needed by some releases, deprecated (a no-op) in others
+                warnings.simplefilter("ignore")
+                try:
+                    symm_mem.enable_symm_mem_for_group(grp.group_name)
+                except Exception:
+                    pass
             local = symm_mem.empty(*shape, dtype=torch.float32, device=device)
             hdl = symm_mem.rendezvous(local, grp)
             peer = hdl.get_buffer(src, tuple(shape), torch.float32)
