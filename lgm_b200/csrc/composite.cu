@@ -14,7 +14,7 @@
 // warp iterations drop to 0.79x (4x4) / 0.68x (4x2) of the 8x4 count.
 //
 // Scheduling: after culling, the work of the 8 warps of a tile is uneven, so block barriers are the enemy.  512 (fwd)
-// / 768 (bwd) Gaussians (24 / 36 KB of the SM's 227 KB shared memory) are staged per barrier — most tiles need one or
+// / 640 (bwd) Gaussians (24 / 30 KB of the SM's 227 KB shared memory) are staged per barrier — most tiles need one or
 // two — and the warps then run independently to the end of the batch.
 //
 // Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / L2 reductions in the backward).
@@ -26,9 +26,10 @@ namespace lgm {
 namespace {
 
 // Gaussians staged per block barrier (LGM_FWD_BATCH / LGM_BWD_BATCH override).  Measured on B200, 208 views x 98,304
-// Gaussians: fwd 3.64 / 3.53 / 3.56 / 3.62 / 4.75 ms and bwd 7.07 / 6.85 / 6.77 / 7.42 / 8.09 ms at 256 / 512 / 768 / 1024 / 1536.
+// Gaussians, shipped kernels: fwd 2.91 / 2.87 / 2.88 / 2.96 / 3.68 / 3.31 ms and bwd 5.25 / 5.17 / 5.10 / 5.08 / 5.15 / 6.10 ms
+// at 256 / 384 / 512 / 640 / 768 / 1024.
 constexpr int kFwdBatch = 512;
-constexpr int kBwdBatch = 768;
+constexpr int kBwdBatch = 640;
 constexpr int kPatchLanes = 32;  // lanes per pixel patch (LGM_PATCH_LANES overrides): 32 = 8x4, 16 = 4x4, 8 = 4x2 pixels
 constexpr uint32_t kClampFlag0 = 1u << 29;      // n_contrib bits 29..31: colour channel 0..2 was clamped
 constexpr uint32_t kContribMask = kClampFlag0 - 1u;
