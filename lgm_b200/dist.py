@@ -1,8 +1,10 @@
-"""View-sharded rendering over the GPUs of one box: every rank holds all Gaussians, renders a
-contiguous block of the step's B*V views with the local CUDA path, and the per-Gaussian gradients are combined with
-ONE all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests of the host logic).  Images stay on the rank that
-rendered them.  The reference itself never shards views (each DDP rank renders its own batch,
-/root/reference/main.py:82,102); this is the north_star's addition.
+"""View-sharded rendering over the GPUs of one box: every rank renders a contiguous block of the step's
+B*V views with the local CUDA path; the per-Gaussian gradients are combined once per step, inside the autograd graph,
+by the cheapest exchange that fits (all-reduce; all-gather of per-scene blocks; scatter + gather when one rank produces
+the Gaussians; or, fused, the preprocess-backward kernel writing straight into the producer's peer-mapped buffer) —
+NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic.  Images stay on the rank that rendered them.  The
+reference itself never shards views (each DDP rank renders its own batch, /root/reference/main.py:82,102); this is the
+north_star's addition.
 """
 import torch
 import torch.distributed as dist

@@ -129,8 +129,8 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
     st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
     st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
-    # The ONE host<->device synchronisation of the step (upstream: one per view): the instance count sizes the
-    # sort buffers.
+    # The host<->device synchronisation of the step (upstream: one per view): the instance count sizes the instance
+    # buffers.  (lgm_forward_bin adds a 4-byte readback of the longest tile when it takes the direct binning path.)
     n_inst = int(total.item())
     st.num_rendered = n_inst
     if n_inst > MAX_INSTANCES:
