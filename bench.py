@@ -268,6 +268,30 @@ def run_native(args):
         loss.backward()
         return float(loss.item())  # D2H read of the step's result
 
+    gt8 = {}
+
+    def step_e2e_u8():
+        """step_e2e with the ground truth kept as 8-bit images / masks on the host (what the image files hold) and read as
+        such by the loss kernel: a quarter of the PCIe bytes.  Reported beside `e2e`, not as `e2e` — the reference's
+        loader hands float32 tensors to the device."""
+        if not gt8:
+            gt8["img"] = (gt_img_host * 255).round().to(torch.uint8).pin_memory()
+            gt8["mask"] = (gt_mask_host * 255).to(torch.uint8).pin_memory()
+        main = torch.cuda.current_stream()
+        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
+        cvd, cvpd, cpd = cv_host.to(dev, non_blocking=True), cvp_host.to(dev, non_blocking=True), cp_host.to(dev, non_blocking=True)
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            gt_i, gt_m = gt8["img"].to(dev, non_blocking=True), gt8["mask"].to(dev, non_blocking=True)
+        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
+        main.wait_stream(copy_stream)
+        gt_i.record_stream(main)
+        gt_m.record_stream(main)
+        loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
+                                    w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
+        loss.backward()
+        return float(loss.item())
+
     def issue_copies():
         """All inputs of one step, host -> device on the copy stream; returns the device tensors and an event."""
         with torch.cuda.stream(copy_stream):
@@ -361,6 +385,8 @@ def run_native(args):
         h2d = sum(t.numel() * t.element_size() for t in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host))
         ms_p, _ = timed(step_e2e_prefetch, max(3, args.steps), 3)
         ms_c, _ = timed(step_copies_only, 5, 3)
+        ms_8, _ = timed(step_e2e_u8, max(3, args.steps), 3)
+        h2d_8 = h2d - 3 * (gt_img_host.numel() + gt_mask_host.numel())
         e2e = {"value": n_views_total / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 8,
                "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss "
@@ -368,6 +394,8 @@ def run_native(args):
                        "the ground truth is copied on a side stream while the same step renders",
                # context: the copies alone, and the step with the next step's inputs prefetched during this one
                "h2d_alone_ms": ms_c, "h2d_alone_gbs": h2d / (ms_c * 1e-3) / 1e9,
+               "u8_ground_truth": {"value": n_views_total / (ms_8 * 1e-3), "ms_per_step": ms_8, "h2d_bytes_per_step": int(h2d_8),
+                                   "what": "the same step with the ground-truth images / masks kept 8-bit on the host and read as such by the loss kernel"},
                "prefetched_inputs": {"value": n_views_total / (ms_p * 1e-3), "ms_per_step": ms_p,
                                      "what": "each step issues the copy of the next step's inputs and consumes the set copied during the previous step"}}
 

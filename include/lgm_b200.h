@@ -196,6 +196,12 @@ int lgm_resize_bilinear_forward(void* stream, const float* x, float* y, int64_t 
 int lgm_resize_bilinear_backward(void* stream, const float* dy, float* dx, int64_t n_planes, int32_t h_in, int32_t w_in,
                                  int32_t h_out, int32_t w_out, float mul);
 
+/* The same with 8-bit ground truth (what an image file holds; a quarter of the host->device bytes): gt = value / 255.
+ * gt_image / gt_alpha 4-byte aligned. */
+int lgm_mse_loss_grad_u8(void* stream, const float* image, const uint8_t* gt_image, float* d_image, int64_t n_image,
+                         float w_image, const float* alpha, const uint8_t* gt_alpha, float* d_alpha, int64_t n_alpha,
+                         float w_alpha, double* loss, const float* grad_scale);
+
 /* Colours from spherical harmonics — the `shs` argument of GaussianRasterizer.forward
  * (diff_gaussian_rasterization/__init__.py: shs / sh_degree / campos; upstream computeColorFromSH in
  * cuda_rasterizer/forward.cu and its backward in backward.cu).  LGM itself passes colors_precomp

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "lgm_mse_loss_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp]),
     "lgm_resize_bilinear_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float, ctypes.c_float]),
     "lgm_resize_bilinear_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float]),
+    "lgm_mse_loss_grad_u8": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp]),
     "lgm_sh_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sh_backward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgm_sort_input_is_tmp": (ctypes.c_int, [_i32]),

@@ -409,6 +409,23 @@ int lgm_resize_bilinear_backward(void* stream, const float* dy, float* dx, int64
     return LGM_OK;
 }
 
+int lgm_mse_loss_grad_u8(void* stream, const float* image, const uint8_t* gt_image, float* d_image, int64_t n_image,
+                         float w_image, const float* alpha, const uint8_t* gt_alpha, float* d_alpha, int64_t n_alpha,
+                         float w_alpha, double* loss, const float* grad_scale)
+{
+    if (n_image < 0 || n_alpha < 0) return fail(LGM_ERR_BAD_SHAPE, "negative element count");
+    if (n_image > 0) { LGM_NOTNULL(image); LGM_NOTNULL(gt_image); }
+    if (n_alpha > 0) { LGM_NOTNULL(alpha); LGM_NOTNULL(gt_alpha); }
+    if (((uintptr_t)image | (uintptr_t)d_image | (uintptr_t)alpha | (uintptr_t)d_alpha) & 15u)
+        return fail(LGM_ERR_BAD_SHAPE, "mse_loss_grad_u8: float pointers must be 16-byte aligned");
+    if (((uintptr_t)gt_image | (uintptr_t)gt_alpha) & 3u)
+        return fail(LGM_ERR_BAD_SHAPE, "mse_loss_grad_u8: 8-bit ground-truth pointers must be 4-byte aligned");
+    LGM_CUDA(lgm::launch_mse_loss_grad_u8((cudaStream_t)stream, image, gt_image, d_image, (size_t)n_image, w_image, alpha,
+                                          gt_alpha, d_alpha, (size_t)n_alpha, w_alpha, loss, grad_scale),
+             "mse_loss_grad_u8");
+    return LGM_OK;
+}
+
 static int sh_shape_ok(int32_t n_points, int32_t degree, int32_t max_coeffs)
 {
     if (n_points < 0) return fail(LGM_ERR_BAD_SHAPE, "n_points < 0");

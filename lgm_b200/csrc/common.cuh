@@ -48,6 +48,9 @@ cudaError_t launch_resize_bilinear_fwd(cudaStream_t stream, const float* x, floa
                                        int w_out, float mul, float add);
 cudaError_t launch_resize_bilinear_bwd(cudaStream_t stream, const float* dy, float* dx, int n_planes, int h_in, int w_in, int h_out,
                                        int w_out, float mul);
+cudaError_t launch_mse_loss_grad_u8(cudaStream_t stream, const float* image, const uint8_t* gt_image, float* d_image, size_t n_img,
+                                    float w_img, const float* alpha, const uint8_t* gt_alpha, float* d_alpha, size_t n_alpha,
+                                    float w_alpha, double* loss, const float* grad_scale);
 // sh.cu: the `shs` input of the Level-1 API (view-dependent colour, degrees 0..3) and its backward
 cudaError_t launch_sh_forward(cudaStream_t stream, int P, int deg, int max_coeffs, const float* means, const float* campos,
                               const float* shs, float* colors, uint8_t* clamped);

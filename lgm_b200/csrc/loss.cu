@@ -22,10 +22,22 @@ __device__ __forceinline__ float4 sq_grad(const float4 x, const float4 y, float 
     return make_float4(w2 * d.x, w2 * d.y, w2 * d.z, w2 * d.w);
 }
 
+// ground truth as float, or as 8-bit values scaled by 1/255 (what an image file holds: a quarter of the PCIe bytes)
+__device__ __forceinline__ float4 load_gt4(const float* y, size_t i) { return __ldg(reinterpret_cast<const float4*>(y) + i); }
+__device__ __forceinline__ float load_gt1(const float* y, size_t i) { return y[i]; }
+__device__ __forceinline__ float4 load_gt4(const uint8_t* y, size_t i)
+{
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(y) + i);
+    constexpr float k = 1.0f / 255.0f;
+    return make_float4(k * (float)v.x, k * (float)v.y, k * (float)v.z, k * (float)v.w);
+}
+__device__ __forceinline__ float load_gt1(const uint8_t* y, size_t i) { return (1.0f / 255.0f) * (float)y[i]; }
+
 // part 0: image (n_img floats, weight w_img), part 1: alpha; both arrays are walked as float4 with a scalar tail
+template <typename GT>
 __global__ void __launch_bounds__(kLossBlock)
-mse_loss_grad_kernel(const float* __restrict__ image, const float* __restrict__ gt_image, float* __restrict__ d_image,
-                     size_t n_img, float w_img, const float* __restrict__ alpha, const float* __restrict__ gt_alpha,
+mse_loss_grad_kernel(const float* __restrict__ image, const GT* __restrict__ gt_image, float* __restrict__ d_image,
+                     size_t n_img, float w_img, const float* __restrict__ alpha, const GT* __restrict__ gt_alpha,
                      float* __restrict__ d_alpha, size_t n_alpha, float w_alpha, double* __restrict__ loss,
                      const float* __restrict__ grad_scale)
 {
@@ -36,7 +48,7 @@ mse_loss_grad_kernel(const float* __restrict__ image, const float* __restrict__ 
 #pragma unroll
     for (int part = 0; part < 2; part++) {
         const float* x = part ? alpha : image;
-        const float* y = part ? gt_alpha : gt_image;
+        const GT* y = part ? gt_alpha : gt_image;
         float* d = part ? d_alpha : d_image;
         const size_t n = part ? n_alpha : n_img;
         const float w = part ? w_alpha : w_img;
@@ -44,12 +56,12 @@ mse_loss_grad_kernel(const float* __restrict__ image, const float* __restrict__ 
         float acc = 0.f;
         const size_t n4 = n / 4;
         for (size_t i = tid; i < n4; i += stride) {
-            const float4 xv = reinterpret_cast<const float4*>(x)[i], yv = __ldg(reinterpret_cast<const float4*>(y) + i);
+            const float4 xv = reinterpret_cast<const float4*>(x)[i], yv = load_gt4(y, i);
             const float4 g = sq_grad(xv, yv, w2, acc);
             if (d) reinterpret_cast<float4*>(d)[i] = g;
         }
         for (size_t i = n4 * 4 + tid; i < n; i += stride) {
-            const float df = x[i] - y[i];
+            const float df = x[i] - load_gt1(y, i);
             acc += df * df;
             if (d) d[i] = w2 * df;
         }
@@ -70,10 +82,11 @@ mse_loss_grad_kernel(const float* __restrict__ image, const float* __restrict__ 
 
 }  // namespace
 
-// Pointers must be 16-byte aligned; d_image / d_alpha / loss / grad_scale may be null.
-cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
-                                 float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,
-                                 float w_alpha, double* loss, const float* grad_scale)
+// Pointers must be 16-byte aligned (4-byte for 8-bit ground truth); d_image / d_alpha / loss / grad_scale may be null.
+template <typename GT>
+static cudaError_t launch_mse(cudaStream_t stream, const float* image, const GT* gt_image, float* d_image, size_t n_img,
+                              float w_img, const float* alpha, const GT* gt_alpha, float* d_alpha, size_t n_alpha, float w_alpha,
+                              double* loss, const float* grad_scale)
 {
     if (loss) {
         cudaError_t err = cudaMemsetAsync(loss, 0, sizeof(double), stream);
@@ -88,9 +101,23 @@ cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const 
     }
     const size_t want = (n_img / 4 + n_alpha / 4 + kLossBlock - 1) / kLossBlock + 1;
     const unsigned grid = (unsigned)(want < (size_t)n_sm * 16 ? want : (size_t)n_sm * 16);
-    mse_loss_grad_kernel<<<grid, kLossBlock, 0, stream>>>(image, gt_image, d_image, n_img, w_img, alpha, gt_alpha, d_alpha, n_alpha,
-                                                          w_alpha, loss, grad_scale);
+    mse_loss_grad_kernel<GT><<<grid, kLossBlock, 0, stream>>>(image, gt_image, d_image, n_img, w_img, alpha, gt_alpha, d_alpha,
+                                                              n_alpha, w_alpha, loss, grad_scale);
     return cudaGetLastError();
+}
+
+cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
+                                 float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,
+                                 float w_alpha, double* loss, const float* grad_scale)
+{
+    return launch_mse<float>(stream, image, gt_image, d_image, n_img, w_img, alpha, gt_alpha, d_alpha, n_alpha, w_alpha, loss, grad_scale);
+}
+
+cudaError_t launch_mse_loss_grad_u8(cudaStream_t stream, const float* image, const uint8_t* gt_image, float* d_image, size_t n_img,
+                                    float w_img, const float* alpha, const uint8_t* gt_alpha, float* d_alpha, size_t n_alpha,
+                                    float w_alpha, double* loss, const float* grad_scale)
+{
+    return launch_mse<uint8_t>(stream, image, gt_image, d_image, n_img, w_img, alpha, gt_alpha, d_alpha, n_alpha, w_alpha, loss, grad_scale);
 }
 
 }  // namespace lgm

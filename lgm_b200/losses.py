@@ -20,13 +20,19 @@ class _MSEImageAlpha(torch.autograd.Function):
         if pred_images.shape != gt_images.shape or pred_alphas.shape != gt_masks.shape:
             raise _lib.LgmError("prediction and ground-truth shapes differ")
         x, a = pred_images.contiguous().float(), pred_alphas.contiguous().float()
-        gx, ga = gt_images.contiguous().float(), gt_masks.contiguous().float()
+        # 8-bit ground truth (both tensors uint8, value / 255 — what an image file holds) stays 8-bit: a quarter of the
+        # bytes to copy from the host; anything else is read as float32
+        ctx.u8 = gt_images.dtype == torch.uint8 and gt_masks.dtype == torch.uint8
+        if ctx.u8:
+            gx, ga = gt_images.contiguous(), gt_masks.contiguous()
+        else:
+            gx, ga = gt_images.contiguous().float(), gt_masks.contiguous().float()
         loss = torch.empty(1, dtype=torch.float64, device=x.device)
         ctx.wi = 1.0 / max(x.numel(), 1) if w_image is None else float(w_image)
         ctx.wa = 1.0 / max(a.numel(), 1) if w_alpha is None else float(w_alpha)
-        _lib.check(_lib.lib().lgm_mse_loss_grad(ops._stream(), _lib.ptr(x), _lib.ptr(gx), None, x.numel(), ctx.wi,
-                                                _lib.ptr(a), _lib.ptr(ga), None, a.numel(), ctx.wa, _lib.ptr(loss), None),
-                   "lgm_mse_loss_grad")
+        fn = _lib.lib().lgm_mse_loss_grad_u8 if ctx.u8 else _lib.lib().lgm_mse_loss_grad
+        _lib.check(fn(ops._stream(), _lib.ptr(x), _lib.ptr(gx), None, x.numel(), ctx.wi, _lib.ptr(a), _lib.ptr(ga), None,
+                      a.numel(), ctx.wa, _lib.ptr(loss), None), "lgm_mse_loss_grad")
         ops.launch_counter["kernels"] += 1
         ctx.save_for_backward(x, a, gx, ga)
         return loss[0].float()
@@ -38,16 +44,17 @@ class _MSEImageAlpha(torch.autograd.Function):
             return None, None, None, None, None, None
         d_x, d_a = torch.empty_like(x), torch.empty_like(a)
         scale = grad_loss.reshape(1).float().contiguous()  # stays on the device: no host sync to look at its value
-        _lib.check(_lib.lib().lgm_mse_loss_grad(ops._stream(), _lib.ptr(x), _lib.ptr(gx), _lib.ptr(d_x), x.numel(), ctx.wi,
-                                                _lib.ptr(a), _lib.ptr(ga), _lib.ptr(d_a), a.numel(), ctx.wa, None,
-                                                _lib.ptr(scale)), "lgm_mse_loss_grad")
+        fn = _lib.lib().lgm_mse_loss_grad_u8 if ctx.u8 else _lib.lib().lgm_mse_loss_grad
+        _lib.check(fn(ops._stream(), _lib.ptr(x), _lib.ptr(gx), _lib.ptr(d_x), x.numel(), ctx.wi, _lib.ptr(a), _lib.ptr(ga),
+                      _lib.ptr(d_a), a.numel(), ctx.wa, None, _lib.ptr(scale)), "lgm_mse_loss_grad")
         ops.launch_counter["kernels"] += 1
         return d_x, d_a, None, None, None, None
 
 
 def mse_image_alpha_loss(pred_images, pred_alphas, gt_images, gt_masks, w_image=None, w_alpha=None):
     """mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks) (mean reduction by default; w_image / w_alpha
-    override the per-element weights, e.g. 1 / global element count when the views are sharded over ranks)."""
+    override the per-element weights, e.g. 1 / global element count when the views are sharded over ranks).
+    gt_images and gt_masks may both be uint8 (0..255 = 0..1): they are then read as they are, without a float copy."""
     return _MSEImageAlpha.apply(pred_images, pred_alphas, gt_images, gt_masks, w_image, w_alpha)
 
 

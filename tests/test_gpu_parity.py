@@ -649,6 +649,14 @@ def test_fused_mse_loss_matches_torch():
         assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
         assert (gx2 - gxr).abs().max().item() <= 1e-6 * gxr.abs().max().item()
         assert (ga2 - gar).abs().max().item() <= 1e-6 * gar.abs().max().item()
+        # 8-bit ground truth (value / 255), read by the kernel as it is
+        gx8, ga8 = (gx * 255).round().to(torch.uint8), (ga * 255).to(torch.uint8)
+        ref8 = F.mse_loss(x.double(), gx8.double() / 255) + F.mse_loss(a.double(), ga8.double() / 255)
+        g8r = torch.autograd.grad(ref8, [x, a])
+        loss8 = mse_image_alpha_loss(x, a, gx8, ga8)
+        g8 = torch.autograd.grad(loss8, [x, a])
+        assert abs(loss8.item() - ref8.item()) <= 1e-6 * abs(ref8.item())
+        assert all((p - q).abs().max().item() <= 1e-6 * q.abs().max().item() for p, q in zip(g8, g8r))
         # explicit weights (views sharded over ranks: normalise by the global element count)
         loss_w = mse_image_alpha_loss(x, a, gx, ga, w_image=0.5 / x.numel(), w_alpha=0.25 / a.numel())
         ref_w = 0.5 * F.mse_loss(x.double(), gx.double()) + 0.25 * F.mse_loss(a.double(), ga.double())
