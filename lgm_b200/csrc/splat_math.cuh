@@ -160,11 +160,15 @@ LGM_HD float ndc2pix(float v, int S)
 
 LGM_HD void tile_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0, int& x1, int& y1)
 {
+    // upstream divides by BLOCK_X = 16; a correctly rounded division by a power of two IS the multiplication by its
+    // reciprocal (exact scaling, no underflow for pixel coordinates), at a fraction of the instructions — this function
+    // runs in K1, the count, the scatter and the emit kernels
     const float r = (float)radius;
-    x0 = imin_(gx, imax_(0, LGM_F2I(LGM_DIV(LGM_SUB(px, r), 16.0f))));
-    y0 = imin_(gy, imax_(0, LGM_F2I(LGM_DIV(LGM_SUB(py, r), 16.0f))));
-    x1 = imin_(gx, imax_(0, LGM_F2I(LGM_DIV(LGM_SUB(LGM_ADD(LGM_ADD(px, r), 16.0f), 1.0f), 16.0f))));
-    y1 = imin_(gy, imax_(0, LGM_F2I(LGM_DIV(LGM_SUB(LGM_ADD(LGM_ADD(py, r), 16.0f), 1.0f), 16.0f))));
+    constexpr float kInvTile = 1.0f / 16.0f;
+    x0 = imin_(gx, imax_(0, LGM_F2I(LGM_MUL(LGM_SUB(px, r), kInvTile))));
+    y0 = imin_(gy, imax_(0, LGM_F2I(LGM_MUL(LGM_SUB(py, r), kInvTile))));
+    x1 = imin_(gx, imax_(0, LGM_F2I(LGM_MUL(LGM_SUB(LGM_ADD(LGM_ADD(px, r), 16.0f), 1.0f), kInvTile))));
+    y1 = imin_(gy, imax_(0, LGM_F2I(LGM_MUL(LGM_SUB(LGM_ADD(LGM_ADD(py, r), 16.0f), 1.0f), kInvTile))));
 }
 
 // A.1 for one (view, Gaussian).  g = the 14 floats of /root/reference/core/gs.py:45-49 minus colour:
