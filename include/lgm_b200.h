@@ -108,7 +108,8 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
  * [n_views,H,W] (bits 0..28: number of list entries the pixel consumed, as upstream).
  * clamp_image == 0: image as upstream writes it (not clamped).  clamp_image != 0: the caller's clamp(0,1) of
  * /root/reference/core/gs.py:87 is fused into the store, and bits 29..31 of n_contrib flag the colour channels whose
- * gradient that clamp blocks; lgm_backward* honours the flags, so d(clamped image) is what it must be given.    */
+ * gradient that clamp blocks; lgm_backward* honours the flags, so d(clamped image) is what it must be given.
+ * depth_img may be NULL: the depth image is not computed (LGM computes it and drops it, core/gs.py:76).          */
 int lgm_forward_composite(void* stream, const lgm_render_params* prm, const float* gaussians,
                           const int32_t* view_scene, const float* xy, const float* conic_opacity, const float* depth,
                           const uint32_t* vals_sorted, const uint32_t* ranges, const float* bg, int32_t clamp_image,

@@ -236,7 +236,7 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     if (p.n_views == 0) return LGM_OK;
-    LGM_NOTNULL(view_scene); LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(image); LGM_NOTNULL(alpha); LGM_NOTNULL(depth_img);
+    LGM_NOTNULL(view_scene); LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(image); LGM_NOTNULL(alpha);
     LGM_NOTNULL(n_contrib);
     if (p.P > 0) { LGM_NOTNULL(gaussians); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth); }
     LGM_CUDA(lgm::launch_composite_fwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),

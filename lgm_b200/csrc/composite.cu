@@ -118,8 +118,9 @@ __device__ __forceinline__ uint32_t patch_mask(float px, float py, const float4 
     return m;
 }
 
-// Gather one instance (row g of the per-(view,Gaussian) arrays + its colour) into a staged record.
-template <int LANES>
+// Gather one instance (row g of the per-(view,Gaussian) arrays + its colour) into a staged record.  DEPTH = false: the
+// caller uses neither the depth image nor its gradient, the depth of the instance is not fetched.
+template <int LANES, bool DEPTH>
 __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view_base, const float* __restrict__ scene_g,
                                           const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                                           const float* __restrict__ depth, float tile_x0, float tile_y0)
@@ -129,7 +130,7 @@ __device__ __forceinline__ void stage_one(Staged& dst, uint32_t g, uint32_t view
     const float* col = scene_g + (size_t)(g - view_base) * 14 + 11;
     dst.p0 = make_float4(p.x, p.y, co.x, co.y);
     dst.p1 = make_float4(co.z, co.w, __uint_as_float(g), __uint_as_float(patch_mask<LANES>(p.x, p.y, co, tile_x0, tile_y0)));
-    dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), depth[g]);
+    dst.rgbd = make_float4(__ldg(col), __ldg(col + 1), __ldg(col + 2), DEPTH ? depth[g] : 0.0f);
 }
 
 // The per-patch hit lists of one group of 32 staged records: lane jl offers the mask of record jl (0 = not a
@@ -147,7 +148,8 @@ __device__ __forceinline__ unsigned patch_hits(uint32_t mk, int warp, int sub)
     return m;
 }
 
-template <int LANES>
+// DEPTH: whether the depth image is wanted (LGM computes it and drops it, /root/reference/core/gs.py:76)
+template <int LANES, bool DEPTH>
 __global__ void __launch_bounds__(kBlock, 6)
 composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                      const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
@@ -185,7 +187,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         if (__syncthreads_count(done) == kBlock) break;  // also the barrier that protects the staging buffer
         const int nb = min(batch, todo - r0);
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one<LANES>(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+            stage_one<LANES, DEPTH>(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             if (__all_sync(0xffffffffu, done)) break;  // every pixel of the warp's region is saturated (or outside)
@@ -215,7 +217,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
                 C1 = LGM_FMA(LGM_MUL(cd.y, ae), T, C1);
                 C2 = LGM_FMA(LGM_MUL(cd.z, ae), T, C2);
                 Wt = LGM_FMA(ae, T, Wt);
-                D = LGM_FMA(LGM_MUL(cd.w, ae), T, D);
+                if (DEPTH) D = LGM_FMA(LGM_MUL(cd.w, ae), T, D);
                 T = comp ? test_T : T;
                 last = comp ? (uint32_t)(r0 + j + 1) : last;  // 1-based position in the tile's list (A.4 "contributor")
             }
@@ -240,7 +242,7 @@ composite_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         img[hw] = o1;
         img[2 * hw] = o2;
         alpha_img[(size_t)view * hw + pix] = Wt;
-        depth_img[(size_t)view * hw + pix] = D;
+        if (DEPTH) depth_img[(size_t)view * hw + pix] = D;
     }
 }
 
@@ -363,8 +365,8 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
         const int nb = min(batch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
         for (int k = threadIdx.x; k < nb; k += kBlock)
-            stage_one<LANES>(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity,
-                             depth, tile_x0, tile_y0);
+            stage_one<LANES, DEPTH>(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy,
+                                    conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
@@ -470,7 +472,7 @@ int patch_lanes_from_env()
     return kPatchLanes;
 }
 
-template <int LANES>
+template <int LANES, bool DEPTH>
 cudaError_t run_fwd(cudaStream_t stream, unsigned blocks, int smem, const RenderParams& prm, const float* gaussians,
                     const int32_t* view_scene, const float2* xy, const float4* conic_opacity, const float* depth,
                     const uint32_t* vals, const uint2* ranges, const float* bg, int clamp_image, int batch, float* image,
@@ -478,12 +480,12 @@ cudaError_t run_fwd(cudaStream_t stream, unsigned blocks, int smem, const Render
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<LANES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kMaxBatch * (int)sizeof(Staged));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    composite_fwd_kernel<LANES><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges,
+    composite_fwd_kernel<LANES, DEPTH><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges,
                                                                   bg, clamp_image, batch, image, alpha, depth_img, n_contrib);
     return cudaGetLastError();
 }
@@ -518,12 +520,20 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
     if (blocks == 0) return cudaSuccess;
     const int batch = batch_from_env("LGM_FWD_BATCH", kFwdBatch);
     const int smem = batch * (int)sizeof(Staged);
-#define LGM_FWD(L) run_fwd<L>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, \
-                              bg, clamp_image, batch, image, alpha, depth_img, n_contrib)
-    switch (patch_lanes_from_env()) {
-        case 32: return LGM_FWD(32);
-        case 16: return LGM_FWD(16);
-        default: return LGM_FWD(8);
+#define LGM_FWD(L, D) run_fwd<L, D>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, \
+                                    ranges, bg, clamp_image, batch, image, alpha, depth_img, n_contrib)
+    const int lanes = patch_lanes_from_env();
+    if (depth_img) {
+        switch (lanes) {
+            case 32: return LGM_FWD(32, true);
+            case 16: return LGM_FWD(16, true);
+            default: return LGM_FWD(8, true);
+        }
+    }
+    switch (lanes) {
+        case 32: return LGM_FWD(32, false);
+        case 16: return LGM_FWD(16, false);
+        default: return LGM_FWD(8, false);
     }
 #undef LGM_FWD
 }

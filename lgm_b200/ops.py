@@ -61,6 +61,7 @@ class ViewConfig:
     scale_modifier: float = 1.0
     keep_binning: bool = False  # keep sorted keys / tiles_touched (parity tests)
     clamp_image: bool = False   # fuse the renderer's clamp(0,1) (core/gs.py:87) and its gradient mask into the kernels
+    want_depth: bool = True     # False: no depth image (returned as None); LGM computes it and drops it (core/gs.py:76)
 
 
 def _stream():
@@ -126,7 +127,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     st.grad_rows = torch.zeros(max(npair, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev) if prepare_backward else None
     image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
     alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
-    depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
+    depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev) if cfg.want_depth else None
     st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
     st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
     # The host<->device synchronisation of the step (upstream: one per view): the instance count sizes the instance
@@ -330,4 +331,4 @@ def render_views(gaussians, view_mats, proj_mats, view_scene_cpu, bg, cfg: ViewC
             break
     if len(outs) == 1:
         return outs[0]
-    return tuple(torch.cat([o[i] for o in outs], 0) for i in range(4))
+    return tuple(None if outs[0][i] is None else torch.cat([o[i] for o in outs], 0) for i in range(4))

@@ -39,7 +39,7 @@ class GaussianRenderer:
         return self._view_scene_cache[key]
 
     def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1,
-               max_views_per_call=None):
+               max_views_per_call=None, return_depth=True):
         # gaussians: [B, N, 14]; cam_view, cam_view_proj: [B, V, 4, 4]; cam_pos: [B, V, 3] (only used by SH
         # evaluation upstream, which LGM never triggers — kept for signature parity)
         B, V = cam_view.shape[:2]
@@ -50,13 +50,17 @@ class GaussianRenderer:
         bg = (self.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
         # core/gs.py:87 clamps the image (alpha is not clamped): fused into the compositing kernels (clamp_image)
         cfg = ops.ViewConfig(S, S, float(self.tan_half_fov), float(self.tan_half_fov), float(scale_modifier),
-                             clamp_image=True)
+                             clamp_image=True, want_depth=bool(return_depth))
         image, alpha, depth, _radii = ops.render_views(g, vm, pm, self._view_scene(B, V), bg, cfg, max_views_per_call)
-        return {
+        out = {
             "image": image.view(B, V, 3, S, S),   # [B, V, 3, H, W]
             "alpha": alpha.view(B, V, 1, S, S),   # [B, V, 1, H, W]
-            "depth": depth.view(B, V, 1, S, S),   # [B, V, 1, H, W]  (superset of the reference's dict)
         }
+        # a superset of the reference's dict (which computes the depth and drops it, core/gs.py:76); return_depth=False
+        # gives exactly the reference's keys and skips the depth image in the kernels
+        if return_depth:
+            out["depth"] = depth.view(B, V, 1, S, S)
+        return out
 
     # on-disk format of the path's input (/root/reference/core/gs.py:101-190)
     def save_ply(self, gaussians, path, compatible=True):

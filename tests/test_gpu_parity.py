@@ -783,3 +783,24 @@ def test_lpips_input_matches_interpolate():
         (gg,) = torch.autograd.grad((y.reshape(ref.shape) * w).sum(), x)
         assert (y.reshape(ref.shape) - ref).abs().max().item() <= 2e-6
         assert (gg - gr).abs().max().item() <= 1e-5 * max(1.0, gr.abs().max().item())
+
+
+def test_render_without_depth_image():
+    """return_depth=False (the reference's dict: image and alpha; it computes the depth and drops it, core/gs.py:76): same
+    image / alpha / gradients, no depth key, the depth of the instances is neither fetched nor accumulated."""
+    from lgm_b200 import GaussianRenderer, default_options
+    r = GaussianRenderer(default_options(output_size=80), device=DEV)
+    g0 = make_gaussians(2, 5000, "trained", seed=51).to(DEV)
+    g0[:, :, 4:7] *= 4.0
+    cv, cvp, cp = [t.to(DEV) for t in make_cameras(2, 3, seed=51)]
+    w = torch.randn(2, 3, 3, 80, 80, generator=torch.Generator().manual_seed(2)).to(DEV)
+    res = []
+    for rd in (True, False):
+        g = g0.clone().requires_grad_(True)
+        out = r.render(g, cv, cvp, cp, return_depth=rd)
+        assert ("depth" in out) == rd
+        ((out["image"] * w).sum() + out["alpha"].sum()).backward()
+        res.append((out["image"].detach(), out["alpha"].detach(), g.grad))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    scale = res[0][2].abs().amax(dim=(0, 1), keepdim=True).clamp_min(1e-20)
+    assert ((res[0][2] - res[1][2]).abs() / scale).max().item() <= 2e-5
