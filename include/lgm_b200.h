@@ -12,7 +12,8 @@
  * Conventions
  *  - plain pointers and sizes; every pointer is DEVICE memory on the current device unless it says "host";
  *    fp32, contiguous.  The caller owns all memory; the library never allocates, frees or keeps pointers.
- *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises, with one
+ *    exception: lgm_forward_bin reads 4 bytes back (the longest tile) when it tries its direct path.
  *  - returns 0 on success, a negative lgm_status for an invalid argument, a positive cudaError_t for a CUDA
  *    failure; lgm_last_error_string() describes the last non-zero return of the calling thread.
  *    No C++ exception crosses the ABI.
@@ -67,7 +68,8 @@ const char* lgm_last_error_string(void);
 int lgm_tiles_per_view(int32_t image_height, int32_t image_width);
 /* Number of per-(view, 256-Gaussian block) partial sums forward_geom writes: n_views * ceil(P / 256). */
 int64_t lgm_num_block_sums(int32_t n_gaussians, int32_t n_views);
-/* Scratch bytes forward_bin needs for L instances (alternate key/value buffers, histograms, look-back state). */
+/* Scratch bytes forward_bin needs for L instances (alternate key/value buffers, histograms, look-back state; the
+ * direct path's pairs and per-tile counters alias / follow them). */
 int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes);
 
 /* K1 preprocess + instance-offset scan.  Replaces preprocessCUDA + InclusiveSum (+ its blocking D2H: here the
