@@ -134,7 +134,9 @@ int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const flo
  * K7 turns the moments into upstream's dL/dmean2D and dL/dconic with per-Gaussian coefficients (conic, opacity);
  * lgm_screen_gradients does the same into a separate array for callers that want upstream's values (means2D.grad).
  * dL_dgaussians [n_scenes, P, 14]: per-Gaussian gradients summed over the views of each scene; overwritten when
- * accumulate == 0, added to when accumulate != 0 (view chunks of one step).                                  */
+ * accumulate == 0, added to when accumulate != 0 (view chunks of one step).  It may point into peer-mapped memory
+ * of another GPU of the node: K7 then delivers a view-sharded rank's gradient block straight to the rank that owns
+ * the Gaussians (lgm_b200/dist.py, peer_gradients).                                                          */
 int lgm_backward(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
                  const float* proj_mats, const int32_t* view_scene, const int32_t* scene_view_offsets,
                  const int32_t* radii, const float* xy, const float* conic_opacity, const float* depth,
