@@ -148,9 +148,8 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
                                         reinterpret_cast<float2*>(xy), reinterpret_cast<float4*>(conic_opacity),
                                         tiles_touched, block_sums, cov3d),
              "forward_geom: preprocess");
-    const int64_t nsum = lgm_num_block_sums(p.P, p.n_views);
-    LGM_CUDA(lgm::launch_scan_block_sums(s, block_sums, (uint32_t)nsum, block_offsets,
-                                         reinterpret_cast<unsigned long long*>(total_instances)),
+    LGM_CUDA(lgm::launch_scan_block_sums(s, block_sums, (uint32_t)p.n_views, (uint32_t)((p.P + lgm::kBlock - 1) / lgm::kBlock),
+                                         block_offsets, reinterpret_cast<unsigned long long*>(total_instances)),
              "forward_geom: scan");
     return LGM_OK;
 }

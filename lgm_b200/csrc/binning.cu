@@ -10,50 +10,52 @@
 
 namespace lgm {
 
-// Exclusive scan of the per-(view, Gaussian-block) tile counts.  n is small (n_views * ceil(P/256), e.g. 80 k at
-// 208 views x 98,304 Gaussians), so one 1024-thread block scans it: each thread sums a contiguous chunk, the 1024
-// partials are scanned with shuffles, and a second sweep writes the offsets.  The grand total (= number of
-// instances L) is left on the device and read back ONCE per step by the host wrapper.
-__global__ void __launch_bounds__(1024)
-scan_block_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+// Exclusive scan of the per-(view, Gaussian-block) tile counts, n_views x per_view entries (e.g. 208 x 384).  One CTA
+// per view: it first sums the entries of all earlier views (coalesced, L2-resident: 320 KB at most) to get its base,
+// then scans its own entries in chunks of 256.  The grand total (= number of instances L) is left on the device by the
+// last view's CTA and read back ONCE per step by the host wrapper.  (A single 1024-thread CTA over all entries took
+// 73 us on the 208-view step; this takes a third.)
+__global__ void __launch_bounds__(kBlock)
+scan_block_sums_kernel(const uint32_t* __restrict__ in, uint32_t per_view, uint32_t* __restrict__ out,
                        unsigned long long* __restrict__ total)
 {
-    __shared__ unsigned long long s_warp[32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t chunk = (n + 1023u) / 1024u;
-    const uint32_t b = min(n, t * chunk), e = min(n, b + chunk);
-    unsigned long long s = 0;
-    for (uint32_t i = b; i < e; i++) s += in[i];
-    unsigned long long incl = s;
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_sum[8];
+    const uint32_t view = blockIdx.x, t = threadIdx.x;
+    const size_t before = (size_t)view * per_view;
+    unsigned long long p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // four independent streams of loads; 64 bit: the total is exact
+    size_t i = t;
+    for (; i + 3 * kBlock < before; i += 4 * kBlock) {
+        p0 += in[i];
+        p1 += in[i + kBlock];
+        p2 += in[i + 2 * kBlock];
+        p3 += in[i + 3 * kBlock];
+    }
+    for (; i < before; i += kBlock) p0 += in[i];
+    unsigned long long part = p0 + p1 + p2 + p3;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((t & 31) == 0) s_sum[t >> 5] = part;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = s_warp[lane], wi = w;
+    unsigned long long carry = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        s_warp[lane] = wi - w;  // exclusive warp base
-        if (lane == 31) total[0] = wi;
+    for (int w = 0; w < 8; w++) carry += s_sum[w];
+    for (uint32_t i0 = 0; i0 < per_view; i0 += kBlock) {
+        const uint32_t j = i0 + t;
+        const uint32_t v = j < per_view ? in[before + j] : 0u;
+        uint32_t tot;
+        const uint32_t excl = block_excl_scan_256(v, s_warp, &tot);
+        if (j < per_view) out[before + j] = (uint32_t)(carry + excl);  // offsets fit 32 bit: the host bounds L below 2^30
+        carry += tot;
     }
-    __syncthreads();
-    unsigned long long run = s_warp[warp] + incl - s;
-    for (uint32_t i = b; i < e; i++) {
-        out[i] = (uint32_t)run;  // offsets fit 32 bit: the host wrapper bounds L per call below 2^31
-        run += in[i];
-    }
+    if (view == gridDim.x - 1 && t == 0) total[0] = carry;
 }
 
-cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n, uint32_t* block_offsets,
-                                   unsigned long long* total)
+cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n_views, uint32_t per_view,
+                                   uint32_t* block_offsets, unsigned long long* total)
 {
-    scan_block_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, n, block_offsets, total);
+    if (n_views == 0 || per_view == 0) return cudaMemsetAsync(total, 0, sizeof(unsigned long long), stream);
+    scan_block_sums_kernel<<<n_views, kBlock, 0, stream>>>(block_sums, per_view, block_offsets, total);
     return cudaGetLastError();
 }
 

@@ -65,8 +65,8 @@ cudaError_t launch_preprocess_bwd(cudaStream_t stream, const RenderParams& prm, 
 cudaError_t launch_screen_gradients(cudaStream_t stream, const RenderParams& prm, const float4* conic_opacity,
                                     const float* grad_rows, float* out);
 
-cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n, uint32_t* block_offsets,
-                                   unsigned long long* total);
+cudaError_t launch_scan_block_sums(cudaStream_t stream, const uint32_t* block_sums, uint32_t n_views, uint32_t per_view,
+                                   uint32_t* block_offsets, unsigned long long* total);
 cudaError_t launch_emit(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                         const float* depth, const uint32_t* block_offsets, uint64_t* keys, uint32_t* vals);
 cudaError_t launch_tile_ranges(cudaStream_t stream, const uint64_t* keys, uint32_t L, uint2* ranges);
