@@ -36,4 +36,25 @@ void emul_preprocess_bwd(int P, const float* means, const float* scales, const f
                                   dscales + 3 * i, drots + 4 * i);
     }
 }
+// K7's per-Gaussian arithmetic as the kernel runs it: the gradient rows arrive in MOMENT form (Sx, Sy, Sxx, Sxy, Syy),
+// the per-view part accumulates dL/dpos and dL/dcov3D over n_views views (here: the same view n_views times), the map to
+// scale / rotation runs once.  moments [P,5], opac [P].
+void emul_preprocess_bwd_moments(int P, int n_views, const float* means, const float* scales, const float* rots,
+                                 const float* opac, float mod, const float* mv, const float* mp, int W, int H, float tanx,
+                                 float tany, const int32_t* radii, const float* moments, const float* gd, float* dmeans,
+                                 float* dscales, float* drots)
+{
+    const float fx = (float)W / (2.0f * tanx), fy = (float)H / (2.0f * tany);
+    for (int i = 0; i < P; i++) {
+        if (!(radii[i] > 0)) continue;
+        float cov6[6], M[9], g6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        lgm::cov3d_from_scale_rot(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], mod, rots[4 * i], rots[4 * i + 1],
+                                  rots[4 * i + 2], rots[4 * i + 3], cov6, M);
+        const float* m = moments + 5 * i;
+        for (int v = 0; v < n_views; v++)
+            lgm::preprocess_point_bwd_view(means + 3 * i, cov6, mv, mp, tanx, tany, fx, fy, m[0], m[1], m[2], m[3], m[4], gd[i],
+                                           dmeans + 3 * i, g6, true, (float)W, (float)H, opac[i]);
+        lgm::preprocess_point_bwd_finish(scales + 3 * i, rots + 4 * i, mod, g6, dscales + 3 * i, drots + 4 * i);
+    }
+}
 }

@@ -92,3 +92,39 @@ def test_preprocess_bwd_matches_oracle(oracle32, oracle64, emul):
     for a, b in ((dm, ref["dL_dmeans"]), (ds, ref["dL_dscales"]), (dr, ref["dL_drots"])):
         err = np.abs(a - b) / (np.abs(b) + 1e-3 * np.abs(b).mean() + 1e-20)
         assert np.quantile(err, 0.99) < 1e-3
+
+
+def test_moment_form_backward_matches_oracle(oracle32, oracle64, emul):
+    """The product's K7 arithmetic (moment-form rows, per-view part accumulated over the views, one map from dL/dcov3D
+    to scale / rotation) against the fp64 oracle fed with the equivalent upstream-form gradients
+    dL/dmean2D = -(W/2, H/2) o (Q S1), dL/dconic = -o S2 / 2  — two identical views, so the result must be twice the
+    oracle's single-view gradient."""
+    P, W, H = 4000, 160, 96
+    g = make_gaussians(1, P, "trained", seed=8)[0].numpy()
+    g[:, 4:7] *= 4
+    cv, cvp, _ = make_cameras(1, 1, seed=5)
+    means, opac, scales, rots, _ = split14(g)
+    t = tan_half(49.1)
+    tanx = t * W / H
+    view, proj = cv[0, 0].numpy().ravel().copy(), cvp[0, 0].numpy().ravel().copy()
+    pre = oracle32.preprocess(means, scales, rots, opac, view, proj, W, H, tanx, t)
+    rng = np.random.RandomState(2)
+    mom = (rng.randn(P, 5) * np.array([1.0, 1.0, 3.0, 3.0, 3.0])).astype(np.float32)
+    gd = rng.randn(P).astype(np.float32)
+    co = pre["conic_opacity"].astype(np.float64)
+    o = co[:, 3]
+    m = mom.astype(np.float64)
+    g2 = np.stack([-0.5 * W * o * (co[:, 0] * m[:, 0] + co[:, 1] * m[:, 1]),
+                   -0.5 * H * o * (co[:, 2] * m[:, 1] + co[:, 1] * m[:, 0])], 1)
+    gc = -0.5 * o[:, None] * m[:, 2:5]
+    ref = oracle64.preprocess_bwd(means, scales, rots, view, proj, W, H, tanx, t, pre["radii"], g2, gc, gd)
+    dm, ds, dr = np.zeros((P, 3), np.float32), np.zeros((P, 3), np.float32), np.zeros((P, 4), np.float32)
+    emul.emul_preprocess_bwd_moments(ctypes.c_int(P), ctypes.c_int(2), _p(means), _p(scales), _p(rots),
+                                     _p(np.ascontiguousarray(opac, np.float32)), ctypes.c_float(1.0), _p(view), _p(proj),
+                                     ctypes.c_int(W), ctypes.c_int(H), ctypes.c_float(tanx), ctypes.c_float(t),
+                                     _p(pre["radii"]), _p(mom), _p(gd), _p(dm), _p(ds), _p(dr))
+    vis = pre["radii"] > 0
+    assert vis.sum() > 1000
+    for a, b in ((dm, 2 * ref["dL_dmeans"]), (ds, 2 * ref["dL_dscales"]), (dr, 2 * ref["dL_drots"])):
+        err = np.abs(a - b)[vis] / (np.abs(b)[vis] + 1e-3 * np.abs(b)[vis].mean() + 1e-20)
+        assert np.quantile(err, 0.99) < 1e-3
