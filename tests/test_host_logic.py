@@ -134,3 +134,25 @@ def test_fused_activations_refuse_cpu_and_bad_shapes():
     from lgm_b200 import activate_gaussians
     with pytest.raises(LgmError, match="no CPU path"):
         activate_gaussians(torch.zeros(1, 4, 14))
+
+
+def test_tile_sort_bucket_map_properties():
+    """The monotone map of depth bits to buckets used by the per-tile sort (direct_bin.cu, tile_bucket_sort_kernel),
+    restated: mul = floor((2^32 - 1) / (((span + 1) >> lg) + 1)), bucket(x) = (x * mul) >> 32 for 0 <= x <= span, used when
+    span >= nb = 2^lg.  It must never reach nb and must be non-decreasing; it should also use most of the buckets."""
+    import random
+    rnd = random.Random(0)
+    for lg in (5, 8, 11, 12):
+        nb = 1 << lg
+        spans = [nb, nb + 1, 2 * nb - 1, 3 * nb + 7, (1 << 23), (1 << 23) + 12345, (1 << 31) - 2] + \
+                [rnd.randrange(nb, 1 << 31) for _ in range(200)]
+        for span in spans:
+            mul = 0xFFFFFFFF // (((span + 1) >> lg) + 1)
+            assert 0 < mul < (1 << 32)
+            top = (span * mul) >> 32
+            assert top < nb, (lg, span, top)
+            xs = sorted({0, 1, span // 3, span // 2, span - 1, span} | {rnd.randrange(0, span + 1) for _ in range(50)})
+            bs = [(x * mul) >> 32 for x in xs]
+            assert all(b0 <= b1 for b0, b1 in zip(bs, bs[1:]))
+            if span >= 64 * nb:
+                assert top >= nb - 1 - nb // 32, (lg, span, top)  # nearly all buckets are reachable
