@@ -249,3 +249,38 @@ def test_sh_backward_matches_finite_differences(oracle64, deg):
         b[idx] -= eps
         num = (loss(means, a) - loss(means, b)) / (2 * eps)
         assert abs(num - dsh[idx]) <= 1e-6 * max(1.0, abs(num))
+
+
+def test_order_claim_behind_direct_binning(oracle32):
+    """What the CUDA direct binning path relies on (direct_bin.cu): the stable sort of the emitted (tile | depth) keys
+    leaves, inside every tile, the instances in ascending (depth bits, value) order — so ANY sort of the unique pairs
+    (depth bits << 32 | value) per tile reproduces upstream's list, in whatever order a tile's instances were collected.
+    Checked on the oracle's own emit + sort, with every Gaussian duplicated (exact depth ties inside every tile)."""
+    rng = np.random.RandomState(3)
+    W, H, P = 112, 80, 1500
+    g = make_gaussians(1, P, "trained", seed=13)[0].numpy()
+    g[:, 4:7] *= 6.0
+    g = np.concatenate([g, g, g[: P // 2]], 0)  # duplicates: identical depth bits
+    cv, cvp, _ = make_cameras(1, 1, seed=13)
+    means, opac, scales, rots, _ = split14(g)
+    t = tan_half(49.1)
+    pre = oracle32.preprocess(means, scales, rots, opac, cv[0, 0].numpy(), cvp[0, 0].numpy(), W, H, t * W / H, t, 1.0)
+    b = oracle32.bin(pre, W, H)
+    assert b["L"] > 5000
+    tile = (b["unsorted_keys"] >> np.uint64(32)).astype(np.int64)
+    dbits = (b["unsorted_keys"] & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    val = b["unsorted_vals"].astype(np.uint64)
+    # collect per tile in a scrambled order (what the atomics of the scatter kernel do), then sort the unique pairs
+    perm = rng.permutation(b["L"])
+    tile, pair = tile[perm], (dbits[perm] << np.uint64(32)) | val[perm]
+    order = np.lexsort((pair, tile))
+    assert np.array_equal(b["keys"], (tile[order].astype(np.uint64) << np.uint64(32)) | (pair[order] >> np.uint64(32)))
+    assert np.array_equal(b["vals"], (pair[order] & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    k = b["keys"]
+    assert (k[1:] == k[:-1]).mean() > 0.3  # the ties are real
+    # and the ranges are the exclusive scan of the per-tile counts
+    counts = np.bincount(tile, minlength=len(b["ranges"]))
+    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    ne = counts > 0
+    assert np.array_equal(b["ranges"][ne, 0], start[ne]) and np.array_equal(b["ranges"][ne, 1], (start + counts)[ne])
+    assert (b["ranges"][~ne] == 0).all()
