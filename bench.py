@@ -464,11 +464,13 @@ def run_native(args):
             keep = os.environ.get("LGM_SORT_VARIANT")
             for vi in range(12):
                 os.environ["LGM_SORT_VARIANT"] = str(vi)
+                _lib.apply_env_tuning()
                 sort_variants[str(vi)] = time_sort()
             if keep is None:
                 del os.environ["LGM_SORT_VARIANT"]
             else:
                 os.environ["LGM_SORT_VARIANT"] = keep
+            _lib.apply_env_tuning()
         peak, peak_src = load_peaks()
         sort_bytes = (npass * 24 + 8) * Lr
         ach = sort_bytes / (t_sort * 1e-3) / 1e9

@@ -12,8 +12,10 @@
  * Conventions
  *  - plain pointers and sizes; every pointer is DEVICE memory on the current device unless it says "host";
  *    fp32, contiguous.  The caller owns all memory; the library never allocates, frees or keeps pointers.
- *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises, with one
- *    exception: lgm_forward_bin reads 4 bytes back (the longest tile) when it tries its direct path.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); NO entry point synchronises, copies to the
+ *    host or reads the environment.  The two data-dependent sizes of a step (instance count, longest tile) are left
+ *    in a device-side lgm_step_counts that the caller reads back ONCE per step (the reference: one blocking
+ *    cudaMemcpy per VIEW inside CudaRasterizer::Rasterizer::forward).
  *  - returns 0 on success, a negative lgm_status for an invalid argument, a positive cudaError_t for a CUDA
  *    failure; lgm_last_error_string() describes the last non-zero return of the calling thread.
  *    No C++ exception crosses the ABI.
@@ -59,17 +61,33 @@ typedef struct lgm_render_params {
 #define LGM_GRAD_ROW 12 /* floats per (view, Gaussian) gradient row (moment form, see lgm_backward): 5 moments,
                            opacity 1, rgb 3, depth 1, pad 2 */
 
-/* 2: moment-form gradient rows (lgm_backward_geom takes conic_opacity), want_sorted_keys, direct binning. */
-#define LGM_ABI_VERSION 2
+/* 2: moment-form gradient rows (lgm_backward_geom takes conic_opacity), want_sorted_keys, direct binning.
+ * 3: enqueue-only binning (lgm_forward_count, lgm_step_counts; lgm_forward_bin takes longest_tile / bin_mode),
+ *    lgm_set_tuning instead of environment variables, activations with the reference's normalisation axis. */
+#define LGM_ABI_VERSION 3
 int lgm_abi_version(void);
 const char* lgm_last_error_string(void);
+
+/* Tuning / test hooks (process-wide; the defaults are the measured optimum).  name: "fwd_batch" / "bwd_batch" (Gaussians
+ * staged per block barrier by the compositing kernels, multiple of 32), "patch_lanes" (32 | 16 | 8), "sort_variant"
+ * (launch shape of the onesweep sort), "enum_global" (1: binning enumeration without the per-CTA shared-memory stage).
+ * value < 0 restores the default. */
+int lgm_set_tuning(const char* name, int32_t value);
+
+/* The step's data-dependent sizes, DEVICE memory, 16 bytes: written by lgm_forward_geom (total_instances) and
+ * lgm_forward_count (longest_tile); the caller reads both back with one 16-byte copy. */
+typedef struct lgm_step_counts {
+    uint64_t total_instances; /* sum of tiles_touched over all (view, Gaussian) pairs of the call */
+    uint32_t longest_tile;    /* instances of the fullest tile */
+    uint32_t reserved;
+} lgm_step_counts;
 
 /* Number of 16x16 tiles of one view. */
 int lgm_tiles_per_view(int32_t image_height, int32_t image_width);
 /* Number of per-(view, 256-Gaussian block) partial sums forward_geom writes: n_views * ceil(P / 256). */
 int64_t lgm_num_block_sums(int32_t n_gaussians, int32_t n_views);
 /* Scratch bytes forward_bin needs for L instances (alternate key/value buffers, histograms, look-back state; the
- * direct path's pairs and per-tile counters alias / follow them). */
+ * direct path's pairs alias them). */
 int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes);
 
 /* K1 preprocess + instance-offset scan.  Replaces preprocessCUDA + InclusiveSum (+ its blocking D2H: here the
@@ -89,22 +107,37 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
                            float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
                            uint64_t* total_instances, const float* cov3d);
 
-/* K2 emit + K3 sort + K4 ranges.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
- * n_instances = the value forward_geom left in total_instances.  keys_sorted u64[L] (view*tiles+tile << 32 |
- * depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges uint2[n_views * tiles] = [start,end).
- * The list order is upstream's: by tile, then depth bits, ties in emit order (ascending value).  Three internal
- * paths produce it bit for bit (lgm_last_bin_mode tells which ran; environment LGM_BIN_MODE=direct|onesweep|hybrid
- * forces one):
- *   direct   (default when every tile fits the per-tile shared-memory sort: <= 20,480 instances) count -> scan ->
- *            scatter -> per-tile sort; costs one extra 4-byte device->host readback (the longest tile) in this call;
- *   onesweep a stable LSD onesweep radix sort over the (compressed) 64-bit keys (tiles beyond that);
- *   hybrid   onesweep over the (view|tile) bits, then a per-tile radix sort of the depth bits.
- * want_sorted_keys == 0 lets direct / hybrid skip writing keys_sorted (its contents are then unspecified);
- * vals_sorted and ranges, all the renderer consumes, are always final. */
+/* Binning, first half (direct path D1 + D2): per-tile instance counts and their scan.  After it `ranges`
+ * uint2[n_views * tiles] holds every tile's [start, end) in the final instance list (empty tiles (0,0)) and
+ * counts->longest_tile the fullest tile.  count_workspace (lgm_count_workspace_bytes; does not depend on the instance
+ * count) must be handed unchanged to lgm_forward_bin.  Enqueue before the step's readback. */
+int lgm_count_workspace_bytes(const lgm_render_params* prm, size_t* bytes);
+int lgm_forward_count(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy, uint32_t* ranges,
+                      void* count_workspace, size_t count_workspace_bytes, lgm_step_counts* counts);
+/* Longest tile the direct path can order in shared memory (20,480). */
+int lgm_direct_bin_tile_cap(void);
+
+/* Binning, second half.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
+ * n_instances, longest_tile = the values read back from lgm_step_counts (longest_tile < 0: unknown).
+ * keys_sorted u64[L] (view*tiles+tile << 32 | depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges
+ * uint2[n_views * tiles] = [start,end).  The list order is upstream's: by tile, then depth bits, ties in emit order
+ * (ascending value).  Three internal paths produce it bit for bit (lgm_last_bin_mode tells which ran):
+ *   direct   count -> scan (lgm_forward_count) -> scatter -> per-tile shared-memory sort.  Taken when bin_mode is
+ *            LGM_BIN_AUTO or LGM_BIN_DIRECT, count_workspace is the one lgm_forward_count filled, and
+ *            0 <= longest_tile <= lgm_direct_bin_tile_cap();
+ *   onesweep emit -> stable LSD onesweep radix sort over the (compressed) 64-bit keys -> ranges (everything else);
+ *   hybrid   (LGM_BIN_HYBRID) onesweep over the (view|tile) bits, then a per-tile radix sort of the depth bits.
+ * block_offsets is only read by the onesweep / hybrid paths.  want_sorted_keys == 0 lets direct / hybrid skip writing
+ * keys_sorted (its contents are then unspecified); vals_sorted and ranges, all the renderer consumes, are always final.
+ * Enqueue-only: nothing is read back. */
+#define LGM_BIN_AUTO 0
+#define LGM_BIN_ONESWEEP 1
+#define LGM_BIN_HYBRID 2
+#define LGM_BIN_DIRECT 3
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
-                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
-                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
-                    int32_t want_sorted_keys);
+                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, int64_t longest_tile,
+                    int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
+                    size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys);
 
 /* K5 compositing.  Replaces renderCUDA fwd.  image [n_views,3,H,W], alpha / depth_img [n_views,H,W], n_contrib u32
  * [n_views,H,W] (bits 0..28: number of list entries the pixel consumed, as upstream).
@@ -121,9 +154,10 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
 int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
-                           int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
-                           void* workspace, size_t workspace_bytes, const float* bg, int32_t clamp_image, float* image,
-                           float* alpha, float* depth_img, uint32_t* n_contrib);
+                           int64_t n_instances, int64_t longest_tile, int32_t bin_mode, uint64_t* keys_sorted,
+                           uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
+                           void* count_workspace, const float* bg, int32_t clamp_image, float* image, float* alpha,
+                           float* depth_img, uint32_t* n_contrib);
 
 /* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
  * dL_ddepth may be NULL (= zero gradient w.r.t. the depth image: LGM's losses never use depth; a cheaper kernel
@@ -166,20 +200,28 @@ int lgm_screen_gradients(void* stream, const lgm_render_params* prm, const float
                          float* screen_grads);
 
 /* markVisible: visible[i] = !(view-space z <= 0.2).  means [P,3], view_mat [16], visible u8[P]. */
-/* Which binning path the calling thread's last lgm_forward_bin took (diagnostics / launch accounting). */
+/* Which binning path the calling thread's last lgm_forward_bin took (LGM_BIN_ONESWEEP / _HYBRID / _DIRECT; LGM_BIN_NONE
+ * when there was nothing to bin): diagnostics / launch accounting. */
 #define LGM_BIN_NONE 0
-#define LGM_BIN_ONESWEEP 1
-#define LGM_BIN_HYBRID 2
-#define LGM_BIN_DIRECT 3
 int lgm_last_bin_mode(void);
 
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 
 /* The step right before the path: /root/reference/core/models.py:40-44,107-115 — raw splatter image
- * x [n_rows,14] -> Gaussians [n_rows,14]: pos = clamp(x[0:3],-1,1), opacity = sigmoid(x[3]), scale = 0.1 softplus(x[4:7]),
- * rotation = normalize(x[7:11]), rgb = 0.5 tanh(x[11:14]) + 0.5; and its backward (dL_dgaussians -> dL_dx). */
-int lgm_activate_forward(void* stream, int64_t n_rows, const float* x, float* gaussians);
-int lgm_activate_backward(void* stream, int64_t n_rows, const float* x, const float* dL_dgaussians, float* dL_dx);
+ * x [n_scenes, n_per_scene, 14] -> Gaussians of the same shape: pos = clamp(x[0:3],-1,1), opacity = sigmoid(x[3]),
+ * scale = 0.1 softplus(x[4:7]), rotation = F.normalize(x[7:11]), rgb = 0.5 tanh(x[11:14]) + 0.5; and its backward
+ * (dL_dgaussians -> dL_dx).
+ * rot_axis: the reference calls F.normalize WITHOUT a dim argument (models.py:43 `self.rot_act = F.normalize`, :112), so
+ * torch's default dim = 1 applies to the [B,N,4] slice: every quaternion COMPONENT is divided by its L2 norm over the N
+ * Gaussians of the scene (max(norm, 1e-12)) — LGM_ROT_NORM_REFERENCE, what reference checkpoints were trained under.
+ * LGM_ROT_NORM_QUATERNION normalises each quaternion to unit length (dim = -1) instead.
+ * col_scratch: n_scenes * 8 doubles of device scratch (column sums), needed for LGM_ROT_NORM_REFERENCE. */
+#define LGM_ROT_NORM_REFERENCE 0
+#define LGM_ROT_NORM_QUATERNION 1
+int lgm_activate_forward(void* stream, int64_t n_scenes, int64_t n_per_scene, const float* x, float* gaussians, int32_t rot_axis,
+                         double* col_scratch);
+int lgm_activate_backward(void* stream, int64_t n_scenes, int64_t n_per_scene, const float* x, const float* dL_dgaussians,
+                          float* dL_dx, int32_t rot_axis, double* col_scratch);
 
 /* The supervision right after the path: /root/reference/core/models.py:153,
  *   loss = mse_loss(pred_images, gt_images) + mse_loss(pred_alphas, gt_masks),

@@ -21,7 +21,7 @@ class LgmError(RuntimeError):
 
 
 _lib = None
-ABI_VERSION = 2  # include/lgm_b200.h LGM_ABI_VERSION
+ABI_VERSION = 3  # include/lgm_b200.h LGM_ABI_VERSION
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _pp = ctypes.POINTER(RenderParams)
 
@@ -34,17 +34,21 @@ _SIGNATURES = {
     "lgm_forward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 12),
     "lgm_forward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 13),
     "lgm_backward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32, _vp, _vp]),
-    "lgm_forward_bin": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _i32]),
+    "lgm_set_tuning": (ctypes.c_int, [ctypes.c_char_p, _i32]),
+    "lgm_count_workspace_bytes": (ctypes.c_int, [_pp, ctypes.POINTER(_sz)]),
+    "lgm_forward_count": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lgm_direct_bin_tile_cap": (ctypes.c_int, []),
+    "lgm_forward_bin": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _i32]),
     "lgm_forward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32] + [_vp] * 4),
-    "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _vp, _vp, _vp, _vp, _sz, _vp, _i32] + [_vp] * 4),
+    "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i32] + [_vp] * 4),
     "lgm_backward": (ctypes.c_int, [_vp, _pp] + [_vp] * 19 + [_i32]),
     "lgm_backward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
     "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32]),
     "lgm_screen_gradients": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp]),
     "lgm_last_bin_mode": (ctypes.c_int, []),
     "lgm_mark_visible": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
-    "lgm_activate_forward": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
-    "lgm_activate_backward": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "lgm_activate_forward": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _vp]),
+    "lgm_activate_backward": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp]),
     "lgm_mse_loss_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp]),
     "lgm_resize_bilinear_forward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float, ctypes.c_float]),
     "lgm_resize_bilinear_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, ctypes.c_float]),
@@ -75,6 +79,32 @@ def lib():
                            "rebuild with `python -m lgm_b200.build --force`")
         _lib = l
     return _lib
+
+
+# Tuning / test hooks of the library (lgm_set_tuning) and the environment variables that drive them from Python.  The
+# C library itself never reads the environment; apply_env_tuning() is called by ops at the head of every render.
+_TUNING_ENV = {"fwd_batch": "LGM_FWD_BATCH", "bwd_batch": "LGM_BWD_BATCH", "patch_lanes": "LGM_PATCH_LANES",
+               "sort_variant": "LGM_SORT_VARIANT", "enum_global": "LGM_ENUM_GLOBAL"}
+_tuning_applied = {}
+BIN_MODE_IDS = {"auto": 0, "onesweep": 1, "hybrid": 2, "direct": 3}
+
+
+def set_tuning(name, value):
+    check(lib().lgm_set_tuning(name.encode(), int(value)), f"lgm_set_tuning({name})")
+
+
+def apply_env_tuning():
+    """Forward LGM_* tuning variables to the library when they changed; returns the binning mode id (LGM_BIN_MODE)."""
+    env = os.environ
+    for name, var in _TUNING_ENV.items():
+        v = env.get(var)
+        if _tuning_applied.get(name) != v:
+            try:
+                set_tuning(name, -1 if v is None else int(v))
+            except ValueError:
+                set_tuning(name, -1)
+            _tuning_applied[name] = v
+    return BIN_MODE_IDS.get(env.get("LGM_BIN_MODE", "auto"), 0)
 
 
 def check(rc, what):

@@ -1,9 +1,10 @@
 // api.cu — the C-ABI of include/lgm_b200.h: argument validation, workspace carving, launch sequencing.
-// No device memory is allocated here and nothing synchronises; no exception leaves these functions.
+// No device memory is allocated here and NO entry point synchronises or copies to the host: every call only enqueues
+// work on the caller's stream (the step's single host readback — instance count + longest tile — is the caller's).
+// No exception leaves these functions.
 #include "../../include/lgm_b200.h"
 #include "common.cuh"
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -38,6 +39,8 @@ int make_params(const lgm_render_params* in, lgm::RenderParams& p)
     if (in->n_scenes < 0 || in->n_gaussians < 0 || in->n_views < 0 || in->image_height <= 0 || in->image_width <= 0)
         return fail(LGM_ERR_BAD_SHAPE, "negative size or empty image in lgm_render_params");
     if (!(in->tanfovx > 0.f) || !(in->tanfovy > 0.f)) return fail(LGM_ERR_BAD_VALUE, "tanfovx / tanfovy must be > 0");
+    // the per-(view, Gaussian) kernels put the view in gridDim.y
+    if (in->n_views > 65535) return fail(LGM_ERR_BAD_SHAPE, "n_views must be <= 65535 per call: split the views into chunks");
     if ((int64_t)in->n_views * in->n_gaussians >= (int64_t)1 << 32)
         return fail(LGM_ERR_BAD_SHAPE, "n_views * n_gaussians must be < 2^32 per call: split the views into chunks");
     p.n_scenes = in->n_scenes;
@@ -73,7 +76,7 @@ int key_end_bit(const lgm::RenderParams& p)
 }
 
 struct BinWorkspace {
-    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, direct_scratch, total;
+    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, total;
 };
 BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
 {
@@ -86,24 +89,50 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     off = align_up(off + w.sort_scratch_bytes, 256);
     w.tile_scratch = off;
     off = align_up(off + lgm::tile_sort_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
-    w.direct_scratch = off;
-    off = align_up(off + lgm::direct_bin_scratch_bytes(p), 256);
     w.total = off;
     return w;
 }
 
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
-// the direct path is tried when the MEAN tile holds at most this many instances (a longer mean makes a tile above
-// the shared-memory capacity near certain, and the count pass would be wasted)
-constexpr uint64_t kDirectMaxMeanTile = 12288;
+
+std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global"};
+std::atomic<int> g_sm_count[lgm::kMaxDevices];
 
 }  // namespace
+
+namespace lgm {
+int tuning(Tuning which) { return g_tuning[which].load(std::memory_order_relaxed); }
+int device_sm_count()
+{
+    const int dev = current_device();
+    int n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+}  // namespace lgm
 
 extern "C" {
 
 int lgm_abi_version(void) { return LGM_ABI_VERSION; }
 int lgm_last_bin_mode(void) { return g_last_bin_mode; }
 const char* lgm_last_error_string(void) { return g_err; }
+
+int lgm_set_tuning(const char* name, int32_t value)
+{
+    LGM_NOTNULL(name);
+    for (int i = 0; i < lgm::kTuneCount; i++)
+        if (strcmp(name, kTuningNames[i]) == 0) {
+            g_tuning[i].store(value, std::memory_order_relaxed);
+            return LGM_OK;
+        }
+    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global)");
+}
+
+int lgm_direct_bin_tile_cap(void) { return lgm::direct_bin_tile_cap(); }
 
 int lgm_tiles_per_view(int32_t H, int32_t W) { return ((W + 15) / 16) * ((H + 15) / 16); }
 int64_t lgm_num_block_sums(int32_t P, int32_t n_views) { return (int64_t)n_views * ((P + lgm::kBlock - 1) / lgm::kBlock); }
@@ -154,23 +183,65 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
     return LGM_OK;
 }
 
+int lgm_count_workspace_bytes(const lgm_render_params* prm, size_t* bytes)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    LGM_NOTNULL(bytes);
+    *bytes = lgm::direct_bin_scratch_bytes(p);
+    return LGM_OK;
+}
+
+int lgm_forward_count(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy, uint32_t* ranges,
+                      void* count_workspace, size_t count_workspace_bytes, lgm_step_counts* counts)
+{
+    lgm::RenderParams p;
+    if (int rc = make_params(prm, p)) return rc;
+    LGM_NOTNULL(counts);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.P == 0 || p.n_views == 0) {
+        LGM_CUDA(cudaMemsetAsync(&counts->longest_tile, 0, sizeof(uint32_t), s), "forward_count: memset");
+        return LGM_OK;
+    }
+    LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(ranges); LGM_NOTNULL(count_workspace);
+    if (count_workspace_bytes < lgm::direct_bin_scratch_bytes(p))
+        return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "forward_count: workspace too small (see lgm_count_workspace_bytes)");
+    LGM_CUDA(lgm::launch_direct_bin_count(s, p, radii, reinterpret_cast<const float2*>(xy), reinterpret_cast<uint2*>(ranges),
+                                          count_workspace, &counts->longest_tile),
+             "forward_count");
+    return LGM_OK;
+}
+
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
-                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, uint64_t* keys_sorted,
-                    uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
-                    int32_t want_sorted_keys)
+                    const float* depth, const uint32_t* block_offsets, int64_t n_instances, int64_t longest_tile,
+                    int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
+                    size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (n_instances < 0) return fail(LGM_ERR_BAD_SHAPE, "n_instances < 0");
     if (n_instances >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "n_instances >= 2^30: split the views into chunks");
+    if (bin_mode < LGM_BIN_AUTO || bin_mode > LGM_BIN_DIRECT) return fail(LGM_ERR_BAD_VALUE, "bin_mode must be LGM_BIN_AUTO .. LGM_BIN_DIRECT");
     const size_t n_ranges = (size_t)p.n_views * p.n_tiles;
-    if (n_ranges) {
-        LGM_NOTNULL(ranges);
+    if (n_ranges) LGM_NOTNULL(ranges);
+    g_last_bin_mode = LGM_BIN_NONE;
+    // The DIRECT path (direct_bin.cu: count, scan, scatter, per-tile shared-memory sort — no global radix sort, 20 B
+    // instead of 152 B of HBM traffic per instance) needs lgm_forward_count to have run (ranges[] are then already
+    // final) and every tile to fit its shared-memory sort; the caller read the longest tile back together with the
+    // instance count.  Otherwise (tiles beyond the capacity, no count, or a forced mode): the ONESWEEP path — emit, one
+    // stable LSD sort of the compressed 64-bit keys, ranges — or HYBRID: onesweep over the (view|tile) bits, then every
+    // tile's segment sorted on its 31 depth bits in shared memory (tile_sort.cu; measured slower on B200, kept as a
+    // tested alternative).
+    const bool direct = (bin_mode == LGM_BIN_AUTO || bin_mode == LGM_BIN_DIRECT) && count_workspace != nullptr &&
+                        longest_tile >= 0 && longest_tile <= (int64_t)lgm::direct_bin_tile_cap();
+    if (!direct && n_ranges)
         LGM_CUDA(cudaMemsetAsync(ranges, 0, n_ranges * sizeof(uint2), s), "forward_bin: memset ranges");
+    if (n_instances == 0 || p.P == 0 || p.n_views == 0) {
+        if (direct && n_ranges) LGM_CUDA(cudaMemsetAsync(ranges, 0, n_ranges * sizeof(uint2), s), "forward_bin: memset ranges");
+        return LGM_OK;
     }
-    if (n_instances == 0 || p.P == 0 || p.n_views == 0) return LGM_OK;
-    LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(depth); LGM_NOTNULL(block_offsets);
+    LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(depth);
     LGM_NOTNULL(keys_sorted); LGM_NOTNULL(vals_sorted); LGM_NOTNULL(workspace);
     const uint32_t L = (uint32_t)n_instances;
     const BinWorkspace w = bin_layout(p, L);
@@ -179,37 +250,16 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     uint64_t* keys_tmp = reinterpret_cast<uint64_t*>(ws + w.keys_tmp);
     uint32_t* vals_tmp = reinterpret_cast<uint32_t*>(ws + w.vals_tmp);
     const int end_bit = key_end_bit(p);
-    // Default: one-stage LSD onesweep over all sort bits.  LGM_BIN_MODE=hybrid selects the two-stage form — onesweep
-    // passes over the (view|tile) bits only, then every tile's segment sorted on its 31 depth bits in shared memory
-    // (tile_sort.cu): same stable order bit for bit and ~1.5x less HBM traffic, but measured SLOWER on B200 in all three
-    // regimes (208-view step: bin 5.05 vs 3.94 ms; init-like 64.2 vs 49.9 ms; 1M-Gaussian 1024^2 views 37.5 vs 30.3 ms):
-    // the stable ballot ranking costs ~250 instructions per element in the per-tile sort.  Kept as a tested alternative.
-    const char* mode = getenv("LGM_BIN_MODE");
-    const char m0 = mode ? mode[0] : 'a';
-    // Auto (default): the DIRECT path (direct_bin.cu: count, scan, scatter, per-tile shared-memory sort — no global
-    // radix sort, 20 B instead of 152 B of HBM traffic per instance) whenever every tile fits its shared-memory sort.
-    // That needs the longest tile: a second 4-byte readback, after the count pass.  Steps with heavy tiles (untrained
-    // Gaussians, 1024^2 views of 1M Gaussians) take the onesweep path below; LGM_BIN_MODE=onesweep|hybrid|direct forces.
-    g_last_bin_mode = LGM_BIN_NONE;
-    if (m0 == 'd' || (m0 == 'a' && (uint64_t)L <= kDirectMaxMeanTile * (uint64_t)n_ranges)) {
-        const uint32_t* longest_dev = nullptr;
-        LGM_CUDA(lgm::launch_direct_bin_count(s, p, radii, reinterpret_cast<const float2*>(xy), reinterpret_cast<uint2*>(ranges),
-                                              ws + w.direct_scratch, &longest_dev),
-                 "forward_bin: tile count");
-        uint32_t longest = 0;
-        LGM_CUDA(cudaMemcpyAsync(&longest, longest_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "forward_bin: longest tile");
-        LGM_CUDA(cudaStreamSynchronize(s), "forward_bin: longest tile sync");
-        if ((int)longest <= lgm::direct_bin_tile_cap()) {
-            LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
-                                                 reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
-                                                 want_sorted_keys ? keys_sorted : nullptr, ws + w.direct_scratch, longest),
-                     "forward_bin: direct sort");
-            g_last_bin_mode = LGM_BIN_DIRECT;
-            return LGM_OK;
-        }
-        LGM_CUDA(cudaMemsetAsync(ranges, 0, n_ranges * sizeof(uint2), s), "forward_bin: memset ranges");
+    if (direct) {
+        LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
+                                             reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
+                                             want_sorted_keys ? keys_sorted : nullptr, count_workspace, (uint32_t)longest_tile),
+                 "forward_bin: direct sort");
+        g_last_bin_mode = LGM_BIN_DIRECT;
+        return LGM_OK;
     }
-    const bool full = m0 != 'h';
+    LGM_NOTNULL(block_offsets);
+    const bool full = bin_mode != LGM_BIN_HYBRID;
     g_last_bin_mode = full ? LGM_BIN_ONESWEEP : LGM_BIN_HYBRID;
     const int begin_bit = full ? 0 : 31;
     const bool in_tmp = lgm::sort_input_is_tmp(begin_bit, end_bit);
@@ -249,12 +299,13 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
 int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
-                           int64_t n_instances, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
-                           void* workspace, size_t workspace_bytes, const float* bg, int32_t clamp_image, float* image,
-                           float* alpha, float* depth_img, uint32_t* n_contrib)
+                           int64_t n_instances, int64_t longest_tile, int32_t bin_mode, uint64_t* keys_sorted,
+                           uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
+                           void* count_workspace, const float* bg, int32_t clamp_image, float* image, float* alpha,
+                           float* depth_img, uint32_t* n_contrib)
 {
-    if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, keys_sorted, vals_sorted, ranges,
-                                 workspace, workspace_bytes, /*want_sorted_keys=*/1))
+    if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, longest_tile, bin_mode, keys_sorted,
+                                 vals_sorted, ranges, workspace, workspace_bytes, count_workspace, /*want_sorted_keys=*/1))
         return rc;
     return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg,
                                  clamp_image, image, alpha, depth_img, n_contrib);
@@ -360,21 +411,34 @@ int lgm_mse_loss_grad(void* stream, const float* image, const float* gt_image, f
     return LGM_OK;
 }
 
-int lgm_activate_forward(void* stream, int64_t n_rows, const float* x, float* gaussians)
+static int activate_shape_ok(int64_t n_scenes, int64_t n_per_scene, int32_t rot_axis, const double* col_scratch)
 {
-    if (n_rows < 0) return fail(LGM_ERR_BAD_SHAPE, "n_rows < 0");
-    if (n_rows == 0) return LGM_OK;
-    LGM_NOTNULL(x); LGM_NOTNULL(gaussians);
-    LGM_CUDA(lgm::launch_activate_fwd((cudaStream_t)stream, (size_t)n_rows, x, gaussians), "activate_forward");
+    if (n_scenes < 0 || n_per_scene < 0 || n_scenes > 65535) return fail(LGM_ERR_BAD_SHAPE, "activate: n_scenes must be 0..65535, n_per_scene >= 0");
+    if (rot_axis != LGM_ROT_NORM_REFERENCE && rot_axis != LGM_ROT_NORM_QUATERNION) return fail(LGM_ERR_BAD_VALUE, "activate: rot_axis");
+    if (rot_axis == LGM_ROT_NORM_REFERENCE && n_scenes * n_per_scene > 0 && col_scratch == nullptr)
+        return fail(LGM_ERR_NULL_POINTER, "activate: col_scratch [n_scenes * 8 doubles] is needed for LGM_ROT_NORM_REFERENCE");
     return LGM_OK;
 }
 
-int lgm_activate_backward(void* stream, int64_t n_rows, const float* x, const float* dL_dgaussians, float* dL_dx)
+int lgm_activate_forward(void* stream, int64_t n_scenes, int64_t n_per_scene, const float* x, float* gaussians, int32_t rot_axis,
+                         double* col_scratch)
 {
-    if (n_rows < 0) return fail(LGM_ERR_BAD_SHAPE, "n_rows < 0");
-    if (n_rows == 0) return LGM_OK;
+    if (int rc = activate_shape_ok(n_scenes, n_per_scene, rot_axis, col_scratch)) return rc;
+    if (n_scenes * n_per_scene == 0) return LGM_OK;
+    LGM_NOTNULL(x); LGM_NOTNULL(gaussians);
+    LGM_CUDA(lgm::launch_activate_fwd((cudaStream_t)stream, (size_t)n_scenes, (size_t)n_per_scene, x, gaussians,
+                                      rot_axis == LGM_ROT_NORM_REFERENCE ? col_scratch : nullptr), "activate_forward");
+    return LGM_OK;
+}
+
+int lgm_activate_backward(void* stream, int64_t n_scenes, int64_t n_per_scene, const float* x, const float* dL_dgaussians,
+                          float* dL_dx, int32_t rot_axis, double* col_scratch)
+{
+    if (int rc = activate_shape_ok(n_scenes, n_per_scene, rot_axis, col_scratch)) return rc;
+    if (n_scenes * n_per_scene == 0) return LGM_OK;
     LGM_NOTNULL(x); LGM_NOTNULL(dL_dgaussians); LGM_NOTNULL(dL_dx);
-    LGM_CUDA(lgm::launch_activate_bwd((cudaStream_t)stream, (size_t)n_rows, x, dL_dgaussians, dL_dx), "activate_backward");
+    LGM_CUDA(lgm::launch_activate_bwd((cudaStream_t)stream, (size_t)n_scenes, (size_t)n_per_scene, x, dL_dgaussians, dL_dx,
+                                      rot_axis == LGM_ROT_NORM_REFERENCE ? col_scratch : nullptr), "activate_backward");
     return LGM_OK;
 }
 

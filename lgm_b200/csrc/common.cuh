@@ -3,7 +3,36 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace lgm {
+
+// ---- per-device host-side state.  A process may drive several GPUs (one thread or stream per device): function
+// attributes and SM counts are properties of the CURRENT device, so every cache below is keyed by cudaGetDevice(). ----
+constexpr int kMaxDevices = 64;
+inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+// SM count of the current device (cached per device; api.cu)
+int device_sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (kernel, device).  `done` is one mask per kernel
+// (a function-local static at the call site); setting the attribute twice from racing threads is harmless.
+template <typename Kernel>
+inline cudaError_t opt_in_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<uint64_t>& done)
+{
+    const uint64_t bit = 1ull << current_device();
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// ---- tuning / test hooks (lgm_set_tuning in include/lgm_b200.h; process-wide, read at launch time; api.cu) ----
+enum Tuning { kTuneFwdBatch = 0, kTunePatchLanes, kTuneBwdBatch, kTuneSortVariant, kTuneEnumGlobal, kTuneCount };
+int tuning(Tuning which);  // < 0: not set, the kernel's built-in default applies
 
 struct RenderParams {
     int n_scenes;   // B
@@ -32,7 +61,7 @@ cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, 
 int direct_bin_tile_cap();
 size_t direct_bin_scratch_bytes(const RenderParams& prm);
 cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
-                                    uint2* ranges, void* scratch, const uint32_t** longest_tile_dev);
+                                    uint2* ranges, void* scratch, uint32_t* longest_out);
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
                                    uint64_t* keys_sorted, void* scratch, uint32_t longest_tile);
@@ -41,8 +70,9 @@ cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const 
                                  float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,
                                  float w_alpha, double* loss, const float* grad_scale);
 // activations.cu: raw splatter image [.,14] -> Gaussians (core/models.py:40-44,107-115), forward and backward
-cudaError_t launch_activate_fwd(cudaStream_t stream, size_t n_rows, const float* x, float* g);
-cudaError_t launch_activate_bwd(cudaStream_t stream, size_t n_rows, const float* x, const float* dg, float* dx);
+cudaError_t launch_activate_fwd(cudaStream_t stream, size_t n_scenes, size_t n_per_scene, const float* x, float* g, double* cols);
+cudaError_t launch_activate_bwd(cudaStream_t stream, size_t n_scenes, size_t n_per_scene, const float* x, const float* dg,
+                                float* dx, double* cols);
 // resize.cu: y = mul * bilinear_resize(x) + add (F.interpolate, align_corners = False) and its backward
 cudaError_t launch_resize_bilinear_fwd(cudaStream_t stream, const float* x, float* y, int n_planes, int h_in, int w_in, int h_out,
                                        int w_out, float mul, float add);

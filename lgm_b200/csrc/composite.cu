@@ -20,7 +20,6 @@
 // Not HBM-bound: FP32 issue + MUFU.EX2 + shared-memory broadcast reads (and shuffles / L2 reductions in the backward).
 #include "common.cuh"
 #include "splat_math.cuh"
-#include <stdlib.h>
 
 namespace lgm {
 namespace {
@@ -450,26 +449,18 @@ composite_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians
 }
 
 constexpr int kMaxBatch = 2048;
-// tuning hook: staged Gaussians per barrier (multiple of 32, 32..2048)
-int batch_from_env(const char* name, int dflt)
+// tuning hook (lgm_set_tuning "fwd_batch" / "bwd_batch"): staged Gaussians per barrier (multiple of 32, 32..2048)
+int batch_or_default(Tuning which, int dflt)
 {
-    const char* e = getenv(name);
-    if (e) {
-        const int v = atoi(e);
-        if (v >= 32 && v <= kMaxBatch && v % 32 == 0) return v;
-    }
-    return dflt;
+    const int v = tuning(which);
+    return (v >= 32 && v <= kMaxBatch && v % 32 == 0) ? v : dflt;
 }
 
-// patch size (lanes per patch): LGM_PATCH_LANES = 32 | 16 | 8
-int patch_lanes_from_env()
+// patch size (lanes per patch; lgm_set_tuning "patch_lanes"): 32 | 16 | 8
+int patch_lanes()
 {
-    const char* e = getenv("LGM_PATCH_LANES");
-    if (e) {
-        const int v = atoi(e);
-        if (v == 32 || v == 16 || v == 8) return v;
-    }
-    return kPatchLanes;
+    const int v = tuning(kTunePatchLanes);
+    return (v == 32 || v == 16 || v == 8) ? v : kPatchLanes;
 }
 
 template <int LANES, bool DEPTH>
@@ -478,13 +469,8 @@ cudaError_t run_fwd(cudaStream_t stream, unsigned blocks, int smem, const Render
                     const uint32_t* vals, const uint2* ranges, const float* bg, int clamp_image, int batch, float* image,
                     float* alpha, float* depth_img, uint32_t* n_contrib)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_fwd_kernel<LANES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxBatch * (int)sizeof(Staged));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> opted{0};
+    if (cudaError_t e = opt_in_dynamic_smem(composite_fwd_kernel<LANES, DEPTH>, kMaxBatch * sizeof(Staged), opted)) return e;
     composite_fwd_kernel<LANES, DEPTH><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges,
                                                                   bg, clamp_image, batch, image, alpha, depth_img, n_contrib);
     return cudaGetLastError();
@@ -496,13 +482,8 @@ cudaError_t run_bwd(cudaStream_t stream, unsigned blocks, int smem, const Render
                     const uint32_t* vals, const uint2* ranges, const float* bg, const float* alpha, const uint32_t* n_contrib,
                     const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth, float* grad_rows, int batch)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(composite_bwd_kernel<LANES, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kMaxBatch * (int)sizeof(Staged));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> opted{0};
+    if (cudaError_t e = opt_in_dynamic_smem(composite_bwd_kernel<LANES, DEPTH>, kMaxBatch * sizeof(Staged), opted)) return e;
     composite_bwd_kernel<LANES, DEPTH><<<blocks, kBlock, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
                                                                          ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
                                                                          dL_ddepth, grad_rows, batch);
@@ -518,11 +499,11 @@ cudaError_t launch_composite_fwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int batch = batch_from_env("LGM_FWD_BATCH", kFwdBatch);
+    const int batch = batch_or_default(kTuneFwdBatch, kFwdBatch);
     const int smem = batch * (int)sizeof(Staged);
 #define LGM_FWD(L, D) run_fwd<L, D>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, \
                                     ranges, bg, clamp_image, batch, image, alpha, depth_img, n_contrib)
-    const int lanes = patch_lanes_from_env();
+    const int lanes = patch_lanes();
     if (depth_img) {
         switch (lanes) {
             case 32: return LGM_FWD(32, true);
@@ -546,11 +527,11 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int batch = batch_from_env("LGM_BWD_BATCH", kBwdBatch);
+    const int batch = batch_or_default(kTuneBwdBatch, kBwdBatch);
     const int smem = batch * (int)sizeof(Staged);
 #define LGM_BWD(L, D) run_bwd<L, D>(stream, (unsigned)blocks, smem, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, \
                                     ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth, grad_rows, batch)
-    const int lanes = patch_lanes_from_env();
+    const int lanes = patch_lanes();
     if (dL_ddepth) {
         switch (lanes) {
             case 32: return LGM_BWD(32, true);

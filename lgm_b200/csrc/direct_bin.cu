@@ -24,8 +24,6 @@
 // for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Two size classes (M: <= 5,632 instances,
 // 3 CTAs per SM; L: <= 20,480, one 1024-thread CTA per SM).  A longer tile cannot be staged in shared memory: the caller
 // (api.cu) reads the longest tile back and uses the onesweep path for such a step.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "splat_math.cuh"
 
@@ -166,8 +164,8 @@ tile_enumerate_global_kernel(const RenderParams prm, const int32_t* __restrict__
     }
 }
 
-// whether the per-CTA shared-memory stage is used (LGM_ENUM_GLOBAL: test hook for the large-view variant)
-bool enumerate_in_smem(const RenderParams& prm) { return prm.n_tiles <= kEnumMaxTiles && getenv("LGM_ENUM_GLOBAL") == nullptr; }
+// whether the per-CTA shared-memory stage is used (lgm_set_tuning "enum_global": test hook for the large-view variant)
+bool enumerate_in_smem(const RenderParams& prm) { return prm.n_tiles <= kEnumMaxTiles && tuning(kTuneEnumGlobal) <= 0; }
 uint32_t enum_ctas_per_view(const RenderParams& prm) { return (uint32_t)((prm.P + kBlock * kEnumItems - 1) / (kBlock * kEnumItems)); }
 
 template <bool SCATTER>
@@ -192,7 +190,8 @@ cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, 
 // ones from the back.  head[0] / head[3] = M / L list length, head[1] / head[4] = their work cursors, head[2] = longest.
 __global__ void __launch_bounds__(kBlock)
 tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ view_totals, int n_tiles,
-                        uint32_t n_ranges, uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head)
+                        uint32_t n_ranges, uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head,
+                        uint32_t* __restrict__ longest_out)
 {
     __shared__ uint32_t s_warp[8];
     const int view = blockIdx.x, t = threadIdx.x, lane = t & 31;
@@ -229,7 +228,10 @@ tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __r
         }
     }
     longest = __reduce_max_sync(0xffffffffu, longest);
-    if (lane == 0 && longest) atomicMax(&head[2], longest);
+    if (lane == 0 && longest) {
+        atomicMax(&head[2], longest);
+        if (longest_out) atomicMax(longest_out, longest);  // the caller's step counters (read back with the instance count)
+    }
 }
 
 // D4.  Persistent CTAs pull tiles from a work list: list[item * list_step] for item < *n_list_ptr, items handed out
@@ -369,18 +371,20 @@ static DirectScratch direct_scratch(const RenderParams& prm, void* scratch)
 
 size_t direct_bin_scratch_bytes(const RenderParams& prm) { return direct_scratch(prm, nullptr).total_bytes; }
 
-// D1 + D2: after this, *longest_tile_dev (device) holds the longest tile.  `scratch` as direct_bin_scratch_bytes.
+// D1 + D2: after this, ranges[] is final for the direct path and *longest_out (device, zeroed here) holds the longest
+// tile.  `scratch` as direct_bin_scratch_bytes; it must reach launch_direct_bin_sort untouched.
 cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
-                                    uint2* ranges, void* scratch, const uint32_t** longest_tile_dev)
+                                    uint2* ranges, void* scratch, uint32_t* longest_out)
 {
     const DirectScratch d = direct_scratch(prm, scratch);
     cudaError_t err = cudaMemsetAsync(scratch, 0, d.zero_bytes, stream);
     if (err != cudaSuccess) return err;
+    if (longest_out && (err = cudaMemsetAsync(longest_out, 0, sizeof(uint32_t), stream)) != cudaSuccess) return err;
     if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, d.counts, d.view_totals, nullptr, nullptr)) != cudaSuccess)
         return err;
     tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(d.counts, d.view_totals, prm.n_tiles,
-                                                                (uint32_t)prm.n_views * (uint32_t)prm.n_tiles, ranges, d.list, d.head);
-    *longest_tile_dev = d.head + 2;
+                                                                (uint32_t)prm.n_views * (uint32_t)prm.n_tiles, ranges, d.list, d.head,
+                                                                longest_out);
     return cudaGetLastError();
 }
 
@@ -395,15 +399,10 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
     auto* sort_m = tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3>;
     auto* sort_l = tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1>;
     constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_l = sort_smem(kSortCapL, kLgBucketsL);
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(sort_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static std::atomic<uint64_t> opted_m{0}, opted_l{0};
+    if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted_m)) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted_l)) return e;
+    const int n_sm = device_sm_count();
     cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, ranges,
                                                   static_cast<uint2*>(pairs));
     if (err != cudaSuccess) return err;

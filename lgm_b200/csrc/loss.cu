@@ -93,12 +93,7 @@ static cudaError_t launch_mse(cudaStream_t stream, const float* image, const GT*
         if (err != cudaSuccess) return err;
     }
     if (n_img + n_alpha == 0) return cudaSuccess;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int n_sm = device_sm_count();
     const size_t want = (n_img / 4 + n_alpha / 4 + kLossBlock - 1) / kLossBlock + 1;
     const unsigned grid = (unsigned)(want < (size_t)n_sm * 16 ? want : (size_t)n_sm * 16);
     mse_loss_grad_kernel<GT><<<grid, kLossBlock, 0, stream>>>(image, gt_image, d_image, n_img, w_img, alpha, gt_alpha, d_alpha,

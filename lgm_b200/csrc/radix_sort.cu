@@ -478,12 +478,8 @@ constexpr int kDefaultVariant = 4;
 
 int variant_index()
 {
-    const char* e = getenv("LGM_SORT_VARIANT");
-    if (e) {
-        const int v = atoi(e);
-        if (v >= 0 && v < kNumVariants) return v;
-    }
-    return kDefaultVariant;
+    const int v = tuning(kTuneSortVariant);  // lgm_set_tuning "sort_variant"
+    return (v >= 0 && v < kNumVariants) ? v : kDefaultVariant;
 }
 
 template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH>
@@ -493,12 +489,8 @@ cudaError_t launch_pass(cudaStream_t stream, uint32_t tiles, const uint64_t* kin
 {
     using Smem = OnesweepSmem<THREADS, ITEMS>;
     auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, MATCH>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> opted{0};
+    if (cudaError_t e = opt_in_dynamic_smem(kern, sizeof(Smem), opted)) return e;
     kern<<<tiles, THREADS, sizeof(Smem), stream>>>(kin, vin, kout, vout, n, shift, dmask, compress, hist, lookback, ticket);
     return cudaGetLastError();
 }
@@ -510,17 +502,16 @@ cudaError_t launch_pass_persistent(cudaStream_t stream, uint32_t tiles, const ui
 {
     using Smem = OnesweepSmem<THREADS, ITEMS>;
     auto kern = onesweep_persistent_kernel<THREADS, ITEMS, MIN_BLOCKS>;
-    static int resident = 0;
-    if (!resident) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        resident = sms * (per_sm > 0 ? per_sm : 1);  // one CTA per resident slot: a multiple of the SM count (148)
+    static std::atomic<uint64_t> opted{0};
+    static std::atomic<int> per_sm_cached{0};  // occupancy of this kernel: the same on every B200 of the box
+    if (cudaError_t e = opt_in_dynamic_smem(kern, sizeof(Smem), opted)) return e;
+    int per_sm = per_sm_cached.load(std::memory_order_relaxed);
+    if (!per_sm) {
+        if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, sizeof(Smem))) return e;
+        per_sm = per_sm > 0 ? per_sm : 1;
+        per_sm_cached.store(per_sm, std::memory_order_relaxed);
     }
+    const int resident = device_sm_count() * per_sm;  // one CTA per resident slot: a multiple of the SM count (148)
     const uint32_t grid = tiles < (uint32_t)resident ? tiles : (uint32_t)resident;
     kern<<<grid, THREADS, sizeof(Smem), stream>>>(kin, vin, kout, vout, n, tiles, shift, dmask, compress, hist, lookback, ticket);
     return cudaGetLastError();

@@ -208,16 +208,10 @@ cudaError_t launch_tile_depth_sort(cudaStream_t stream, uint64_t* keys, uint32_t
     if (n_ranges == 0) return cudaSuccess;
     constexpr size_t small_smem = (size_t)(kSmallThreads / 32) * kBins * 4 + (size_t)kSmallCap * 16;
     constexpr size_t large_smem = (size_t)(kLargeThreads / 32) * kBins * 4 + (size_t)kLargeCap * 16;
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(tile_sort_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static std::atomic<uint64_t> opted_s{0}, opted_l{0};
+    if (cudaError_t e = opt_in_dynamic_smem(tile_sort_short_kernel, small_smem, opted_s)) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(tile_sort_long_kernel, large_smem, opted_l)) return e;
+    const int n_sm = device_sm_count();
     uint32_t* head = static_cast<uint32_t*>(scratch);
     cudaError_t err = cudaMemsetAsync(head, 0, 64 * sizeof(uint32_t), stream);
     if (err != cudaSuccess) return err;

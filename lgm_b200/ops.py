@@ -15,6 +15,7 @@ from . import _lib
 
 MAX_INSTANCES = (1 << 30) - 1       # look-back counters of the sort are 30 bit
 MAX_PAIRS_PER_CALL = 1 << 28        # (view, Gaussian) pairs per launch group: ~22 GB of state at 84 B / pair
+MAX_VIEWS_PER_CALL = 65535          # the per-(view, Gaussian) kernels put the view in gridDim.y
 
 # launch accounting for bench.py's "gpu_launches" (kernels this library enqueues; memsets not counted)
 launch_counter = {"kernels": 0}
@@ -100,6 +101,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     H, W = cfg.image_height, cfg.image_width
     prm = _lib.make_params(B, P, VW, H, W, cfg.tanfovx, cfg.tanfovy, cfg.scale_modifier)
     n_tiles = L.lgm_tiles_per_view(H, W)
+    bin_mode = _lib.apply_env_tuning()
     st = ForwardState()
     st.cfg, st.n_scenes, st.P, st.n_views = cfg, B, P, VW
     st.view_scene, st.scene_view_offsets = view_scene, scene_view_offsets
@@ -112,7 +114,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     nsum = int(L.lgm_num_block_sums(P, VW))
     block_sums = torch.empty(max(nsum, 1), dtype=torch.int32, device=dev)
     block_offsets = torch.empty(max(nsum, 1), dtype=torch.int32, device=dev)
-    total = torch.empty(1, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)  # lgm_step_counts: total instances | longest tile
     s = _stream()
     if cov3d is not None:
         _check_cuda_f32(cov3d, "cov3d", (6,))
@@ -121,18 +123,30 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     _timed("geom", lambda: _lib.check(L.lgm_forward_geom_cov3d(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(view_scene), _lib.ptr(st.depth),
         _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.tiles_touched), _lib.ptr(block_sums),
-        _lib.ptr(block_offsets), _lib.ptr(total), _lib.ptr(cov3d)), "lgm_forward_geom"))
+        _lib.ptr(block_offsets), _lib.ptr(counts), _lib.ptr(cov3d)), "lgm_forward_geom"))
     launch_counter["kernels"] += 2 if npair else 0
+    # first half of the binning (per-tile counts and their scan = the final ranges of the direct path): it does not
+    # need the instance count, so it runs before the step's readback and leaves the longest tile next to the count
+    st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
+    count_ws = None
+    if bin_mode in (0, 3) and npair:
+        nb = _lib._sz(0)
+        _lib.check(L.lgm_count_workspace_bytes(prm, nb), "lgm_count_workspace_bytes")
+        count_ws = torch.empty(int(nb.value), dtype=torch.uint8, device=dev)
+        _timed("bin_count", lambda: _lib.check(L.lgm_forward_count(
+            s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.ranges), _lib.ptr(count_ws), count_ws.numel(),
+            _lib.ptr(counts)), "lgm_forward_count"))
+        launch_counter["kernels"] += 2
     # work that does not depend on the instance count is queued before the host waits for it
     st.grad_rows = torch.zeros(max(npair, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev) if prepare_backward else None
     image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
     alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
     depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev) if cfg.want_depth else None
     st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
-    st.ranges = torch.empty(max(VW * n_tiles, 1), 2, dtype=torch.int32, device=dev)
-    # The host<->device synchronisation of the step (upstream: one per view): the instance count sizes the instance
-    # buffers.  (lgm_forward_bin adds a 4-byte readback of the longest tile when it takes the direct binning path.)
-    n_inst = int(total.item())
+    # THE host<->device synchronisation of the step (upstream: one per view): 16 bytes — the instance count sizes the
+    # instance buffers, the longest tile selects the binning path.  Nothing inside the library synchronises.
+    n_inst, longest = (int(v) for v in counts.tolist())
+    longest = (longest & 0xFFFFFFFF) if count_ws is not None else -1
     st.num_rendered = n_inst
     if n_inst > MAX_INSTANCES:
         raise TooManyInstances(n_inst)
@@ -143,9 +157,9 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     workspace = torch.empty(max(int(ws_bytes.value), 1), dtype=torch.uint8, device=dev)
     # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)
     _timed("bin", lambda: _lib.check(L.lgm_forward_bin(
-        s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, _lib.ptr(keys),
-        _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel(), 1 if cfg.keep_binning else 0),
-        "lgm_forward_bin"))
+        s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, longest, bin_mode,
+        _lib.ptr(keys), _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel(), _lib.ptr(count_ws),
+        1 if cfg.keep_binning else 0), "lgm_forward_bin"))
     _timed("composite_fwd", lambda: _lib.check(L.lgm_forward_composite(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_scene), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.depth),
         _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(bg), 1 if cfg.clamp_image else 0, _lib.ptr(image), _lib.ptr(alpha),
@@ -153,8 +167,8 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     if n_inst > 0:
         mode = int(L.lgm_last_bin_mode())
         last_bin_mode["mode"] = BIN_MODES.get(mode, "none")
-        if mode == 3:    # count, scan, ranges, scatter, tile sort
-            launch_counter["kernels"] += 5
+        if mode == 3:    # scatter, tile sort (one or two size classes); count + ranges scan were counted above
+            launch_counter["kernels"] += 3 if longest > 5632 else 2
         elif mode == 2:  # emit, histogram, tile-bit passes, ranges, short + long tile sort
             launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
         else:            # emit, histogram, ranges + onesweep passes
@@ -306,7 +320,7 @@ def render_views(gaussians, view_mats, proj_mats, view_scene_cpu, bg, cfg: ViewC
     chunk = VW if max_views_per_call is None else max_views_per_call
     if P > 0:
         chunk = min(chunk, max(1, MAX_PAIRS_PER_CALL // P))
-    chunk = max(chunk, 1)
+    chunk = max(min(chunk, MAX_VIEWS_PER_CALL), 1)
     outs, v0 = [], 0
     while v0 < VW or (VW == 0 and not outs):
         v1 = min(VW, v0 + chunk)

@@ -32,15 +32,25 @@ def test_exports_every_declared_symbol(lib):
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes signature table out of sync with the header"
 
 
+def lib_step_counts_bytes():
+    """sizeof(lgm_step_counts) as declared in the header: uint64 + 2 x uint32."""
+    src = open(os.path.join(ROOT, "include", "lgm_b200.h")).read()
+    body = re.search(r"typedef struct lgm_step_counts \{(.*?)\}", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    sizes = {"uint64_t": 8, "uint32_t": 4}
+    return sum(sizes[t] for t in re.findall(r"(uint64_t|uint32_t)\s+\w+;", body))
+
+
 def test_struct_layout_matches_header():
     from lgm_b200 import _lib
     assert ctypes.sizeof(_lib.RenderParams) == 8 * 4  # 5 int32 + 3 float
+    assert lib_step_counts_bytes() == 16
     assert _lib.GRAD_ROW == 12
 
 
 def test_size_queries_and_errors(lib):
     from lgm_b200 import _lib
-    assert lib.lgm_abi_version() == 2
+    assert lib.lgm_abi_version() == 3
     assert lib.lgm_tiles_per_view(320, 320) == 400 and lib.lgm_tiles_per_view(512, 512) == 1024
     assert lib.lgm_tiles_per_view(17, 33) == 2 * 3
     assert lib.lgm_num_block_sums(98304, 208) == 208 * 384 and lib.lgm_num_block_sums(257, 3) == 6
@@ -66,4 +76,15 @@ def test_size_queries_and_errors(lib):
     assert lib.lgm_sort_pairs(None, None, None, None, None, 5, 40, 0, None, 0) == -1
     assert lib.lgm_sort_pairs(None, None, None, None, None, 5, 64, 1, None, 0) == -5
     assert lib.lgm_forward_geom(None, ok, *([None] * 12)) == -1
+    # the enqueue-only binning interface: sizes, modes, tuning names
+    assert lib.lgm_count_workspace_bytes(ok, b) == 0 and b.value >= 2 * 4 * 208 * 400
+    assert lib.lgm_direct_bin_tile_cap() == 20480
+    assert lib.lgm_forward_count(None, ok, None, None, None, None, 0, None) == -1
+    assert lib.lgm_forward_bin(None, ok, None, None, None, None, 10, -1, 7, None, None, None, None, 0, None, 0) == -5  # bin_mode
+    too_many_views = _lib.make_params(1, 16, 65536, 32, 32, 0.5, 0.5, 1.0)
+    assert lib.lgm_bin_workspace_bytes(too_many_views, 10, b) == -2 and b"65535" in lib.lgm_last_error_string()
+    assert lib.lgm_set_tuning(b"fwd_batch", 256) == 0 and lib.lgm_set_tuning(b"fwd_batch", -1) == 0
+    assert lib.lgm_set_tuning(b"no_such_knob", 1) == -5
+    assert lib.lgm_activate_forward(None, 2, 100, None, None, 0, None) == -1   # reference axis needs its scratch
+    assert lib.lgm_activate_forward(None, 2, 100, None, None, 5, None) == -5   # rot_axis
     assert lib.lgm_backward_composite(None, ok, *([None] * 14)) == -1

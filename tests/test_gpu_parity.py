@@ -394,7 +394,9 @@ def test_full_size_properties(cfg):
 def test_onesweep_every_launch_shape(variant, monkeypatch):
     """Every tunable launch shape of the sort (LGM_SORT_VARIANT: one-tile-per-CTA and persistent pipelined forms,
     match.any and ballot ranking) sorts stably; n is not a multiple of any tile size and spans many tiles."""
+    from lgm_b200 import _lib
     monkeypatch.setenv("LGM_SORT_VARIANT", str(variant))
+    _lib.apply_env_tuning()  # the library never reads the environment itself
     for n, end_bit, dist in ((1_000_003, -48, "tiles"), (4097, 64, "uniform"), (250_000, 49, "equal")):
         test_onesweep_sort_pairs.__wrapped__(n, end_bit, dist) if hasattr(test_onesweep_sort_pairs, "__wrapped__") \
             else test_onesweep_sort_pairs(n, end_bit, dist)
@@ -663,32 +665,40 @@ def test_fused_mse_loss_matches_torch():
         assert abs(loss_w.item() - ref_w.item()) <= 1e-6 * abs(ref_w.item())
 
 
-def test_fused_activations_match_torch():
+@pytest.mark.parametrize("rot_axis", ["reference", "quaternion"])
+def test_fused_activations_match_torch(rot_axis):
     """lgm_b200.activate_gaussians = the five activations + cat of /root/reference/core/models.py:40-44,107-115, forward
-    and backward, including the clamp's edges, softplus' threshold and a zero quaternion."""
+    and backward, including the clamp's edges, softplus' threshold and a zero quaternion.  rot_axis="reference" is
+    `F.normalize(x[..., 7:11])` exactly as the reference calls it — no dim, so torch's default dim=1: every quaternion
+    component is normalised over the N Gaussians of the scene; "quaternion" is dim=-1."""
     import torch.nn.functional as F
     from lgm_b200 import activate_gaussians
     gen = torch.Generator().manual_seed(11)
     x = (3.0 * torch.randn(2, 5000, 14, generator=gen))
     x[0, 0, 0:3] = torch.tensor([-1.0, 1.0, 1.5])      # clamp edges (gradient passes at +-1) and outside
     x[0, 1, 4:7] = torch.tensor([19.5, 20.5, 40.0])    # softplus threshold
-    x[0, 2, 7:11] = 0.0                                # zero quaternion: normalize's eps clamp
+    x[0, 2, 7:11] = 0.0                                # zero quaternion: normalize's eps clamp (dim=-1)
     x[0, 3, 11:14] = torch.tensor([-12.0, 0.0, 12.0])  # saturated tanh
     w = torch.randn(2, 5000, 14, generator=gen)
+    rot_act = F.normalize if rot_axis == "reference" else (lambda t: F.normalize(t, dim=-1))   # models.py:43
 
     def ref(t):
         return torch.cat([t[..., 0:3].clamp(-1, 1), torch.sigmoid(t[..., 3:4]), 0.1 * F.softplus(t[..., 4:7]),
-                          F.normalize(t[..., 7:11], dim=-1), 0.5 * torch.tanh(t[..., 11:]) + 0.5], dim=-1)
+                          rot_act(t[..., 7:11]), 0.5 * torch.tanh(t[..., 11:]) + 0.5], dim=-1)
 
     xr = x.double().to(DEV).requires_grad_(True)
     yr = ref(xr)
     (gr,) = torch.autograd.grad((yr * w.double().to(DEV)).sum(), xr)
     xg = x.to(DEV).requires_grad_(True)
-    yg = activate_gaussians(xg)
+    yg = activate_gaussians(xg, rot_axis=rot_axis)
     (gg,) = torch.autograd.grad((yg * w.to(DEV)).sum(), xg)
     assert (yg.double() - yr).abs().max().item() <= 2e-6
+    if rot_axis == "reference":  # the two axes really differ: unit quaternions are NOT what the reference produces
+        assert (yg[..., 7:11].norm(dim=-1) - 1).abs().max().item() > 0.5
+        assert (yg[..., 7:11].norm(dim=1) - 1).abs().max().item() <= 1e-5
     keep = torch.ones_like(gr, dtype=torch.bool)
-    keep[0, 2, 7:11] = False  # at |q| = 0 torch's normalize backward is 0/0-free but eps-scaled; compare separately
+    if rot_axis == "quaternion":
+        keep[0, 2, 7:11] = False  # at |q| = 0 torch's normalize backward is 0/0-free but eps-scaled; compare separately
     assert ((gg.double() - gr).abs()[keep] / (1.0 + gr.abs()[keep])).max().item() <= 1e-5
     assert torch.isfinite(gg).all()
 
