@@ -15,8 +15,14 @@ the gradient (lgm_b200.dist, producer_only: NCCL scatter + gather; all-reduce / 
 
 Prints ONE JSON line (rank 0).  `value` = whole-job views/s with inputs resident in HBM; `e2e` = the same metric
 with, every step, the step's inputs (Gaussians, cameras, ground-truth images and masks) copied from pinned host
-memory and the loss read back; `roofline` = the HBM-bound group K1-K4 (preprocess + binning), SURVEY.md 8d's algorithmic
-bytes / CUDA-event time against MEASURED_PEAKS.json (the onesweep sort alone is reported beside it); `cpu_baseline` = the CPU oracle port on a bounded sample.
+memory — every rank copies what IT renders — and the loss read back; `roofline` = the HBM-bound group K1 + binning:
+the bytes the implemented algorithm must move / CUDA-event time against MEASURED_PEAKS.json (SURVEY.md 8d's figure,
+which counts a radix sort this path does not run, and the onesweep sort alone are reported beside it); `issue_roofline`
+= the compositing kernels against the warp-instruction issue ceiling that bounds them; `cpu_baseline` = the CPU oracle
+port on a bounded sample; `gpu_baseline` = the reference-shaped CUDA rasterizer (baseline/) driven per view as
+core/gs.py:42-93 drives the external package; `scale_sweep` = BASELINE.json configs[4] (ONE scene of 1 M Gaussians, 256
+views at 1024^2) STRONG-scaled over the N ranks as the north_star partitions it: Gaussians broadcast from rank 0, views
+rendered locally, gradients combined by one NCCL all-reduce.
 """
 import argparse
 import json
@@ -63,6 +69,11 @@ def parse():
     ap.add_argument("--sort-sweep", action="store_true", help="also time every onesweep launch shape (LGM_SORT_VARIANT)")
     ap.add_argument("--loop-baseline", action="store_true",
                     help="also time the reference's per-view driver loop (core/gs.py:42-93) on the same kernels")
+    ap.add_argument("--no-scale-sweep", action="store_true", help="skip the configs[4] strong-scaling leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-shaped CUDA baseline (baseline/)")
+    ap.add_argument("--sweep-views", type=int, default=256, help="views of the configs[4] leg (256 = BASELINE.json)")
+    ap.add_argument("--sweep-gaussians", type=int, default=1000000)
+    ap.add_argument("--sweep-chunk", type=int, default=32, help="views per launch group in the configs[4] leg (all N alike)")
     return ap.parse_args()
 
 
@@ -184,11 +195,27 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_counters():
+    """ncu-measured per-launch counters of the shipped build on the headline workload (profiles/*_counters.json: DRAM bytes
+    and executed warp instructions per kernel, from one `ncu --set full` capture; see profiles/*_summary.md)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_counters.json"):
+            best = os.path.join(pdir, f)
+    if best is None:
+        return None, None
+    try:
+        return json.load(open(best)), os.path.relpath(best, ROOT)
+    except Exception:
+        return None, None
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from lgm_b200 import default_options, ops, _lib
-    from lgm_b200.dist import ShardedGaussianRenderer
+    from lgm_b200 import GaussianRenderer, default_options, mse_image_alpha_loss, ops, _lib
+    from lgm_b200.dist import ShardedGaussianRenderer, partition_views
     from lgm_b200.synthetic import make_bg, make_cameras, make_gaussians
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,29 +234,32 @@ def run_native(args):
     B = Bg * world
     opt = default_options(output_size=S, fovy=fovy)
     renderer = ShardedGaussianRenderer(opt, device=dev, peer_gradients=not args.no_peer_gradients)
-    # host-side (pinned) copies of the step's inputs; device-resident copies for the HBM-resident `value`
-    g_host = make_gaussians(B, N, args.kind, seed=1234).pin_memory()
-    cv, cvp, cp = make_cameras(B, V, fovy=fovy, seed=1234)
-    cv_host, cvp_host, cp_host = cv.pin_memory(), cvp.pin_memory(), cp.pin_memory()
-    bg = make_bg().to(dev)
+    local_renderer = GaussianRenderer(opt, device=dev)
     n_views_total = B * V
-    per = (n_views_total + world - 1) // world
-    b0, b1 = min(n_views_total, rank * per), min(n_views_total, (rank + 1) * per)
+    b0, b1 = partition_views(n_views_total, world, rank)
     n_local = b1 - b0
+    # Device-resident inputs of the HBM-resident `value`: rank 0 produces the Gaussians of the whole step (the other
+    # ranks' copies are only shapes: the step scatters rank 0's); every rank holds the cameras.
+    g_dev = make_gaussians(B, N, args.kind, seed=1234).to(dev) if rank == 0 else torch.zeros(B, N, 14, device=dev)
+    cv, cvp, cp = make_cameras(B, V, fovy=fovy, seed=1234)
+    cv_dev, cvp_dev, cp_dev = cv.to(dev), cvp.to(dev), cp.to(dev)
+    bg = make_bg().to(dev)
+    # Host-side (pinned) inputs of `e2e`: what THIS rank renders — its own Bg scenes, their cameras and ground truth, as
+    # the reference's data-parallel loader hands every rank its own batch (/root/reference/main.py:82-102).
+    g_host = make_gaussians(Bg, N, args.kind, seed=1234 + rank * Bg).pin_memory()
+    sl = slice(rank * Bg, (rank + 1) * Bg)
+    cv_host, cvp_host, cp_host = cv[sl].contiguous().pin_memory(), cvp[sl].contiguous().pin_memory(), cp[sl].contiguous().pin_memory()
     gen = torch.Generator().manual_seed(4321 + rank)
-    gt_img_host = torch.rand(n_local, 3, S, S, generator=gen).pin_memory()     # ground-truth views of this rank's block
-    gt_mask_host = (torch.rand(n_local, 1, S, S, generator=gen) > 0.5).float().pin_memory()
-    g_dev = g_host.to(dev)
-    cv_dev, cvp_dev, cp_dev = cv_host.to(dev), cvp_host.to(dev), cp_host.to(dev)
+    gt_img_host = torch.rand(Bg, V, 3, S, S, generator=gen).pin_memory()
+    gt_mask_host = (torch.rand(Bg, V, 1, S, S, generator=gen) > 0.5).float().pin_memory()
     # upstream gradients of the loss shape 2 (x - gt) / numel (core/models.py:153), resident
     d_img = (2.0 * (torch.rand(n_local, 3, S, S, generator=gen) - torch.rand(n_local, 3, S, S, generator=gen)) / (n_views_total * 3 * S * S)).to(dev)
     d_alpha = (2.0 * (torch.rand(n_local, 1, S, S, generator=gen) - torch.rand(n_local, 1, S, S, generator=gen)) / (n_views_total * S * S)).to(dev)
     src = 0 if world > 1 else None
-    info = {}
 
     forward_only = args.forward_only or args.workload == "orbit"
     if forward_only:
-        args.no_e2e, args.no_stages, args.no_cpu_baseline = True, True, True
+        args.no_e2e, args.no_stages, args.no_cpu_baseline, args.no_scale_sweep, args.no_gpu_baseline = True, True, True, True, True
 
     def step_resident():
         if forward_only:
@@ -241,85 +271,65 @@ def run_native(args):
         return g.grad
 
     copy_stream = torch.cuda.Stream(device=dev)
-    mse_sum = torch.nn.functional.mse_loss
-    from lgm_b200 import mse_image_alpha_loss
+    w_i, w_a = 1.0 / (n_views_total * 3 * S * S), 1.0 / (n_views_total * S * S)   # the loss is normalised over the whole job
+    gt8 = {}
 
-    def step_e2e():
-        main = torch.cuda.current_stream()
-        # what the renderer needs first (Gaussians, cameras) goes on the compute stream; the ground truth, needed only
-        # by the loss, is copied by the copy engine on a side stream while the views are rendered
-        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
-        cvd, cvpd, cpd = cv_host.to(dev, non_blocking=True), cvp_host.to(dev, non_blocking=True), cp_host.to(dev, non_blocking=True)
-        copy_stream.wait_stream(main)
-        with torch.cuda.stream(copy_stream):
-            gt_i, gt_m = gt_img_host.to(dev, non_blocking=True), gt_mask_host.to(dev, non_blocking=True)
-        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
-        main.wait_stream(copy_stream)
-        gt_i.record_stream(main)
-        gt_m.record_stream(main)
-        # loss of /root/reference/core/models.py:153 (MSE image + MSE alpha), normalised over the whole job; the
-        # package's fused form (lgm_b200.mse_image_alpha_loss) unless --torch-loss
+    def host_set(u8):
+        if not u8:
+            return (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host)
+        if not gt8:  # the ground truth as an image file holds it: 8 bit
+            gt8["img"] = (gt_img_host * 255).round().to(torch.uint8).pin_memory()
+            gt8["mask"] = (gt_mask_host * 255).to(torch.uint8).pin_memory()
+        return (g_host, cv_host, cvp_host, cp_host, gt8["img"], gt8["mask"])
+
+    def render_loss_backward(gd, cvd, cvpd, cpd, gt_i, gt_m):
+        g = gd.requires_grad_(True)
+        out = local_renderer.render(g, cvd, cvpd, cpd, bg_color=bg, return_depth=False)
         if args.torch_loss:
-            loss = mse_sum(out["image"], gt_i, reduction="sum") / (n_views_total * 3 * S * S) + \
-                mse_sum(out["alpha"], gt_m, reduction="sum") / (n_views_total * S * S)
+            mse = torch.nn.functional.mse_loss
+            loss = mse(out["image"], gt_i, reduction="sum") * w_i + mse(out["alpha"], gt_m, reduction="sum") * w_a
         else:
-            loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
-                                        w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
+            loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i, gt_m, w_image=w_i, w_alpha=w_a)
         loss.backward()
         return float(loss.item())  # D2H read of the step's result
 
-    gt8 = {}
-
-    def step_e2e_u8():
-        """step_e2e with the ground truth kept as 8-bit images / masks on the host (what the image files hold) and read as
-        such by the loss kernel: a quarter of the PCIe bytes.  Reported beside `e2e`, not as `e2e` — the reference's
-        loader hands float32 tensors to the device."""
-        if not gt8:
-            gt8["img"] = (gt_img_host * 255).round().to(torch.uint8).pin_memory()
-            gt8["mask"] = (gt_mask_host * 255).to(torch.uint8).pin_memory()
+    def step_e2e_serial():
+        """Everything of ONE step in sequence: its copies start when the step starts (the ground truth on a side stream
+        while the same step's forward renders), nothing overlaps the previous step."""
         main = torch.cuda.current_stream()
-        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
-        cvd, cvpd, cpd = cv_host.to(dev, non_blocking=True), cvp_host.to(dev, non_blocking=True), cp_host.to(dev, non_blocking=True)
+        gd, cvd, cvpd, cpd = [x.to(dev, non_blocking=True) for x in (g_host, cv_host, cvp_host, cp_host)]
         copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
-            gt_i, gt_m = gt8["img"].to(dev, non_blocking=True), gt8["mask"].to(dev, non_blocking=True)
-        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
-        main.wait_stream(copy_stream)
+            gt_i, gt_m = gt_img_host.to(dev, non_blocking=True), gt_mask_host.to(dev, non_blocking=True)
+        main.wait_stream(copy_stream)  # (the loss needs it; the renderer's launches queued before this point do not wait)
         gt_i.record_stream(main)
         gt_m.record_stream(main)
-        loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
-                                    w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
-        loss.backward()
-        return float(loss.item())
+        return render_loss_backward(gd, cvd, cvpd, cpd, gt_i, gt_m)
 
-    def issue_copies():
+    def issue_copies(u8=False):
         """All inputs of one step, host -> device on the copy stream; returns the device tensors and an event."""
         with torch.cuda.stream(copy_stream):
-            t = [x.to(dev, non_blocking=True) for x in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host)]
+            t = [x.to(dev, non_blocking=True) for x in host_set(u8)]
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return t, ev
 
-    pending = {"next": None}
+    pending = {False: None, True: None}
 
-    def step_e2e_prefetch():
-        """The same step as step_e2e with the usual data-loader overlap: every step issues the copy of the NEXT step's
-        inputs and consumes the set copied while the previous step computed (reported beside `e2e`, not as `e2e`)."""
+    def step_e2e_pipelined(u8=False):
+        """The data-loader overlap: every step issues the host->device copy of the NEXT step's inputs (double
+        buffered, copy engine) and consumes the set copied while the previous step computed.  Every step still copies one
+        full input set from pinned host memory and reads its loss back inside the timed region."""
         main = torch.cuda.current_stream()
-        if pending["next"] is None:
-            pending["next"] = issue_copies()
-        (gd, cvd, cvpd, cpd, gt_i, gt_m), ev = pending["next"]
+        if pending[u8] is None:
+            pending[u8] = issue_copies(u8)
+        (gd, cvd, cvpd, cpd, gt_i, gt_m), ev = pending[u8]
         main.wait_event(ev)
         copy_stream.wait_stream(main)  # the next set's buffers may reuse memory the main stream has just released
-        pending["next"] = issue_copies()
+        pending[u8] = issue_copies(u8)
         for t in (gd, cvd, cvpd, cpd, gt_i, gt_m):
             t.record_stream(main)
-        g = gd.requires_grad_(True)
-        out = renderer.render(g, cvd, cvpd, cpd, bg_color=bg, broadcast_src=src, producer_only=True)
-        loss = mse_image_alpha_loss(out["image"], out["alpha"], gt_i.view_as(out["image"]), gt_m.view_as(out["alpha"]),
-                                    w_image=1.0 / (n_views_total * 3 * S * S), w_alpha=1.0 / (n_views_total * S * S))
-        loss.backward()
-        return float(loss.item())
+        return render_loss_backward(gd, cvd, cvpd, cpd, gt_i, gt_m)
 
     def step_copies_only():
         t, ev = issue_copies()
@@ -340,12 +350,13 @@ def run_native(args):
     flush_l2 = working_set < 4 * 126e6
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush_l2 else None
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, flush=None, reduce="max"):
+        flush = flush_l2 if flush is None else flush
         for _ in range(warmup):
             fn()
         barrier()
         k0 = ops.launch_counter["kernels"]
-        if flush_l2:
+        if flush:
             total = 0.0
             for _ in range(steps):
                 flush_buf.fill_(1)
@@ -366,9 +377,9 @@ def run_native(args):
             barrier()
             ms = e0.elapsed_time(e1) / steps
         launches = ops.launch_counter["kernels"] - k0
-        if world > 1:
+        if world > 1 and reduce is not None:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if reduce == "max" else dist.ReduceOp.MIN)
             ms = float(t.item())
         return ms, launches
 
@@ -381,26 +392,31 @@ def run_native(args):
 
     e2e = None
     if not args.no_e2e:
-        ms_e, _ = timed(step_e2e, max(3, args.steps), 3)
-        h2d = sum(t.numel() * t.element_size() for t in (g_host, cv_host, cvp_host, cp_host, gt_img_host, gt_mask_host))
-        ms_p, _ = timed(step_e2e_prefetch, max(3, args.steps), 3)
+        h2d = sum(t.numel() * t.element_size() for t in host_set(False))
+        h2d_8 = sum(t.numel() * t.element_size() for t in host_set(True))
+        k = max(3, args.steps)
+        ms_p, _ = timed(step_e2e_pipelined, k, 3)
+        ms_s, _ = timed(step_e2e_serial, k, 3)
         ms_c, _ = timed(step_copies_only, 5, 3)
-        ms_8, _ = timed(step_e2e_u8, max(3, args.steps), 3)
-        h2d_8 = h2d - 3 * (gt_img_host.numel() + gt_mask_host.numel())
-        e2e = {"value": n_views_total / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 8,
-               "what": "pinned-host Gaussians + cameras + ground-truth images/masks -> render -> MSE loss "
-                       f"({'torch autograd' if args.torch_loss else 'lgm_b200.mse_image_alpha_loss'}) -> backward -> loss.item(); "
-                       "the ground truth is copied on a side stream while the same step renders",
-               # context: the copies alone, and the step with the next step's inputs prefetched during this one
-               "h2d_alone_ms": ms_c, "h2d_alone_gbs": h2d / (ms_c * 1e-3) / 1e9,
+        ms_8, _ = timed(lambda: step_e2e_pipelined(True), k, 3)
+        pending[False] = pending[True] = None
+        e2e = {"value": n_views_total / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 16,
+               "what": "per rank and step: ITS scenes' Gaussians, cameras and float32 ground-truth images / masks copied from "
+                       "pinned host memory (copy engine, double buffered: the copy of step k+1's inputs is issued at the head of "
+                       f"step k) -> GaussianRenderer.render -> MSE loss ({'torch autograd' if args.torch_loss else 'lgm_b200.mse_image_alpha_loss'}) "
+                       "-> backward -> loss.item(); whole-job views / max-over-ranks step time",
+               "per_rank_h2d_gbs_in_step": h2d / (ms_p * 1e-3) / 1e9,
+               "serial": {"value": n_views_total / (ms_s * 1e-3), "ms_per_step": ms_s,
+                          "what": "the same step with its own copies issued at its head (ground truth on a side stream during "
+                                  "the forward): no overlap with the previous step — PCIe-bound"},
+               "h2d_alone_ms": ms_c, "h2d_alone_gbs_per_rank": h2d / (ms_c * 1e-3) / 1e9,
                "u8_ground_truth": {"value": n_views_total / (ms_8 * 1e-3), "ms_per_step": ms_8, "h2d_bytes_per_step": int(h2d_8),
-                                   "what": "the same step with the ground-truth images / masks kept 8-bit on the host and read as such by the loss kernel"},
-               "prefetched_inputs": {"value": n_views_total / (ms_p * 1e-3), "ms_per_step": ms_p,
-                                     "what": "each step issues the copy of the next step's inputs and consumes the set copied during the previous step"}}
+                                   "what": "pipelined, with the ground-truth images / masks kept 8-bit on the host (what the image "
+                                           "files hold) and read as such by the loss kernel"}}
 
-    # ---- stage breakdown + roofline of the HBM-bound group, measured live with CUDA events (rank 0) ----
-    stages, roofline, extra = None, None, {}
+    # ---- stage breakdown + rooflines, measured live with CUDA events (rank 0) ----
+    stages, roofline, issue_roofline, extra = None, None, None, {}
     # (N = 1 only: at N > 1 a step contains collectives, which rank 0 must not enter alone)
     if rank == 0 and world == 1 and not args.no_stages:
         ops.enable_stage_timing(True)
@@ -472,45 +488,55 @@ def run_native(args):
                 os.environ["LGM_SORT_VARIANT"] = keep
             _lib.apply_env_tuning()
         peak, peak_src = load_peaks()
+        counters, counters_src = load_counters()
+        counters = counters or {}
+        same_workload = counters.get("workload") == f"{args.workload}/{args.kind}"
         sort_bytes = (npass * 24 + 8) * Lr
         ach = sort_bytes / (t_sort * 1e-3) / 1e9
-        onesweep_sort = {"kernel": f"onesweep radix sort alone (histogram + {npass} passes, u64 key + u32 value)",
+        onesweep_sort = {"kernel": f"onesweep radix sort alone (histogram + {npass} passes, u64 key + u32 value) — not on the default path",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         # DRAM bytes from the ncu --set full capture (profiles/r01_summary.md): 23.6 B per pair per
-                         # pass and 8.0 B per pair for the histogram
-                         "traffic": int((npass * 23.6 + 8.0) * Lr), "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
+                         "traffic": int((npass * 23.6 + 8.0) * Lr), "traffic_source": "profiles/r01_summary.md: 23.6 B per pair per pass + 8.0 for the histogram (ncu dram bytes)",
+                         "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
                          "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
-        # roofline.achieved = (B_pre + B_emit + B_sort + B_rng) x n_views / t(K1..K4), with
-        # B_pre = 80 P, B_emit = 20 P + 12 L, B_sort = n_pass x 24 L + 8 L (n_pass = 6: an LSD sort of the 41..48-bit
-        # keys), B_rng = 8 L + 8 tiles.  t(K1..K4) = the geom + bin stages of the step (CUDA events around the C-ABI calls).
-        # The binning path the step actually took is named; the direct path (count / scatter / per-tile shared-memory
-        # sort) moves ~20 B per instance instead of the definition's 152, so `implemented_bytes` is given beside it.
+        # ---- roofline of the HBM-bound group: K1 preprocess + binning, as IMPLEMENTED ----
+        # bytes the implemented algorithm must move: K1 44 + 36 per (view, Gaussian); direct binning:
+        # count 12 and scatter 16 per (view, Gaussian) + 8 per instance written, per-tile sort 8 read + 4 written per
+        # instance, 20 per tile; onesweep path: emit 20 per pair + 12 per instance, sort (24 n_pass + 8) per instance,
+        # ranges 8 per instance + 8 per tile.
         P_ = N
         bin_mode = ops.last_bin_mode["mode"]
-        grp_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + (6 * 24 + 8) * Lr + 8 * Lr + 8 * n_local * n_tiles
         if bin_mode == "direct":
-            impl_bytes = n_local * (80 * P_ + 2 * 12 * P_ + 4 * P_) + 20 * Lr + 20 * n_local * n_tiles
-            # dram__bytes_read.sum + dram__bytes_write.sum of K1 + D1..D4 from the ncu --set full capture
-            # (profiles/r01_summary.md): 59.7 B per (view, Gaussian) pair (K1 31.4, count 12.3, scatter's geometry reads 16.0)
-            # and 21.7 B per instance (scatter 10.2, tile sort 11.6)
-            traffic = int(59.7 * n_local * P_ + 21.7 * Lr)
+            impl_bytes = n_local * (80 + 12 + 16) * P_ + 20 * Lr + 20 * n_local * n_tiles
         else:
-            impl_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
-            traffic = int(n_local * 100 * P_ + 12 * Lr + (npass * 23.6 + 8.0) * Lr + 8 * Lr)
-        t_grp = stages.get("geom", 0.0) + stages.get("bin", 0.0)
-        ach_grp = grp_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None
-        roofline = {"bound": "hbm", "kernel": f"K1-K4 group: preprocess + binning ({bin_mode} path)",
+            impl_bytes = n_local * (80 + 20) * P_ + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
+        t_grp = stages.get("geom", 0.0) + stages.get("bin_count", 0.0) + stages.get("bin", 0.0)
+        ach_grp = impl_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None
+        survey_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + (6 * 24 + 8) * Lr + 8 * Lr + 8 * n_local * n_tiles
+        grp_traffic = counters.get("hbm_group_dram_bytes") if same_workload else None
+        roofline = {"bound": "hbm", "kernel": f"K1 preprocess + binning ({bin_mode} path): the HBM-bound group of the step",
                     "achieved": ach_grp, "peak": peak, "unit": "GB/s", "frac": ach_grp / peak if ach_grp else None,
-                    "traffic": traffic, "traffic_source": "profiles/r01_summary.md (ncu --set full, dram bytes per launch)",
-                    "peak_source": peak_src, "algorithmic_bytes": int(grp_bytes), "implemented_bytes": int(impl_bytes),
-                    "achieved_implemented": impl_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None,
-                    "frac_implemented": impl_bytes / (t_grp * 1e-3) / 1e9 / peak if t_grp > 0 else None,
-                    "ms": t_grp, "definition": "SURVEY.md 8d: (80P+20P) per view + (12 + 6*24+8 + 8) per instance + 8 per tile",
-                    "note": ("SURVEY 8d's algorithmic bytes assume a 6-pass LSD radix sort of the instance list (152 B per instance); "
-                             "the direct path orders each tile in shared memory and moves ~20 B per instance, so frac can exceed 1 — "
-                             "implemented_bytes / traffic give the bytes this implementation needs / moves") if bin_mode == "direct" else None}
+                    "traffic": grp_traffic, "traffic_source": counters_src if grp_traffic else None,
+                    "peak_source": peak_src, "algorithmic_bytes": int(impl_bytes), "ms": t_grp,
+                    "definition": "bytes the implemented algorithm must move (108 B per (view, Gaussian) + 20 B per instance + 20 B "
+                                  "per tile on the direct path) / CUDA-event time of the geom + bin_count + bin stages",
+                    "survey_8d": {"algorithmic_bytes": int(survey_bytes), "frac": survey_bytes / (t_grp * 1e-3) / 1e9 / peak if t_grp > 0 else None,
+                                  "note": "SURVEY.md 8d's figure (100 B per (view, Gaussian) + 172 B per instance) counts a 6-pass LSD radix "
+                                          "sort of the instance list that the direct path does not execute; it is an avoided-traffic "
+                                          "ratio, not an achieved bandwidth"}}
         lens = (st.ranges[:, 1] - st.ranges[:, 0]).long()
         pair_evals = int(lens.sum()) * 256
+        # ---- what bounds compositing: warp-instruction issue (4 schedulers x 148 SMs x clock) ----
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_clock * 1e6 / 1e9  # G warp-instructions / s
+        ir = {}
+        for name, stage in (("composite_fwd", "composite_fwd"), ("composite_bwd", "composite_bwd")):
+            winst = (counters.get("warp_instructions") or {}).get(name) if same_workload else None
+            t = stages.get(stage)
+            if winst and t:
+                ir[name] = {"warp_instructions": winst, "ms": t, "achieved": winst / (t * 1e-3) / 1e9, "frac": winst / (t * 1e-3) / 1e9 / issue_peak}
+        issue_roofline = {"bound": "issue", "peak": issue_peak, "unit": "G warp-instr/s", "kernels": ir,
+                          "peak_source": f"148 SMs x 4 schedulers x {sm_clock:.0f} MHz (sampled under load)",
+                          "counters_source": counters_src if ir else None}
         extra = {
             "instances_per_step_rank0": Lr, "instances_per_view": Lr / max(n_local, 1), "sort_variants_ms": sort_variants,
             "bin_mode": bin_mode, "onesweep_sort": onesweep_sort,
@@ -519,7 +545,7 @@ def run_native(args):
                           "bwd_gpairs_per_s": pair_evals / (stages.get("composite_bwd", float("nan")) * 1e-3) / 1e9,
                           "max_tile_len": int(lens.max()), "mean_tile_len": float(lens.float().mean())},
         }
-        del st
+        del st, keys_u, vals_u, k_other, v_other
 
     # ---- the reference's DRIVER shape on the same kernels: core/gs.py:42-93's Python loop over B and V with one
     # GaussianRasterizer call (and one host readback) per view, clamp, stack, one autograd backward ----
@@ -554,9 +580,27 @@ def run_native(args):
                                           "rasterizer: Python loop over B x V, one GaussianRasterizer call and one host "
                                           "readback per view, clamp, torch.stack, one backward"}
 
+    # ---- GPU baseline: the reference-shaped CUDA rasterizer (baseline/, a restatement of the external package's
+    # algorithm: per-view launches, CUB scan + radix sort, 256-thread tiles, 10 atomics per pair) driven per view ----
+    gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            from baseline import ref_rasterizer
+            gpu_baseline = ref_rasterizer.bench_leg(g_dev, cv_dev, cvp_dev, cp_dev, bg, d_img, d_alpha, S, float(renderer.inner.tan_half_fov),
+                                                    value, UNIT)
+        except Exception as e:  # the baseline is test infrastructure: its absence must not take the bench down
+            gpu_baseline = {"unavailable": f"{type(e).__name__}: {e}"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _, _ = cpu_reference_run(args.workload, args.kind, 3, 0, budget_s=15.0)
+
+    exchange = getattr(renderer, "exchange", "?")
+    scale_sweep = None
+    if not args.no_scale_sweep:
+        g_dev = d_img = d_alpha = flush_buf = None  # free the headline workload's tensors
+        torch.cuda.empty_cache()
+        scale_sweep = run_scale_sweep(args, dev, rank, world, timed, barrier)
 
     if rank == 0:
         line = {
@@ -566,18 +610,118 @@ def run_native(args):
             "config": {"workload": f"{args.workload}: {cfgname}; per GPU {Bg} scenes x {V} views = {Bg * V} views/step, "
                                    f"{args.kind}-like Gaussians (SURVEY.md 8d), step = {B} scenes view-sharded over {world} GPU(s)",
                        "global_views": n_views_total, "gaussians_per_scene": N, "image": f"{S}x{S}",
-                       "parallelism": f"view-sharded x{world}" + (f", rank 0 produces the Gaussians and receives their gradient: {getattr(renderer, 'exchange', '?')}" if world > 1 else ""),
+                       "parallelism": f"view-sharded x{world}" + (f", rank 0 produces the Gaussians and receives their gradient: {exchange}" if world > 1 else ""),
                        "l2": (f"per-step working set {working_set / 1e6:.0f} MB + instances: L2 flushed (256 MB write) between the "
                               "timed steps, each step timed on its own") if flush_l2 else
                              (f"per-step working set ({working_set / 1e9:.1f} GB of geometry, gradient rows and images, plus the "
                               "instance lists) >> 126 MB L2; no explicit flush")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "stages_ms": stages,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "issue_roofline": issue_roofline,
+            "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "scale_sweep": scale_sweep, "stages_ms": stages,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_scale_sweep(args, dev, rank, world, timed, barrier):
+    """BASELINE.json configs[4] as the north_star partitions it: ONE scene of 1 M Gaussians, 256 views at
+    1024^2, STRONG-scaled — rank 0's Gaussians are broadcast, every rank renders its contiguous block of 256 / N views
+    with the local kernels, and the [1, 1M, 14] gradient (56 MB) is combined by one NCCL all-reduce inside autograd
+    (lgm_b200.dist._ReplicatedInput).  All N use the same launch groups (--sweep-chunk views), so that N = 1 runs the
+    same chunks one after the other.  At N > 1 every rank afterwards renders ALL the views alone (no collective): the
+    single-GPU time of the same job on the same box, for the efficiency."""
+    import torch
+    import torch.distributed as dist
+    from lgm_b200 import GaussianRenderer, default_options, ops
+    from lgm_b200.dist import ShardedGaussianRenderer, partition_views
+    from lgm_b200.synthetic import make_bg, make_cameras, make_gaussians
+    Vs, Ns, Ss, fovy, chunk = args.sweep_views, args.sweep_gaussians, 1024, 49.1, args.sweep_chunk
+    opt = default_options(output_size=Ss, fovy=fovy)
+    sharded = ShardedGaussianRenderer(opt, device=dev)
+    g0 = make_gaussians(1, Ns, args.kind, seed=4242).to(dev) if rank == 0 else torch.zeros(1, Ns, 14, device=dev)
+    cv, cvp, cp = [t.to(dev) for t in make_cameras(1, Vs, fovy=fovy, seed=4242)]
+    bg = make_bg().to(dev)
+    b0, b1 = partition_views(Vs, world, rank)
+    n_local = b1 - b0
+    gen = torch.Generator(device=dev).manual_seed(977 + rank)
+    d_img = (torch.rand(n_local, 3, Ss, Ss, device=dev, generator=gen) - 0.5) * (4.0 / (Vs * 3 * Ss * Ss))
+    d_alpha = (torch.rand(n_local, 1, Ss, Ss, device=dev, generator=gen) - 0.5) * (4.0 / (Vs * Ss * Ss))
+    src = 0 if world > 1 else None
+
+    def step():
+        g = g0.detach().requires_grad_(True)
+        out = sharded.render(g, cv, cvp, cp, bg_color=bg, broadcast_src=src, return_depth=False, max_views_per_call=chunk)
+        torch.autograd.backward([out["image"], out["alpha"]], [d_img, d_alpha])
+        return g.grad
+
+    steps = max(2, min(args.steps, 5))
+    ms, _ = timed(step, steps, 2, flush=False)
+    vps = Vs / (ms * 1e-3)
+    # stage times of rank 0's share (the library calls only; collectives are outside them)
+    ops.enable_stage_timing(True)
+    step()
+    ops.stage_times_ms()
+    step()
+    stages = {k: sum(v) for k, v in ops.stage_times_ms().items()}
+    ops.enable_stage_timing(False)
+    barrier()
+    res = {"config": f"configs[4]: 1 scene x {Ns} Gaussians, {Vs} views at {Ss}^2, {args.kind}-like, fwd+bwd, {chunk} views per launch group",
+           "scaling": "strong", "n_gpus": world, "views_per_rank": n_local, "value": vps, "unit": UNIT, "ms_per_step": ms,
+           "steps": steps, "exchange": sharded.exchange if world > 1 else "none (single rank)",
+           "bin_mode": ops.last_bin_mode["mode"], "stages_ms_rank0": stages,
+           "limiter": max(stages, key=stages.get) if stages else None}
+    if world > 1:
+        # the collectives alone, on the gradient's size
+        buf = torch.zeros(Ns * 14, device=dev)
+
+        def t_coll(fn, reps=10):
+            for _ in range(3):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        t_ar = t_coll(lambda: dist.all_reduce(buf))
+        t_bc = t_coll(lambda: dist.broadcast(buf, src=0))
+        nbytes = buf.numel() * 4
+        res.update({"allreduce_ms": t_ar, "allreduce_bytes": nbytes,
+                    "allreduce_bus_gbs": 2.0 * (world - 1) / world * nbytes / (t_ar * 1e-3) / 1e9,
+                    "allreduce_bus_gbs_reference": "725 GB/s measured for an 8-rank all-reduce at 1 GiB (B200_PROFILING.md)",
+                    "broadcast_ms": t_bc, "collectives_share_of_step": (t_ar + t_bc) / ms})
+        del buf
+        # single-GPU time of the whole job, on every rank at once (no collective), for the efficiency
+        del d_img, d_alpha
+        torch.cuda.empty_cache()
+        local = GaussianRenderer(opt, device=dev)
+        g_all = g0 if rank == 0 else make_gaussians(1, Ns, args.kind, seed=4242).to(dev)
+        d_img = (torch.rand(Vs, 3, Ss, Ss, device=dev, generator=gen) - 0.5) * (4.0 / (Vs * 3 * Ss * Ss))
+        d_alpha = (torch.rand(Vs, 1, Ss, Ss, device=dev, generator=gen) - 0.5) * (4.0 / (Vs * Ss * Ss))
+
+        def step_alone():
+            g = g_all.detach().requires_grad_(True)
+            out = local.render(g, cv, cvp, cp, bg_color=bg, return_depth=False, max_views_per_call=chunk)
+            torch.autograd.backward([out["image"].view(Vs, 3, Ss, Ss), out["alpha"].view(Vs, 1, Ss, Ss)], [d_img, d_alpha])
+            return g.grad
+
+        ms1_max, _ = timed(step_alone, 2, 1, flush=False, reduce="max")
+        ms1_min, _ = timed(step_alone, 1, 0, flush=False, reduce="min")
+        res.update({"single_gpu_ms_per_step": ms1_min, "single_gpu_ms_per_step_slowest_rank": ms1_max,
+                    "single_gpu_value": Vs / (ms1_min * 1e-3),
+                    "efficiency": vps / (world * (Vs / (ms1_min * 1e-3))),
+                    "efficiency_note": "views/s at N ranks / (N x views/s of ONE GPU rendering all the views with the same launch "
+                                       "groups, measured in this same run on every rank at once; the fastest rank's time is used, "
+                                       "the conservative choice)"})
+    else:
+        res.update({"efficiency": 1.0})
+    return res
 
 
 if __name__ == "__main__":

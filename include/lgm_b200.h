@@ -128,7 +128,8 @@ int lgm_direct_bin_tile_cap(void);
  *   onesweep emit -> stable LSD onesweep radix sort over the (compressed) 64-bit keys -> ranges (everything else);
  *   hybrid   (LGM_BIN_HYBRID) onesweep over the (view|tile) bits, then a per-tile radix sort of the depth bits.
  * block_offsets is only read by the onesweep / hybrid paths.  want_sorted_keys == 0 lets direct / hybrid skip writing
- * keys_sorted (its contents are then unspecified); vals_sorted and ranges, all the renderer consumes, are always final.
+ * keys_sorted (its contents are then unspecified; on the direct path it may then be NULL); vals_sorted and ranges, all
+ * the renderer consumes, are always final.
  * Enqueue-only: nothing is read back. */
 #define LGM_BIN_AUTO 0
 #define LGM_BIN_ONESWEEP 1

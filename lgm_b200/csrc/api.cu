@@ -242,7 +242,8 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
         return LGM_OK;
     }
     LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(depth);
-    LGM_NOTNULL(keys_sorted); LGM_NOTNULL(vals_sorted); LGM_NOTNULL(workspace);
+    LGM_NOTNULL(vals_sorted); LGM_NOTNULL(workspace);
+    if (!direct || want_sorted_keys) LGM_NOTNULL(keys_sorted);  // the direct path needs no key buffer of its own
     const uint32_t L = (uint32_t)n_instances;
     const BinWorkspace w = bin_layout(p, L);
     if (workspace_bytes < w.total) return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "forward_bin: workspace too small (see lgm_bin_workspace_bytes)");

@@ -162,7 +162,7 @@ class ShardedGaussianRenderer:
         self.peer_gradients = peer_gradients
 
     def render(self, gaussians, cam_view, cam_view_proj, cam_pos, bg_color=None, scale_modifier=1, broadcast_src=None,
-               producer_only=False, return_depth=True):
+               producer_only=False, return_depth=True, max_views_per_call=None):
         from . import ops
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -186,5 +186,6 @@ class ShardedGaussianRenderer:
         bg = (self.inner.bg_color if bg_color is None else bg_color).to(g.device).float().reshape(3).contiguous()
         cfg = ops.ViewConfig(S, S, float(self.inner.tan_half_fov), float(self.inner.tan_half_fov), float(scale_modifier),
                              clamp_image=True, want_depth=bool(return_depth))  # clamp: core/gs.py:87, fused
-        image, alpha, depth, _ = ops.render_views(g, vm.to(g.device), pm.to(g.device), scene, bg, cfg, grad_sink=sink)
+        image, alpha, depth, _ = ops.render_views(g, vm.to(g.device), pm.to(g.device), scene, bg, cfg,
+                                                  max_views_per_call=max_views_per_call, grad_sink=sink)
         return {"image": image, "alpha": alpha, "depth": depth, "views": (b, e)}

@@ -152,7 +152,9 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         raise TooManyInstances(n_inst)
     ws_bytes = _lib._sz(0)
     _lib.check(L.lgm_bin_workspace_bytes(prm, n_inst, ws_bytes), "lgm_bin_workspace_bytes")
-    keys = torch.empty(max(n_inst, 1), dtype=torch.int64, device=dev)
+    # the direct path (every tile fits its shared-memory sort) orders the instances without a key buffer
+    direct = count_ws is not None and 0 <= longest <= int(L.lgm_direct_bin_tile_cap())
+    keys = None if (direct and not cfg.keep_binning) else torch.empty(max(n_inst, 1), dtype=torch.int64, device=dev)
     st.vals = torch.empty(max(n_inst, 1), dtype=torch.int32, device=dev)
     workspace = torch.empty(max(int(ws_bytes.value), 1), dtype=torch.uint8, device=dev)
     # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)

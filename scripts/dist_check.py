@@ -4,7 +4,11 @@ GPU).  On rank 0 the gradient of a seeded loss w.r.t. the Gaussians must agree b
   (a) the single-GPU GaussianRenderer over all views,
   (b) ShardedGaussianRenderer with broadcast + all-gather,
   (c) producer_only (scatter + gather),
-  (d) producer_only with peer_gradients (K7 writes into rank 0's symmetric buffer, device barrier).
+  (d) producer_only with peer_gradients (K7 writes into rank 0's symmetric buffer, device barrier),
+and, for the north_star's partition proper — ONE scene whose views straddle the ranks (B = 1, V = 2 x world; also
+B = 3 with V chosen so that rank boundaries fall inside scenes): Gaussians broadcast from rank 0, views rendered locally,
+per-Gaussian gradients combined by the NCCL all-reduce (lgm_b200/dist.py, _ReplicatedInput.backward) — every rank must
+end with the single-GPU gradient.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dist_check.py
 """
@@ -56,9 +60,39 @@ def main():
             err = ((g - ref).abs() / scale).max().item()
             print(f"{name:28s} max error / column scale = {err:.2e}   ({peer.exchange if name.startswith('peer') else ''})")
             ok = ok and err <= 1e-4
-        print("DIST CHECK", "PASSED" if ok else "FAILED")
     else:
         assert res["scatter + gather"] is None and res["peer-memory"] is None  # only the producer gets the gradient
+
+    # ---- the all-reduce branch: scenes whose views straddle ranks ----
+    for (Bs, Vs, chunk) in ((1, 2 * world, None), (3, 2 * world + 1, None), (1, 4 * world, 2)):
+        gs = make_gaussians(Bs, N, "trained", seed=11)
+        gs[:, :, 4:7] *= 4.0
+        gs = gs.to(dev)
+        cvs, cvps, cps = [t.to(dev) for t in make_cameras(Bs, Vs, seed=11)]
+        ws = torch.randn(Bs * Vs, 3, S, S, generator=torch.Generator().manual_seed(5)).to(dev)
+        wa = torch.randn(Bs * Vs, 1, S, S, generator=torch.Generator().manual_seed(6)).to(dev)
+
+        def run_s(renderer, **kw):
+            # every rank but 0 starts from garbage: the broadcast must deliver rank 0's Gaussians
+            g = (gs if rank == 0 or not kw else torch.full_like(gs, float("nan"))).clone().requires_grad_(True)
+            out = renderer.render(g, cvs, cvps, cps, **kw)
+            b, e = out.get("views", (0, Bs * Vs))
+            ((out["image"].reshape(-1, 3, S, S) * ws[b:e]).sum() + (out["alpha"].reshape(-1, 1, S, S) * wa[b:e]).sum()).backward()
+            torch.cuda.synchronize()
+            return g.grad.clone()
+
+        ref_s = run_s(GaussianRenderer(opt, device=dev))   # every rank computes the single-GPU gradient itself
+        sh = ShardedGaussianRenderer(opt, device=dev)
+        got = run_s(sh, broadcast_src=0, max_views_per_call=chunk)
+        scale = ref_s.abs().amax(dim=(0, 1), keepdim=True).clamp_min(1e-20)
+        err = torch.tensor([((got - ref_s).abs() / scale).max().item()], device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"B={Bs} V={Vs} chunk={chunk}: {sh.exchange:12s} max error / column scale over all ranks = {err.item():.2e}")
+            assert sh.exchange == "all-reduce", sh.exchange
+        ok = ok and err.item() <= 1e-4
+    if rank == 0:
+        print("DIST CHECK", "PASSED" if ok else "FAILED")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

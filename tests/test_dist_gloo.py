@@ -60,6 +60,18 @@ def _worker(rank, world, port, q):
             ok = ok and torch.allclose(g3.grad, exp, rtol=1e-5, atol=1e-5)
         else:
             ok = ok and g3.grad is None  # only the producer receives the gradient
+        # ONE scene whose views straddle the ranks (the north_star's partition, BASELINE.json configs[4]): no whole-scene
+        # blocks exist, so the exchange must be the all-reduce; every rank ends with the gradient of ALL views
+        cams1 = torch.randn(1, 4, 4, 4)
+        g4 = (g_full[:1].clone() if rank == 0 else torch.full_like(g_full[:1], float("nan"))).requires_grad_(True)
+        assert scene_blocks(1, 4, world) is None
+        g4r = replicate_for_view_sharding(g4, None, 0, scene_blocks(1, 4, world))
+        vm1, _, _, scene1, (b1, e1) = shard_views(cams1, cams1, torch.zeros(1, 4, 3), rank, world)
+        assert (b1, e1) == (2 * rank, 2 * rank + 2) and int(scene1.max()) == 0
+        w1 = vm1.sum(-1)
+        sum((g4r[0] * w1[j]).sum() for j in range(e1 - b1)).backward()
+        exp1 = torch.zeros_like(g_full[:1]) + cams1.reshape(4, 16).sum()
+        ok = ok and torch.allclose(g4.grad, exp1, rtol=1e-5, atol=1e-5)
         q.put((rank, bool(ok), (b, e)))
     finally:
         dist.destroy_process_group()
