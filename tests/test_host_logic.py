@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: the drop-in API's argument checks, camera conventions, view partitioning."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -75,6 +76,31 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "liboracle" not in src and "splat_oracle" not in src, f
+                # nor the reference-shaped GPU baseline (baseline/: test / measurement infrastructure)
+                assert not re.search(r"^\s*(from|import)\s+baseline", src, re.M), f
+                assert "libref_rasterizer" not in src and "ref_rasterizer" not in src, f
+
+
+def test_reference_shaped_baseline_builds_and_exports():
+    """baseline/ref_rasterizer.cu cross-compiles for sm_100a without a GPU and exports its four entry points; the real
+    package is not importable offline (so parity stays unpinned) and the golden-from-reference hook says so and exits 0."""
+    import ctypes, subprocess, sys
+    from baseline import ref_rasterizer
+    so = ref_rasterizer.build()
+    l = ctypes.CDLL(so)
+    for name in ("ref_forward", "ref_backward", "ref_arena_offsets", "ref_last_error"):
+        assert hasattr(l, name), name
+    off = (ctypes.c_size_t * 6)()
+    l.ref_arena_offsets.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    l.ref_arena_offsets(1000, 5000, 64 * 64, off)
+    # Appendix A.7: point_list u32[L] first, then unsorted values, then the sorted keys; n_contrib before ranges;
+    # every field 128-byte aligned
+    assert off[1] == 0 and off[0] == 2 * ((5000 * 4 + 127) // 128 * 128) and off[3] == 0 and off[2] == (64 * 64 * 4 + 127) // 128 * 128
+    assert all(o % 128 == 0 for o in off)
+    assert ref_rasterizer.real_package() is None
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_golden_from_ref.py")], capture_output=True, text=True)
+    assert r.returncode == 0 and "unpinned" in r.stdout
 
 
 def test_orbit_camera_convention():
