@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblgm_b200.so")
-SOURCES = ["preprocess.cu", "binning.cu", "radix_sort.cu", "tile_sort.cu", "direct_bin.cu", "composite.cu", "sh.cu", "loss.cu", "activations.cu", "resize.cu", "api.cu"]
+SOURCES = ["preprocess.cu", "binning.cu", "radix_sort.cu", "tile_sort.cu", "direct_bin.cu", "composite.cu", "composite2.cu", "sh.cu", "loss.cu", "activations.cu", "resize.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

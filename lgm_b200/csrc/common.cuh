@@ -126,6 +126,17 @@ cudaError_t launch_composite_bwd(cudaStream_t stream, const RenderParams& prm, c
                                  const float* alpha, const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha,
                                  const float* dL_ddepth, float* grad_rows);
 
+// composite2.cu: the same two kernels with two pixels per lane and packed fp32 (the default; see launch_composite_fwd)
+cudaError_t launch_composite2_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                  const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                  int clamp_image, float* image, float* alpha, float* depth_img, uint32_t* n_contrib);
+cudaError_t launch_composite2_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
+                                  const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
+                                  const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
+                                  const float* alpha, const uint32_t* n_contrib, const float* dL_dimage, const float* dL_dalpha,
+                                  const float* dL_ddepth, float* grad_rows);
+
 // ---- small device helpers ----
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 {

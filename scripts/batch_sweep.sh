@@ -1,8 +1,11 @@
 #!/bin/bash
-# Developer experiment: compositing staging-batch sizes (LGM_FWD_BATCH / LGM_BWD_BATCH)
-for fb in ${BATCHES:-256 512 768 1024}; do
-    LGM_FWD_BATCH=$fb LGM_BWD_BATCH=$fb python bench.py --steps 5 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stages_ms']
-print('batch', $fb, 'fwd %.2f bwd %.2f step %.2f' % (s['composite_fwd'], s['composite_bwd'], d['ms_per_step']))"
+# Developer experiment: staging batch of the compositing kernels (LGM_FWD_BATCH / LGM_BWD_BATCH) on the headline workload.
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+for b in ${BATCHES:-256 384 512 640 768 1024}; do
+LGM_FWD_BATCH=$b LGM_BWD_BATCH=$b python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-scale-sweep --no-gpu-baseline ${BENCH_ARGS:-} 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+s = d['stages_ms']
+print('batch $b: step %.3f ms  fwd %.3f  bwd %.3f' % (d['ms_per_step'], s['composite_fwd'], s['composite_bwd']))"
 done

@@ -1,14 +1,31 @@
 #!/bin/bash
-# One GPU-box pass: sort tests first (short timeout: a hung look-back must not eat the budget), then the parity
-# suite, smoke and a short bench.  Everything lands in gpurun_out/.
+# One GPU-box pass: build, the parity suite (the slow full-size oracle comparisons only with FULL=1), smoke and a short bench.
+# Everything lands in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; exit 1; }
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "onesweep" > gpurun_out/pytest_sort.log 2>&1
-rc=$?; echo "sort tests rc=$rc"; tail -5 gpurun_out/pytest_sort.log
+rc=$?; echo "sort tests rc=$rc"; tail -3 gpurun_out/pytest_sort.log
 if [ $rc -eq 124 ]; then echo "sort tests TIMED OUT - stopping"; exit 2; fi
-timeout 900 python -m pytest tests -m gpu -q --tb=short --maxfail=12 -k "not onesweep" > gpurun_out/pytest_gpu.log 2>&1
+IGN="--ignore=tests/test_gpu_fullsize.py"; [ "${FULL:-0}" = "1" ] && IGN=""
+timeout 1100 python -m pytest tests -m gpu -q --tb=short --maxfail=12 -k "not onesweep" $IGN > gpurun_out/pytest_gpu.log 2>&1
 echo "parity tests rc=$?"; tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
-timeout 600 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+    print("value %.0f views/s  %.3f ms/step  launches %s" % (d["value"], d["ms_per_step"], d["gpu_launches"]))
+    print("stages", {k: round(v, 3) for k, v in (d.get("stages_ms") or {}).items()})
+    e = d.get("e2e") or {}
+    if e: print("e2e %.0f (%.2f ms)  serial %.2f ms  u8 %.2f ms  copies %.2f ms" % (e["value"], e["ms_per_step"], e["serial"]["ms_per_step"], e["u8_ground_truth"]["ms_per_step"], e["h2d_alone_ms"]))
+    print("roofline", {k: d["roofline"][k] for k in ("achieved", "frac", "ms")} if d.get("roofline") else None)
+    print("gpu_baseline", {k: v for k, v in (d.get("gpu_baseline") or {}).items() if k != "what"})
+    ss = d.get("scale_sweep") or {}
+    print("scale_sweep", {k: v for k, v in ss.items() if k in ("value", "ms_per_step", "efficiency", "stages_ms_rank0", "limiter")})
+except Exception as ex:
+    print("bench parse failed:", ex)
+PY
+tail -5 gpurun_out/bench.err

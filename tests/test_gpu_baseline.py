@@ -81,7 +81,7 @@ def test_baseline_against_oracle(ref, oracle32, oracle64):
     wi, wa, wd = rng.randn(3, S, S).astype(np.float32), rng.randn(1, S, S).astype(np.float32), rng.randn(1, S, S).astype(np.float32)
     ((color * torch.tensor(wi, device=DEV)).sum() + (alpha * torch.tensor(wa, device=DEV)).sum() +
      (depth * torch.tensor(wd, device=DEV)).sum()).backward()
-    # the fp32 oracle (same algorithm, same precision, same forward decisions): 1e-4; the fp64 oracle differentiates the
+    # the fp32 oracle (same algorithm, same precision, same forward decisions; fp32 atomics in arbitrary order): 1e-3; the fp64 oracle differentiates the
     # branch ITS forward took (other alpha < 1/255 decisions), which costs both fp32 implementations ~1e-3: 5e-3
     r32 = oracle32.rasterize_backward(*args, pre, b, f, wi, wa[0], wd[0])
     p64, b64, f64 = oracle64.rasterize(*args)
@@ -89,7 +89,7 @@ def test_baseline_against_oracle(ref, oracle32, oracle64):
     for got, key, nm in ((m3.grad, "dL_dmeans", "means"), (op.grad[:, 0], "dL_dopacity", "opacity"), (sc.grad, "dL_dscales", "scales"),
                          (ro.grad, "dL_drots", "rots"), (col.grad, "dL_dcolor", "rgb")):
         scale = np.abs(r64[key]).max() + 1e-30
-        assert np.abs(got.cpu().numpy() - r32[key]).max() <= 1e-4 * scale, nm
+        assert np.abs(got.cpu().numpy() - r32[key]).max() <= 1e-3 * scale, nm
         assert np.abs(got.cpu().numpy() - r64[key]).max() <= 5e-3 * scale, nm
 
 

@@ -604,20 +604,28 @@ def test_rasterizer_with_shs_matches_precomputed_colours(oracle64):
     assert sh.grad.abs().sum().item() > 0 and torch.isfinite(sh.grad).all() and torch.isfinite(m3.grad).all()
 
 
-def test_patch_sizes_agree(monkeypatch):
-    """The compositing kernels with 8x4 / 4x4 / 4x2-pixel patches (LGM_PATCH_LANES = 32 / 16 / 8): culling granularity
-    only decides which non-contributing pairs are skipped, so the forward outputs are bit-identical and the gradients
-    agree up to fp32 summation order.  Image not a multiple of 16, depth gradient present and absent."""
+def test_composite_variants_agree(monkeypatch):
+    """The shipped compositing kernels (composite2.cu: two pixels per lane, 8x8 patches, packed fp32 FFMA2 / FMUL2 / FADD2;
+    LGM_PATCH_LANES unset or 64) against the one-pixel-per-lane kernels of composite.cu with 8x4 / 4x4 / 4x2-pixel patches
+    (LGM_PATCH_LANES = 32 / 16 / 8): every packed half is the same correctly rounded operation in the same order, and the
+    culling granularity only decides which non-contributing pairs are skipped, so the forward outputs are bit-identical
+    and the gradients agree up to fp32 summation order.  Image not a multiple of 16 (pixels outside the image are
+    "parked"), saturating splats (pixels that stop are parked), depth gradient present and absent."""
     from lgm_b200 import ops
     B, V, N, S = 2, 3, 6000, 72
     g0 = make_gaussians(B, N, "trained", seed=23)
     g0[:, :, 4:7] *= 4.0
+    g0[1] = make_gaussians(1, N, "init", seed=24)[0]   # scene 1: large saturating splats (the stop rule fires)
     cv, cvp, _ = make_cameras(B, V, seed=23)
     t = tan_half(49.1)
     d_img, d_alpha, d_depth = make_upstream_grads(B, V, S, S, seed=23, with_depth=True)
+    d_img, d_alpha, d_depth = d_img * 1e4, d_alpha * 1e4, d_depth * 1e4
     res = {}
-    for lanes in (32, 16, 8):
-        monkeypatch.setenv("LGM_PATCH_LANES", str(lanes))
+    for lanes in (32, 16, 8, 64):
+        if lanes == 64:
+            monkeypatch.delenv("LGM_PATCH_LANES", raising=False)   # the default
+        else:
+            monkeypatch.setenv("LGM_PATCH_LANES", str(lanes))
         g, vm, pm, bg, img, al, dp, st = _cuda_forward(g0.numpy(), cv, cvp, [0.1, 0.2, 0.3], S, S, t, t)
         outs = []
         for dd in (d_depth, None):
@@ -626,7 +634,8 @@ def test_patch_sizes_agree(monkeypatch):
                                        None if dd is None else dd.reshape(B * V, 1, S, S).to(DEV).contiguous())
             outs.append(dg.clone())
         res[lanes] = (img.clone(), al.clone(), dp.clone(), st.n_contrib.clone(), outs)
-    for lanes in (16, 8):
+    assert int((res[32][3] & 0x1FFFFFFF).max()) > 50 and float(res[32][1].max()) > 0.999  # long lists, saturated pixels
+    for lanes in (16, 8, 64):
         for k in range(4):
             assert torch.equal(res[32][k], res[lanes][k]), f"forward output {k} differs at LGM_PATCH_LANES={lanes}"
         for a, b in zip(res[32][4], res[lanes][4]):
