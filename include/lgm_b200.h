@@ -70,25 +70,28 @@ const char* lgm_last_error_string(void);
 
 /* Tuning / test hooks (process-wide; the defaults are the measured optimum).  name: "fwd_batch" / "bwd_batch" (Gaussians
  * staged per block barrier by the compositing kernels, multiple of 32), "patch_lanes" (32 | 16 | 8), "sort_variant"
- * (launch shape of the onesweep sort), "enum_global" (1: binning enumeration without the per-CTA shared-memory stage).
+ * (launch shape of the onesweep sort), "enum_global" (1: binning enumeration without the per-CTA shared-memory stage),
+ * "coarse_ratio" (instances per coarse entry from which the direct binning groups by super-tile first; 0 = never).
  * value < 0 restores the default. */
 int lgm_set_tuning(const char* name, int32_t value);
 
 /* The step's data-dependent sizes, DEVICE memory, 16 bytes: written by lgm_forward_geom (total_instances) and
- * lgm_forward_count (longest_tile); the caller reads both back with one 16-byte copy. */
+ * lgm_forward_count (longest_tile, coarse_entries); the caller reads them back with one 16-byte copy. */
 typedef struct lgm_step_counts {
     uint64_t total_instances; /* sum of tiles_touched over all (view, Gaussian) pairs of the call */
     uint32_t longest_tile;    /* instances of the fullest tile */
-    uint32_t reserved;
+    uint32_t coarse_entries;  /* (view, Gaussian, 8x8-tile super-tile) entries: what the coarse grouping of steps with large
+                                 footprints would hold (0 when the image shape does not allow it) */
 } lgm_step_counts;
 
 /* Number of 16x16 tiles of one view. */
 int lgm_tiles_per_view(int32_t image_height, int32_t image_width);
 /* Number of per-(view, 256-Gaussian block) partial sums forward_geom writes: n_views * ceil(P / 256). */
 int64_t lgm_num_block_sums(int32_t n_gaussians, int32_t n_views);
-/* Scratch bytes forward_bin needs for L instances (alternate key/value buffers, histograms, look-back state; the
- * direct path's pairs alias them). */
-int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes);
+/* Scratch bytes forward_bin needs for L instances and E coarse entries, both as read back from lgm_step_counts
+ * (alternate key/value buffers, histograms, look-back state; the direct path's pairs alias them; 16 B per entry when
+ * the step takes the coarse grouping). */
+int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, int64_t coarse_entries, size_t* bytes);
 
 /* K1 preprocess + instance-offset scan.  Replaces preprocessCUDA + InclusiveSum (+ its blocking D2H: here the
  * total stays on the device in total_instances[0], read back once per step by the host wrapper).
@@ -109,7 +112,8 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
 
 /* Binning, first half (direct path D1 + D2): per-tile instance counts and their scan.  After it `ranges`
  * uint2[n_views * tiles] holds every tile's [start, end) in the final instance list (empty tiles (0,0)) and
- * counts->longest_tile the fullest tile.  count_workspace (lgm_count_workspace_bytes; does not depend on the instance
+ * counts->longest_tile the fullest tile; counts->total_instances must already have been written (lgm_forward_geom, same
+ * stream).  count_workspace (lgm_count_workspace_bytes; does not depend on the instance
  * count) must be handed unchanged to lgm_forward_bin.  Enqueue before the step's readback. */
 int lgm_count_workspace_bytes(const lgm_render_params* prm, size_t* bytes);
 int lgm_forward_count(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy, uint32_t* ranges,
@@ -118,7 +122,10 @@ int lgm_forward_count(void* stream, const lgm_render_params* prm, const int32_t*
 int lgm_direct_bin_tile_cap(void);
 
 /* Binning, second half.  Replaces duplicateWithKeys + SortPairs + identifyTileRanges.
- * n_instances, longest_tile = the values read back from lgm_step_counts (longest_tile < 0: unknown).
+ * n_instances, longest_tile, coarse_entries = the values read back from lgm_step_counts (longest_tile < 0: unknown;
+ * coarse_entries 0: no coarse grouping).  Steps with large footprints (>= 6 instances per entry; lgm_set_tuning
+ * "coarse_ratio") first group the (view, Gaussian) pairs by 8x8-tile super-tile, so that the scatter of the direct path
+ * writes long runs instead of isolated 8-byte pairs (lgm_last_bin_coarse tells).
  * keys_sorted u64[L] (view*tiles+tile << 32 | depth bits), vals_sorted u32[L] (view * P + Gaussian index), ranges
  * uint2[n_views * tiles] = [start,end).  The list order is upstream's: by tile, then depth bits, ties in emit order
  * (ascending value).  Three internal paths produce it bit for bit (lgm_last_bin_mode tells which ran):
@@ -137,8 +144,8 @@ int lgm_direct_bin_tile_cap(void);
 #define LGM_BIN_DIRECT 3
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, int64_t longest_tile,
-                    int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
-                    size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys);
+                    int64_t coarse_entries, int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
+                    void* workspace, size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys);
 
 /* K5 compositing.  Replaces renderCUDA fwd.  image [n_views,3,H,W], alpha / depth_img [n_views,H,W], n_contrib u32
  * [n_views,H,W] (bits 0..28: number of list entries the pixel consumed, as upstream).
@@ -155,10 +162,10 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
 int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
-                           int64_t n_instances, int64_t longest_tile, int32_t bin_mode, uint64_t* keys_sorted,
-                           uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
-                           void* count_workspace, const float* bg, int32_t clamp_image, float* image, float* alpha,
-                           float* depth_img, uint32_t* n_contrib);
+                           int64_t n_instances, int64_t longest_tile, int64_t coarse_entries, int32_t bin_mode,
+                           uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
+                           size_t workspace_bytes, void* count_workspace, const float* bg, int32_t clamp_image, float* image,
+                           float* alpha, float* depth_img, uint32_t* n_contrib);
 
 /* K6 + K7.  Replaces renderCUDA bwd + computeCov2DCUDA + preprocessCUDA bwd.
  * dL_ddepth may be NULL (= zero gradient w.r.t. the depth image: LGM's losses never use depth; a cheaper kernel
@@ -205,6 +212,7 @@ int lgm_screen_gradients(void* stream, const lgm_render_params* prm, const float
  * when there was nothing to bin): diagnostics / launch accounting. */
 #define LGM_BIN_NONE 0
 int lgm_last_bin_mode(void);
+int lgm_last_bin_coarse(void); /* 1: the last direct binning grouped the pairs by super-tile first */
 
 int lgm_mark_visible(void* stream, int32_t n_points, const float* means, const float* view_mat, uint8_t* visible);
 

@@ -30,7 +30,7 @@ _SIGNATURES = {
     "lgm_last_error_string": (ctypes.c_char_p, []),
     "lgm_tiles_per_view": (ctypes.c_int, [_i32, _i32]),
     "lgm_num_block_sums": (_i64, [_i32, _i32]),
-    "lgm_bin_workspace_bytes": (ctypes.c_int, [_pp, _i64, ctypes.POINTER(_sz)]),
+    "lgm_bin_workspace_bytes": (ctypes.c_int, [_pp, _i64, _i64, ctypes.POINTER(_sz)]),
     "lgm_forward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 12),
     "lgm_forward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 13),
     "lgm_backward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32, _vp, _vp]),
@@ -38,9 +38,10 @@ _SIGNATURES = {
     "lgm_count_workspace_bytes": (ctypes.c_int, [_pp, ctypes.POINTER(_sz)]),
     "lgm_forward_count": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lgm_direct_bin_tile_cap": (ctypes.c_int, []),
-    "lgm_forward_bin": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _i32]),
+    "lgm_forward_bin": (ctypes.c_int, [_vp, _pp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _i32]),
+    "lgm_last_bin_coarse": (ctypes.c_int, []),
     "lgm_forward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32] + [_vp] * 4),
-    "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i32] + [_vp] * 4),
+    "lgm_forward_bin_render": (ctypes.c_int, [_vp, _pp] + [_vp] * 7 + [_i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i32] + [_vp] * 4),
     "lgm_backward": (ctypes.c_int, [_vp, _pp] + [_vp] * 19 + [_i32]),
     "lgm_backward_composite": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
     "lgm_backward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32]),
@@ -84,7 +85,7 @@ def lib():
 # Tuning / test hooks of the library (lgm_set_tuning) and the environment variables that drive them from Python.  The
 # C library itself never reads the environment; apply_env_tuning() is called by ops at the head of every render.
 _TUNING_ENV = {"fwd_batch": "LGM_FWD_BATCH", "bwd_batch": "LGM_BWD_BATCH", "patch_lanes": "LGM_PATCH_LANES",
-               "sort_variant": "LGM_SORT_VARIANT", "enum_global": "LGM_ENUM_GLOBAL"}
+               "sort_variant": "LGM_SORT_VARIANT", "enum_global": "LGM_ENUM_GLOBAL", "coarse_ratio": "LGM_COARSE_RATIO"}
 _tuning_applied = {}
 BIN_MODE_IDS = {"auto": 0, "onesweep": 1, "hybrid": 2, "direct": 3}
 

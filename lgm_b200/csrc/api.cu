@@ -76,9 +76,10 @@ int key_end_bit(const lgm::RenderParams& p)
 }
 
 struct BinWorkspace {
-    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, total;
+    size_t keys_tmp, vals_tmp, sort_scratch, sort_scratch_bytes, tile_scratch, entries, total;
 };
-BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
+// E: coarse entries of the step (0: none) — a step that takes the coarse grouping needs 16 B per entry on top
+BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L, uint64_t E)
 {
     BinWorkspace w;
     size_t off = 0;
@@ -89,14 +90,17 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L)
     off = align_up(off + w.sort_scratch_bytes, 256);
     w.tile_scratch = off;
     off = align_up(off + lgm::tile_sort_scratch_bytes((uint32_t)((size_t)p.n_views * p.n_tiles)), 256);
+    w.entries = off;
+    if (lgm::direct_bin_use_coarse(p, L, E)) off = align_up(off + (size_t)E * 16, 256);
     w.total = off;
     return w;
 }
 
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
+thread_local bool g_last_coarse = false;
 
-std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}};
-const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global"};
+std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio"};
 std::atomic<int> g_sm_count[lgm::kMaxDevices];
 
 }  // namespace
@@ -119,6 +123,7 @@ extern "C" {
 
 int lgm_abi_version(void) { return LGM_ABI_VERSION; }
 int lgm_last_bin_mode(void) { return g_last_bin_mode; }
+int lgm_last_bin_coarse(void) { return g_last_coarse ? 1 : 0; }
 const char* lgm_last_error_string(void) { return g_err; }
 
 int lgm_set_tuning(const char* name, int32_t value)
@@ -129,7 +134,7 @@ int lgm_set_tuning(const char* name, int32_t value)
             g_tuning[i].store(value, std::memory_order_relaxed);
             return LGM_OK;
         }
-    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global)");
+    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global, coarse_ratio)");
 }
 
 int lgm_direct_bin_tile_cap(void) { return lgm::direct_bin_tile_cap(); }
@@ -137,14 +142,15 @@ int lgm_direct_bin_tile_cap(void) { return lgm::direct_bin_tile_cap(); }
 int lgm_tiles_per_view(int32_t H, int32_t W) { return ((W + 15) / 16) * ((H + 15) / 16); }
 int64_t lgm_num_block_sums(int32_t P, int32_t n_views) { return (int64_t)n_views * ((P + lgm::kBlock - 1) / lgm::kBlock); }
 
-int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, size_t* bytes)
+int lgm_bin_workspace_bytes(const lgm_render_params* prm, int64_t n_instances, int64_t coarse_entries, size_t* bytes)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     LGM_NOTNULL(bytes);
     if (n_instances < 0) return fail(LGM_ERR_BAD_SHAPE, "n_instances < 0");
     if (n_instances >= ((int64_t)1 << 30)) return fail(LGM_ERR_TOO_MANY_INSTANCES, "n_instances >= 2^30: split the views into chunks");
-    *bytes = bin_layout(p, (uint32_t)n_instances).total;
+    if (coarse_entries < 0) return fail(LGM_ERR_BAD_SHAPE, "coarse_entries < 0");
+    *bytes = bin_layout(p, (uint32_t)n_instances, (uint64_t)coarse_entries).total;
     return LGM_OK;
 }
 
@@ -200,22 +206,23 @@ int lgm_forward_count(void* stream, const lgm_render_params* prm, const int32_t*
     LGM_NOTNULL(counts);
     cudaStream_t s = (cudaStream_t)stream;
     if (p.P == 0 || p.n_views == 0) {
-        LGM_CUDA(cudaMemsetAsync(&counts->longest_tile, 0, sizeof(uint32_t), s), "forward_count: memset");
+        LGM_CUDA(cudaMemsetAsync(&counts->longest_tile, 0, 2 * sizeof(uint32_t), s), "forward_count: memset");
         return LGM_OK;
     }
     LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(ranges); LGM_NOTNULL(count_workspace);
     if (count_workspace_bytes < lgm::direct_bin_scratch_bytes(p))
         return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "forward_count: workspace too small (see lgm_count_workspace_bytes)");
     LGM_CUDA(lgm::launch_direct_bin_count(s, p, radii, reinterpret_cast<const float2*>(xy), reinterpret_cast<uint2*>(ranges),
-                                          count_workspace, &counts->longest_tile),
+                                          count_workspace, &counts->longest_tile, &counts->coarse_entries,
+                                          reinterpret_cast<const unsigned long long*>(&counts->total_instances)),
              "forward_count");
     return LGM_OK;
 }
 
 int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* radii, const float* xy,
                     const float* depth, const uint32_t* block_offsets, int64_t n_instances, int64_t longest_tile,
-                    int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
-                    size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys)
+                    int64_t coarse_entries, int32_t bin_mode, uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges,
+                    void* workspace, size_t workspace_bytes, void* count_workspace, int32_t want_sorted_keys)
 {
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
@@ -226,6 +233,7 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     const size_t n_ranges = (size_t)p.n_views * p.n_tiles;
     if (n_ranges) LGM_NOTNULL(ranges);
     g_last_bin_mode = LGM_BIN_NONE;
+    g_last_coarse = false;
     // The DIRECT path (direct_bin.cu: count, scan, scatter, per-tile shared-memory sort — no global radix sort, 20 B
     // instead of 152 B of HBM traffic per instance) needs lgm_forward_count to have run (ranges[] are then already
     // final) and every tile to fit its shared-memory sort; the caller read the longest tile back together with the
@@ -245,16 +253,21 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
     LGM_NOTNULL(vals_sorted); LGM_NOTNULL(workspace);
     if (!direct || want_sorted_keys) LGM_NOTNULL(keys_sorted);  // the direct path needs no key buffer of its own
     const uint32_t L = (uint32_t)n_instances;
-    const BinWorkspace w = bin_layout(p, L);
+    if (coarse_entries < 0) return fail(LGM_ERR_BAD_SHAPE, "coarse_entries < 0");
+    const BinWorkspace w = bin_layout(p, L, direct ? (uint64_t)coarse_entries : 0);
     if (workspace_bytes < w.total) return fail(LGM_ERR_WORKSPACE_TOO_SMALL, "forward_bin: workspace too small (see lgm_bin_workspace_bytes)");
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     uint64_t* keys_tmp = reinterpret_cast<uint64_t*>(ws + w.keys_tmp);
     uint32_t* vals_tmp = reinterpret_cast<uint32_t*>(ws + w.vals_tmp);
     const int end_bit = key_end_bit(p);
     if (direct) {
+        // steps with large footprints group the pairs by super-tile first (16 B per entry at the end of the workspace)
+        void* entries = nullptr;
+        if (lgm::direct_bin_use_coarse(p, (uint64_t)L, (uint64_t)coarse_entries)) entries = ws + w.entries;
+        g_last_coarse = entries != nullptr;
         LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
                                              reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
-                                             want_sorted_keys ? keys_sorted : nullptr, count_workspace, (uint32_t)longest_tile),
+                                             want_sorted_keys ? keys_sorted : nullptr, count_workspace, (uint32_t)longest_tile, entries),
                  "forward_bin: direct sort");
         g_last_bin_mode = LGM_BIN_DIRECT;
         return LGM_OK;
@@ -300,13 +313,13 @@ int lgm_forward_composite(void* stream, const lgm_render_params* prm, const floa
 int lgm_forward_bin_render(void* stream, const lgm_render_params* prm, const float* gaussians,
                            const int32_t* view_scene, const int32_t* radii, const float* xy,
                            const float* conic_opacity, const float* depth, const uint32_t* block_offsets,
-                           int64_t n_instances, int64_t longest_tile, int32_t bin_mode, uint64_t* keys_sorted,
-                           uint32_t* vals_sorted, uint32_t* ranges, void* workspace, size_t workspace_bytes,
-                           void* count_workspace, const float* bg, int32_t clamp_image, float* image, float* alpha,
-                           float* depth_img, uint32_t* n_contrib)
+                           int64_t n_instances, int64_t longest_tile, int64_t coarse_entries, int32_t bin_mode,
+                           uint64_t* keys_sorted, uint32_t* vals_sorted, uint32_t* ranges, void* workspace,
+                           size_t workspace_bytes, void* count_workspace, const float* bg, int32_t clamp_image, float* image,
+                           float* alpha, float* depth_img, uint32_t* n_contrib)
 {
-    if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, longest_tile, bin_mode, keys_sorted,
-                                 vals_sorted, ranges, workspace, workspace_bytes, count_workspace, /*want_sorted_keys=*/1))
+    if (int rc = lgm_forward_bin(stream, prm, radii, xy, depth, block_offsets, n_instances, longest_tile, coarse_entries, bin_mode,
+                                 keys_sorted, vals_sorted, ranges, workspace, workspace_bytes, count_workspace, /*want_sorted_keys=*/1))
         return rc;
     return lgm_forward_composite(stream, prm, gaussians, view_scene, xy, conic_opacity, depth, vals_sorted, ranges, bg,
                                  clamp_image, image, alpha, depth_img, n_contrib);

@@ -35,6 +35,10 @@ namespace {
 // Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
 constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
 constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
+// X: the class between them — tiles of up to 9,216 instances, 1024 threads, 109 KB: TWO CTAs per SM, so that one CTA's
+// global load / store phases overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians have most of their
+// instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
+constexpr int kSortThreadsX = 1024, kSortCapX = 9216, kLgBucketsX = 12;
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
@@ -91,18 +95,72 @@ __device__ __forceinline__ void for_each_touched_tile(const RenderParams& prm, c
 constexpr int kEnumItems = 8;
 constexpr int kEnumMaxTiles = 6144;  // 2 x 4 B per tile of dynamic shared memory must stay under the default 48 KB
 
+// ---- coarse grouping for steps with large footprints (many tiles per Gaussian) ----
+// With ~16 tiles per Gaussian and Gaussians in arbitrary spatial order, the scatter's 8-byte stores of one CTA go to
+// thousands of tile segments at once: measured on 32 views of 1 M Gaussians at 1024^2 (499 M instances) 9.3 ms, DRAM
+// write 9.7 GB for 4 GB of pairs plus 5.5 GB of read-for-ownership — partial-sector traffic.  So such steps first group
+// the (view, Gaussian) pairs by SUPER-TILE (8x8 tiles): one 16-byte entry per touched super-tile (value, depth bits, the
+// tile rect clipped to the super-tile, view) in a counting sort whose runs are long, and the fine scatter then works
+// through one super-tile's entries at a time: a CTA's stores go to the 64 segments of that super-tile only, in runs of
+// hundreds of pairs.  The entry counts come for free with the tile counts (same enumeration).
+constexpr int kSuperShift = 3, kSuperTiles = 1 << kSuperShift;
+constexpr int kCoarseChunk = 2048;       // entries per work item of the fine scatter
+constexpr uint32_t kCoarseMaxSupers = 1024;  // per view (a 4096^2 image); beyond that the plain scatter is used
+
+__host__ __device__ inline int supers_x(const RenderParams& prm) { return (prm.gx + kSuperTiles - 1) >> kSuperShift; }
+__host__ __device__ inline int supers_y(const RenderParams& prm) { return (prm.gy + kSuperTiles - 1) >> kSuperShift; }
+
+// the tile rect of (view, idx), area 0 when culled
+__device__ __forceinline__ uint32_t load_rect(const RenderParams& prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+                                              size_t gi, bool in_range, int& x0, int& y0, int& x1, int& y1)
+{
+    x0 = y0 = x1 = y1 = 0;
+    if (!in_range) return 0;
+    const int r = radii[gi];
+    if (r <= 0) return 0;
+    const float2 p = xy[gi];
+    tile_rect(p.x, p.y, r, prm.gx, prm.gy, x0, y0, x1, y1);
+    return (uint32_t)((x1 - x0) * (y1 - y0));
+}
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(kBlock)
 tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
                       const float* __restrict__ depth, uint32_t* __restrict__ counts, uint32_t* __restrict__ view_totals,
-                      const uint2* __restrict__ ranges, uint2* __restrict__ pairs)
+                      const uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint32_t* __restrict__ super_counts,
+                      uint32_t* __restrict__ view_entries, const unsigned long long* __restrict__ total_instances,
+                      unsigned long long coarse_gate)
 {
     extern __shared__ uint32_t s_enum[];
     uint32_t* s_hist = s_enum;                 // [n_tiles] instances of this CTA per tile, then the fill cursor
-    uint32_t* s_base = s_enum + prm.n_tiles;   // [n_tiles] first slot of this CTA's run (SCATTER)
+    uint32_t* s_base = s_enum + prm.n_tiles;   // [n_tiles] first slot of this CTA's run (SCATTER); count: coarse entries per super-tile
     const int view = blockIdx.y;
     const int first = blockIdx.x * (kBlock * kEnumItems) + threadIdx.x;
     const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+    const int nsx = supers_x(prm), n_super = nsx * supers_y(prm);
+    // the coarse entries are only counted for steps that can use them: large footprints, i.e. at least coarse_gate
+    // instances per (view, Gaussian) pair — the instance total is on the device since the preprocess stage's scan
+    if (!SCATTER && super_counts && *total_instances >= coarse_gate * (unsigned long long)prm.n_views * (unsigned long long)prm.P) {
+        // entries per super-tile of this CTA's Gaussians (a Gaussian has one entry per super-tile its rect touches)
+        for (int i = threadIdx.x; i < n_super; i += kBlock) s_base[i] = 0u;
+        __syncthreads();
+        for (int k = 0; k < kEnumItems; k++) {
+            const int idx = first + k * kBlock;
+            int x0, y0, x1, y1;
+            if (load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+            for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
+                for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) atomicAdd(&s_base[sy * nsx + sx], 1u);
+        }
+        __syncthreads();
+        uint32_t mine = 0;
+        for (int i = threadIdx.x; i < n_super; i += kBlock) {
+            const uint32_t c = s_base[i];
+            if (c) atomicAdd(&super_counts[(size_t)view * n_super + i], c);
+            mine += c;
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&view_entries[view], mine);
+    }
     // (handing the count launch's per-CTA histogram to the scatter launch through global memory instead of
     // recounting was measured slower: 0.63 vs 0.53 ms — the recount sweep also warms L1 with the rows the scatter reads)
     for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
@@ -171,12 +229,14 @@ uint32_t enum_ctas_per_view(const RenderParams& prm) { return (uint32_t)((prm.P 
 template <bool SCATTER>
 cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                   const float* depth, uint32_t* counts, uint32_t* view_totals, const uint2* ranges,
-                                  uint2* pairs)
+                                  uint2* pairs, uint32_t* super_counts = nullptr, uint32_t* view_entries = nullptr,
+                                  const unsigned long long* total_instances = nullptr, unsigned long long coarse_gate = 0)
 {
     if (enumerate_in_smem(prm)) {
         dim3 grid(enum_ctas_per_view(prm), prm.n_views);
         tile_enumerate_kernel<SCATTER><<<grid, kBlock, (size_t)prm.n_tiles * 8, stream>>>(prm, radii, xy, depth, counts, view_totals,
-                                                                                          ranges, pairs);
+                                                                                          ranges, pairs, super_counts, view_entries,
+                                                                                          total_instances, coarse_gate);
     } else {
         dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
         tile_enumerate_global_kernel<SCATTER><<<grid, kBlock, 0, stream>>>(prm, radii, xy, depth, counts, view_totals, ranges, pairs);
@@ -184,14 +244,23 @@ cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, 
     return cudaGetLastError();
 }
 
+// head[] words of the direct path's scratch
+enum Head { kHeadM = 0, kHeadMCursor = 1, kHeadLongest = 2, kHeadL = 3, kHeadLCursor = 4, kHeadX = 5, kHeadXCursor = 6,
+            kHeadItems = 7, kHeadItemCursor = 8, kHeadItemOverflow = 9 };
+
 // D2.  One CTA per view: the view's first slot is the sum of the totals of the views before it, the tiles of the view
-// are scanned in chunks of 256.  Writes ranges[] (empty tiles stay (0,0)), appends the non-empty tiles to the work list
-// (warp-aggregated) and records the longest tile.  Tiles of the M class (<= kSortCapM) fill the list from the front, longer
-// ones from the back.  head[0] / head[3] = M / L list length, head[1] / head[4] = their work cursors, head[2] = longest.
+// are scanned in chunks of 256.  Writes ranges[] (empty tiles stay (0,0)), appends the non-empty tiles to the work lists
+// (warp-aggregated) and records the longest tile.  Tiles of the M class (<= kSortCapM) fill `list` from the front, those
+// of the L class (> kSortCapX) from the back, the X class in between fills `list_x`.
+// Coarse grouping (super_counts != null): the same for the entries — super_offsets[] = first entry of every (view,
+// super-tile) group in the grouped entry list, one work item (group, chunk) per kCoarseChunk entries of a group, and
+// the total number of entries (the last view's CTA writes it to *entries_out).
 __global__ void __launch_bounds__(kBlock)
 tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ view_totals, int n_tiles,
-                        uint32_t n_ranges, uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ head,
-                        uint32_t* __restrict__ longest_out)
+                        uint32_t n_ranges, uint2* __restrict__ ranges, uint32_t* __restrict__ list, uint32_t* __restrict__ list_x,
+                        uint32_t* __restrict__ head, uint32_t* __restrict__ longest_out, const uint32_t* __restrict__ super_counts,
+                        const uint32_t* __restrict__ view_entries, int n_super, uint32_t* __restrict__ super_offsets,
+                        uint2* __restrict__ items, uint32_t item_capacity, uint32_t* __restrict__ entries_out)
 {
     __shared__ uint32_t s_warp[8];
     const int view = blockIdx.x, t = threadIdx.x, lane = t & 31;
@@ -209,12 +278,13 @@ tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __r
         carry += tot;
         if (i < n_tiles) ranges[gt] = n ? make_uint2(start, start + n) : make_uint2(0u, 0u);
         longest = max(longest, n);
-        const bool is_m = n != 0u && n <= (uint32_t)kSortCapM, is_l = n > (uint32_t)kSortCapM;
+        const bool is_m = n != 0u && n <= (uint32_t)kSortCapM, is_l = n > (uint32_t)kSortCapX;
+        const bool is_x = n > (uint32_t)kSortCapM && !is_l;
         const unsigned m = __ballot_sync(0xffffffffu, is_m);
         if (m) {
             const int leader = __ffs(m) - 1;
             uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&head[0], (uint32_t)__popc(m));
+            if (lane == leader) base = atomicAdd(&head[kHeadM], (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (is_m) list[base + __popc(m & ((1u << lane) - 1u))] = gt;
         }
@@ -222,15 +292,179 @@ tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __r
         if (ml) {
             const int leader = __ffs(ml) - 1;
             uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&head[3], (uint32_t)__popc(ml));
+            if (lane == leader) base = atomicAdd(&head[kHeadL], (uint32_t)__popc(ml));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (is_l) list[n_ranges - 1u - (base + __popc(ml & ((1u << lane) - 1u)))] = gt;
+        }
+        const unsigned mx = __ballot_sync(0xffffffffu, is_x);
+        if (mx) {
+            const int leader = __ffs(mx) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&head[kHeadX], (uint32_t)__popc(mx));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_x) list_x[base + __popc(mx & ((1u << lane) - 1u))] = gt;
         }
     }
     longest = __reduce_max_sync(0xffffffffu, longest);
     if (lane == 0 && longest) {
-        atomicMax(&head[2], longest);
+        atomicMax(&head[kHeadLongest], longest);
         if (longest_out) atomicMax(longest_out, longest);  // the caller's step counters (read back with the instance count)
+    }
+    if (super_counts == nullptr) return;
+    // ---- coarse groups of this view ----
+    __syncthreads();
+    part = 0;
+    for (int v = t; v < view; v += kBlock) part += view_entries[v];
+    uint32_t ecarry;
+    block_excl_scan_256(part, s_warp, &ecarry);
+    for (int i0 = 0; i0 < n_super; i0 += kBlock) {
+        const int i = i0 + t;
+        const uint32_t g = (uint32_t)view * (uint32_t)n_super + (uint32_t)i;
+        const uint32_t n = i < n_super ? super_counts[g] : 0u;
+        uint32_t tot;
+        const uint32_t start = ecarry + block_excl_scan_256(n, s_warp, &tot);
+        ecarry += tot;
+        if (i < n_super) super_offsets[g] = start;
+        const uint32_t chunks = (n + kCoarseChunk - 1) / kCoarseChunk;
+        if (chunks) {
+            const uint32_t base = atomicAdd(&head[kHeadItems], chunks);
+            if (base + chunks <= item_capacity) {
+                for (uint32_t c = 0; c < chunks; c++) items[base + c] = make_uint2(g, c);
+            } else {
+                head[kHeadItemOverflow] = 1u;
+            }
+        }
+    }
+    if (view == (int)gridDim.x - 1 && t == 0 && entries_out) *entries_out = ecarry;
+}
+
+// Coarse scatter: the (view, Gaussian) pairs grouped by super-tile.  Same CTA shape as the count kernel; per touched
+// super-tile one 16-byte entry (value, depth bits, tile rect clipped to the super-tile packed as x0 | y0 << 8 | x1 << 16 |
+// y1 << 24, view) at the next slot of the group's run.
+__global__ void __launch_bounds__(kBlock)
+coarse_scatter_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+                      const float* __restrict__ depth, const uint32_t* __restrict__ super_offsets,
+                      uint32_t* __restrict__ super_cursor, uint4* __restrict__ entries)
+{
+    extern __shared__ uint32_t s_enum[];
+    const int nsx = supers_x(prm), n_super = nsx * supers_y(prm);
+    uint32_t* s_cnt = s_enum;             // [n_super]
+    uint32_t* s_base = s_enum + n_super;  // [n_super]
+    const int view = blockIdx.y;
+    const int first = blockIdx.x * (kBlock * kEnumItems) + threadIdx.x;
+    for (int i = threadIdx.x; i < n_super; i += kBlock) s_cnt[i] = 0u;
+    __syncthreads();
+    for (int k = 0; k < kEnumItems; k++) {
+        const int idx = first + k * kBlock;
+        int x0, y0, x1, y1;
+        if (load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+        for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
+            for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) atomicAdd(&s_cnt[sy * nsx + sx], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_super; i += kBlock) {
+        const uint32_t c = s_cnt[i];
+        const size_t g = (size_t)view * n_super + i;
+        if (c) s_base[i] = super_offsets[g] + atomicAdd(&super_cursor[g], c);
+        s_cnt[i] = 0u;
+    }
+    __syncthreads();
+    for (int k = 0; k < kEnumItems; k++) {
+        const int idx = first + k * kBlock;
+        const size_t gi = (size_t)view * prm.P + idx;
+        int x0, y0, x1, y1;
+        if (load_rect(prm, radii, xy, gi, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+        const uint32_t dbits = __float_as_uint(depth[gi]);
+        for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
+            for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) {
+                const int s = sy * nsx + sx;
+                const int cx0 = max(x0, sx << kSuperShift), cx1 = min(x1, (sx + 1) << kSuperShift);
+                const int cy0 = max(y0, sy << kSuperShift), cy1 = min(y1, (sy + 1) << kSuperShift);
+                const uint32_t rect = (uint32_t)cx0 | (uint32_t)cy0 << 8 | (uint32_t)cx1 << 16 | (uint32_t)cy1 << 24;
+                entries[s_base[s] + atomicAdd(&s_cnt[s], 1u)] = make_uint4((uint32_t)gi, dbits, rect, (uint32_t)view);
+            }
+    }
+}
+
+// Fine scatter from the grouped entries.  Persistent CTAs pull (group, chunk) work items; all entries of an item lie in
+// ONE super-tile, so the CTA's histogram has 64 counters and its stores go to the 64 tile segments of that super-tile in
+// long runs.  Same reservation protocol as the plain scatter (counts[] counted down by the CTA's number).
+__global__ void __launch_bounds__(kBlock, 4)
+tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ entries, const uint32_t* __restrict__ super_offsets,
+                            const uint32_t* __restrict__ super_counts, const uint2* __restrict__ items,
+                            const uint32_t* __restrict__ head, uint32_t* __restrict__ item_cursor, uint32_t* __restrict__ counts,
+                            const uint2* __restrict__ ranges, uint2* __restrict__ pairs)
+{
+    constexpr int kFine = kSuperTiles * kSuperTiles;
+    __shared__ uint32_t s_cnt[kFine], s_base[kFine];
+    __shared__ uint32_t s_item;
+    const int nsx = supers_x(prm), n_super = nsx * supers_y(prm);
+    const uint32_t n_items = head[kHeadItems];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(item_cursor, 1u);
+        if (threadIdx.x < kFine) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint2 it = items[item];
+        const uint32_t g = it.x;
+        const int view = (int)(g / (uint32_t)n_super), s = (int)(g - (uint32_t)view * (uint32_t)n_super);
+        const int sx0 = (s % nsx) << kSuperShift, sy0 = (s / nsx) << kSuperShift;
+        const uint32_t e0 = super_offsets[g] + it.y * kCoarseChunk;
+        const uint32_t n = min((uint32_t)kCoarseChunk, super_counts[g] - it.y * kCoarseChunk);
+        const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
+        // two sweeps over the item's entries (L1-resident, 32 KB): count per fine tile, then place.  A warp walks 32 entries
+        // at a time; every entry's rect (<= 64 tiles, ~12 on average) is enumerated by the whole warp when it is large
+#pragma unroll 1
+        for (int sweep = 0; sweep < 2; sweep++) {
+            for (uint32_t i0 = 0; i0 < n; i0 += kBlock) {
+                const uint32_t i = i0 + threadIdx.x;
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n) e = __ldg(entries + e0 + i);
+                const int x0 = (int)(e.z & 255u) - sx0, y0 = (int)((e.z >> 8) & 255u) - sy0;
+                const int w = (int)((e.z >> 16) & 255u) - sx0 - x0, h = (int)(e.z >> 24) - sy0 - y0;
+                const uint32_t area = i < n ? (uint32_t)(w * h) : 0u;
+                const bool big = area > kCoopAreaD;
+                if (area != 0u && !big) {
+                    for (int y = y0; y < y0 + h; y++)
+                        for (int x = x0; x < x0 + w; x++) {
+                            const int f = y * kSuperTiles + x;
+                            if (sweep == 0) atomicAdd(&s_cnt[f], 1u);
+                            else pairs[s_base[f] + atomicAdd(&s_cnt[f], 1u)] = make_uint2(e.x, e.y);
+                        }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, big);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t a = __shfl_sync(0xffffffffu, area, src);
+                    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+                    const uint32_t bw = (uint32_t)__shfl_sync(0xffffffffu, w, src);
+                    const uint32_t sv = __shfl_sync(0xffffffffu, e.x, src), sd = __shfl_sync(0xffffffffu, e.y, src);
+                    for (uint32_t q = lane; q < a; q += 32) {
+                        const uint32_t ry = q / bw, rx = q - ry * bw;
+                        const int f = (by0 + (int)ry) * kSuperTiles + bx0 + (int)rx;
+                        if (sweep == 0) atomicAdd(&s_cnt[f], 1u);
+                        else pairs[s_base[f] + atomicAdd(&s_cnt[f], 1u)] = make_uint2(sv, sd);
+                    }
+                }
+            }
+            __syncthreads();
+            if (sweep == 0) {
+                if (threadIdx.x < kFine) {
+                    const uint32_t c = s_cnt[threadIdx.x];
+                    const int fx = sx0 + (threadIdx.x & (kSuperTiles - 1)), fy = sy0 + (threadIdx.x >> kSuperShift);
+                    if (c) {  // (c != 0 implies the tile exists: rects are clipped to the tile grid)
+                        const uint32_t gt = tile_base + (uint32_t)(fy * prm.gx + fx);
+                        s_base[threadIdx.x] = ranges[gt].x + atomicSub(&counts[gt], c) - c;
+                    }
+                    s_cnt[threadIdx.x] = 0u;
+                }
+                __syncthreads();
+            }
+        }
     }
 }
 
@@ -350,9 +584,14 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
 
 int direct_bin_tile_cap() { return kSortCapL; }
 
-// scratch of the direct path: head [64 u32] | view totals [n_views, padded to 64] | counts [n_ranges] | list [n_ranges]
+// scratch of the direct path.  Zeroed at the head of every step: head [64 u32] | view totals [nv] | view entries [nv] |
+// counts [n_ranges] | super counts [n_groups] | super cursor [n_groups]; not zeroed: list [n_ranges] | list_x [n_ranges] |
+// super offsets [n_groups] | items [item_capacity x uint2]
 struct DirectScratch {
-    uint32_t *head, *view_totals, *counts, *list;
+    uint32_t *head, *view_totals, *view_entries, *counts, *super_counts, *super_cursor, *list, *list_x, *super_offsets;
+    uint2* items;
+    uint32_t item_capacity, n_super;
+    bool coarse;  // whether the coarse grouping can be used at all for this shape
     size_t zero_bytes, total_bytes;
 };
 static DirectScratch direct_scratch(const RenderParams& prm, void* scratch)
@@ -360,62 +599,122 @@ static DirectScratch direct_scratch(const RenderParams& prm, void* scratch)
     const size_t n_ranges = (size_t)prm.n_views * prm.n_tiles;
     const size_t nv = ((size_t)prm.n_views + 63) / 64 * 64;
     DirectScratch d;
+    d.n_super = (uint32_t)(supers_x(prm) * supers_y(prm));
+    // packed 8-bit rect coordinates and the per-CTA shared-memory stage bound the shapes the grouping serves
+    d.coarse = prm.gx <= 255 && prm.gy <= 255 && d.n_super <= kCoarseMaxSupers && prm.n_tiles <= kEnumMaxTiles;
+    const size_t n_groups = ((size_t)prm.n_views * d.n_super + 63) / 64 * 64;
+    d.item_capacity = (uint32_t)(((size_t)prm.n_views * prm.P * 4) / kCoarseChunk + n_groups);
     d.head = static_cast<uint32_t*>(scratch);
     d.view_totals = d.head + 64;
-    d.counts = d.view_totals + nv;
-    d.list = d.counts + n_ranges;
-    d.zero_bytes = (64 + nv + n_ranges) * sizeof(uint32_t);  // head, view totals, counts
-    d.total_bytes = (64 + nv + 2 * n_ranges) * sizeof(uint32_t) + 256;
+    d.view_entries = d.view_totals + nv;
+    d.counts = d.view_entries + nv;
+    d.super_counts = d.counts + n_ranges;
+    d.super_cursor = d.super_counts + n_groups;
+    d.list = d.super_cursor + n_groups;
+    d.list_x = d.list + n_ranges;
+    d.super_offsets = d.list_x + n_ranges;
+    uint32_t* end = d.super_offsets + n_groups;
+    end += (8 - ((size_t)(end - d.head) & 7)) & 7;  // items are 8-byte aligned (the scratch itself is 256-byte aligned)
+    d.items = reinterpret_cast<uint2*>(end);
+    d.zero_bytes = (size_t)(d.list - d.head) * sizeof(uint32_t);
+    d.total_bytes = (size_t)(end - d.head) * sizeof(uint32_t) + (size_t)d.item_capacity * sizeof(uint2) + 256;
     return d;
 }
 
 size_t direct_bin_scratch_bytes(const RenderParams& prm) { return direct_scratch(prm, nullptr).total_bytes; }
 
-// D1 + D2: after this, ranges[] is final for the direct path and *longest_out (device, zeroed here) holds the longest
-// tile.  `scratch` as direct_bin_scratch_bytes; it must reach launch_direct_bin_sort untouched.
+// D1 + D2: after this, ranges[] is final for the direct path, *longest_out (device, zeroed here) holds the longest
+// tile and *entries_out the number of coarse entries (0 when the shape does not allow the grouping).  `scratch` as
+// direct_bin_scratch_bytes; it must reach launch_direct_bin_sort untouched.
+// minimum instances per coarse entry from which the grouping is used (lgm_set_tuning "coarse_ratio"; 0 = never)
+static uint64_t coarse_ratio()
+{
+    const int t = tuning(kTuneCoarseRatio);
+    return t >= 0 ? (uint64_t)t : 6;
+}
+
 cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
-                                    uint2* ranges, void* scratch, uint32_t* longest_out)
+                                    uint2* ranges, void* scratch, uint32_t* longest_out, uint32_t* entries_out,
+                                    const unsigned long long* total_instances)
 {
     const DirectScratch d = direct_scratch(prm, scratch);
     cudaError_t err = cudaMemsetAsync(scratch, 0, d.zero_bytes, stream);
     if (err != cudaSuccess) return err;
     if (longest_out && (err = cudaMemsetAsync(longest_out, 0, sizeof(uint32_t), stream)) != cudaSuccess) return err;
-    if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, d.counts, d.view_totals, nullptr, nullptr)) != cudaSuccess)
+    if (entries_out && (err = cudaMemsetAsync(entries_out, 0, sizeof(uint32_t), stream)) != cudaSuccess) return err;
+    const bool coarse = d.coarse && entries_out != nullptr && total_instances != nullptr && enumerate_in_smem(prm) && coarse_ratio() != 0;
+    // device-side gate: entries <= pairs, so a step with fewer than (ratio - 1) instances per pair is unlikely to reach
+    // `ratio` instances per entry
+    if ((err = launch_tile_enumerate<false>(stream, prm, radii, xy, nullptr, d.counts, d.view_totals, nullptr, nullptr,
+                                            coarse ? d.super_counts : nullptr, d.view_entries, total_instances,
+                                            coarse_ratio() - (coarse_ratio() != 0))) != cudaSuccess)
         return err;
-    tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(d.counts, d.view_totals, prm.n_tiles,
-                                                                (uint32_t)prm.n_views * (uint32_t)prm.n_tiles, ranges, d.list, d.head,
-                                                                longest_out);
+    tile_ranges_scan_kernel<<<prm.n_views, kBlock, 0, stream>>>(
+        d.counts, d.view_totals, prm.n_tiles, (uint32_t)prm.n_views * (uint32_t)prm.n_tiles, ranges, d.list, d.list_x, d.head, longest_out,
+        coarse ? d.super_counts : nullptr, d.view_entries, (int)d.n_super, d.super_offsets, d.items, d.item_capacity, entries_out);
     return cudaGetLastError();
 }
 
+// Whether a step with these counts takes the coarse grouping: large footprints (instances per entry) — the regime in
+// which the plain scatter's 8-byte stores spread over thousands of segments — and the entries fit the buffer.
+bool direct_bin_use_coarse(const RenderParams& prm, uint64_t n_instances, uint64_t coarse_entries)
+{
+    const DirectScratch d = direct_scratch(prm, nullptr);
+    if (!d.coarse || !enumerate_in_smem(prm) || coarse_entries == 0) return false;
+    if (coarse_entries > (uint64_t)prm.n_views * prm.P * 4) return false;  // the work-item list was sized for this bound
+    const uint64_t ratio = coarse_ratio();
+    return ratio != 0 && n_instances >= ratio * coarse_entries;
+}
+
 // D3 + D4.  pairs: L x 8 B of workspace.  keys_sorted may be null (keys not wanted).  longest_tile: the value read back
-// after launch_direct_bin_count (decides whether the L-class launch is needed).
+// after launch_direct_bin_count (decides which size classes are launched).  entries != null: coarse grouping first
+// (entry buffer of coarse_entries x 16 B), then the fine scatter from the grouped entries.
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
-                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile)
+                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile, void* entries)
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
     const DirectScratch d = direct_scratch(prm, scratch);
     auto* sort_m = tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3>;
+    auto* sort_x = tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2>;
     auto* sort_l = tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1>;
-    constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_l = sort_smem(kSortCapL, kLgBucketsL);
-    static std::atomic<uint64_t> opted_m{0}, opted_l{0};
+    constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_x = sort_smem(kSortCapX, kLgBucketsX),
+                     smem_l = sort_smem(kSortCapL, kLgBucketsL);
+    static std::atomic<uint64_t> opted_m{0}, opted_x{0}, opted_l{0};
     if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted_m)) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted_x)) return e;
     if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted_l)) return e;
     const int n_sm = device_sm_count();
-    cudaError_t err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, ranges,
-                                                  static_cast<uint2*>(pairs));
+    cudaError_t err;
+    if (entries) {
+        dim3 grid(enum_ctas_per_view(prm), prm.n_views);
+        coarse_scatter_kernel<<<grid, kBlock, (size_t)d.n_super * 8, stream>>>(prm, radii, xy, depth, d.super_offsets, d.super_cursor,
+                                                                               static_cast<uint4*>(entries));
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+        tile_scatter_entries_kernel<<<4 * n_sm, kBlock, 0, stream>>>(prm, static_cast<const uint4*>(entries), d.super_offsets,
+                                                                     d.super_counts, d.items, d.head, d.head + kHeadItemCursor, d.counts,
+                                                                     ranges, static_cast<uint2*>(pairs));
+        err = cudaGetLastError();
+    } else {
+        err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, ranges, static_cast<uint2*>(pairs));
+    }
     if (err != cudaSuccess) return err;
     // the long tiles first: they are the critical path of the tail
-    if (longest_tile > (uint32_t)kSortCapM) {
+    if (longest_tile > (uint32_t)kSortCapX) {
         const uint32_t n_cta = (uint32_t)min((unsigned)n_sm, n_ranges);
         sort_l<<<n_cta, kSortThreadsL, smem_l, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list + (n_ranges - 1), -1,
-                                                        d.head + 3, d.head + 4, vals_sorted, keys_sorted);
+                                                        d.head + kHeadL, d.head + kHeadLCursor, vals_sorted, keys_sorted);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    if (longest_tile > (uint32_t)kSortCapM) {
+        const uint32_t n_cta = (uint32_t)min((unsigned)(2 * n_sm), n_ranges);
+        sort_x<<<n_cta, kSortThreadsX, smem_x, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list_x, 1, d.head + kHeadX,
+                                                        d.head + kHeadXCursor, vals_sorted, keys_sorted);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
-    sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head, d.head + 1,
-                                                    vals_sorted, keys_sorted);
+    sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head + kHeadM,
+                                                    d.head + kHeadMCursor, vals_sorted, keys_sorted);
     return cudaGetLastError();
 }
 

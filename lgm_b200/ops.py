@@ -20,7 +20,7 @@ MAX_VIEWS_PER_CALL = 65535          # the per-(view, Gaussian) kernels put the v
 # launch accounting for bench.py's "gpu_launches" (kernels this library enqueues; memsets not counted)
 launch_counter = {"kernels": 0}
 BIN_MODES = {0: "none", 1: "onesweep", 2: "hybrid", 3: "direct"}
-last_bin_mode = {"mode": "none"}
+last_bin_mode = {"mode": "none", "coarse": False}
 
 # Optional per-stage CUDA-event timing (bench.py's stage breakdown; off in normal use).  When enabled, every stage
 # call is bracketed by events on the launching stream; read with stage_times_ms() after a synchronize.
@@ -145,13 +145,14 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     st.n_contrib = torch.empty(VW, H, W, dtype=torch.int32, device=dev)
     # THE host<->device synchronisation of the step (upstream: one per view): 16 bytes — the instance count sizes the
     # instance buffers, the longest tile selects the binning path.  Nothing inside the library synchronises.
-    n_inst, longest = (int(v) for v in counts.tolist())
-    longest = (longest & 0xFFFFFFFF) if count_ws is not None else -1
+    n_inst, word = (int(v) for v in counts.tolist())
+    longest = (word & 0xFFFFFFFF) if count_ws is not None else -1
+    coarse_entries = ((word >> 32) & 0xFFFFFFFF) if count_ws is not None else 0
     st.num_rendered = n_inst
     if n_inst > MAX_INSTANCES:
         raise TooManyInstances(n_inst)
     ws_bytes = _lib._sz(0)
-    _lib.check(L.lgm_bin_workspace_bytes(prm, n_inst, ws_bytes), "lgm_bin_workspace_bytes")
+    _lib.check(L.lgm_bin_workspace_bytes(prm, n_inst, coarse_entries, ws_bytes), "lgm_bin_workspace_bytes")
     # the direct path (every tile fits its shared-memory sort) orders the instances without a key buffer
     direct = count_ws is not None and 0 <= longest <= int(L.lgm_direct_bin_tile_cap())
     keys = None if (direct and not cfg.keep_binning) else torch.empty(max(n_inst, 1), dtype=torch.int64, device=dev)
@@ -159,7 +160,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     workspace = torch.empty(max(int(ws_bytes.value), 1), dtype=torch.uint8, device=dev)
     # (lgm_forward_bin_render is these two calls back to back; split here so that stages can be timed)
     _timed("bin", lambda: _lib.check(L.lgm_forward_bin(
-        s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, longest, bin_mode,
+        s, prm, _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.depth), _lib.ptr(block_offsets), n_inst, longest, coarse_entries, bin_mode,
         _lib.ptr(keys), _lib.ptr(st.vals), _lib.ptr(st.ranges), _lib.ptr(workspace), workspace.numel(), _lib.ptr(count_ws),
         1 if cfg.keep_binning else 0), "lgm_forward_bin"))
     _timed("composite_fwd", lambda: _lib.check(L.lgm_forward_composite(
@@ -169,8 +170,9 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
     if n_inst > 0:
         mode = int(L.lgm_last_bin_mode())
         last_bin_mode["mode"] = BIN_MODES.get(mode, "none")
-        if mode == 3:    # scatter, tile sort (one or two size classes); count + ranges scan were counted above
-            launch_counter["kernels"] += 3 if longest > 5632 else 2
+        if mode == 3:    # scatter (plain, or coarse grouping + fine scatter), tile sort (one to three size classes)
+            last_bin_mode["coarse"] = bool(L.lgm_last_bin_coarse())
+            launch_counter["kernels"] += (2 if last_bin_mode["coarse"] else 1) + 1 + (longest > 5632) + (longest > 9216)
         elif mode == 2:  # emit, histogram, tile-bit passes, ranges, short + long tile sort
             launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
         else:            # emit, histogram, ranges + onesweep passes

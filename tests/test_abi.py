@@ -56,16 +56,16 @@ def test_size_queries_and_errors(lib):
     assert lib.lgm_num_block_sums(98304, 208) == 208 * 384 and lib.lgm_num_block_sums(257, 3) == 6
     b = ctypes.c_size_t(0)
     ok = _lib.make_params(8, 98304, 208, 320, 320, 0.577, 0.577, 1.0)
-    assert lib.lgm_bin_workspace_bytes(ok, 1_000_000, b) == 0 and b.value >= 12_000_000
-    assert lib.lgm_bin_workspace_bytes(ok, 1 << 30, b) == -4  # LGM_ERR_TOO_MANY_INSTANCES
+    assert lib.lgm_bin_workspace_bytes(ok, 1_000_000, 0, b) == 0 and b.value >= 12_000_000
+    assert lib.lgm_bin_workspace_bytes(ok, 1 << 30, 0, b) == -4  # LGM_ERR_TOO_MANY_INSTANCES
     assert b"2^30" in lib.lgm_last_error_string()
     bad = _lib.make_params(8, 98304, 208, 0, 320, 0.577, 0.577, 1.0)
-    assert lib.lgm_bin_workspace_bytes(bad, 10, b) == -2      # LGM_ERR_BAD_SHAPE
+    assert lib.lgm_bin_workspace_bytes(bad, 10, 0, b) == -2      # LGM_ERR_BAD_SHAPE
     bad = _lib.make_params(8, 98304, 208, 320, 320, 0.0, 0.577, 1.0)
-    assert lib.lgm_bin_workspace_bytes(bad, 10, b) == -5      # LGM_ERR_BAD_VALUE
-    assert lib.lgm_bin_workspace_bytes(None, 10, b) == -1     # LGM_ERR_NULL_POINTER
+    assert lib.lgm_bin_workspace_bytes(bad, 10, 0, b) == -5      # LGM_ERR_BAD_VALUE
+    assert lib.lgm_bin_workspace_bytes(None, 10, 0, b) == -1     # LGM_ERR_NULL_POINTER
     huge = _lib.make_params(1, 1 << 30, 8, 320, 320, 0.5, 0.5, 1.0)
-    assert lib.lgm_bin_workspace_bytes(huge, 10, b) == -2
+    assert lib.lgm_bin_workspace_bytes(huge, 10, 0, b) == -2
     assert lib.lgm_sort_workspace_bytes(4096 * 3 + 1, 49, b) == 0 and b.value >= 7 * 4 * 256 * 4
     assert lib.lgm_sort_workspace_bytes(10, 65, b) == -5
     assert lib.lgm_sort_input_is_tmp(48) == 0 and lib.lgm_sort_input_is_tmp(49) == 1
@@ -80,9 +80,9 @@ def test_size_queries_and_errors(lib):
     assert lib.lgm_count_workspace_bytes(ok, b) == 0 and b.value >= 2 * 4 * 208 * 400
     assert lib.lgm_direct_bin_tile_cap() == 20480
     assert lib.lgm_forward_count(None, ok, None, None, None, None, 0, None) == -1
-    assert lib.lgm_forward_bin(None, ok, None, None, None, None, 10, -1, 7, None, None, None, None, 0, None, 0) == -5  # bin_mode
+    assert lib.lgm_forward_bin(None, ok, None, None, None, None, 10, -1, 0, 7, None, None, None, None, 0, None, 0) == -5  # bin_mode
     too_many_views = _lib.make_params(1, 16, 65536, 32, 32, 0.5, 0.5, 1.0)
-    assert lib.lgm_bin_workspace_bytes(too_many_views, 10, b) == -2 and b"65535" in lib.lgm_last_error_string()
+    assert lib.lgm_bin_workspace_bytes(too_many_views, 10, 0, b) == -2 and b"65535" in lib.lgm_last_error_string()
     assert lib.lgm_set_tuning(b"fwd_batch", 256) == 0 and lib.lgm_set_tuning(b"fwd_batch", -1) == 0
     assert lib.lgm_set_tuning(b"no_such_knob", 1) == -5
     assert lib.lgm_activate_forward(None, 2, 100, None, None, 0, None) == -1   # reference axis needs its scratch

@@ -488,7 +488,8 @@ def _bin_result(monkeypatch, mode, g, cv, cvp, S):
     _, _, _, _, img, al, dp, st = _cuda_forward(g, cv, cvp, [0.5, 0.5, 0.5], S, S, t, t)
     L = st.num_rendered
     return dict(keys=st.keys[:L].clone(), vals=st.vals[:L].clone(), ranges=st.ranges.clone(), img=img.clone(),
-                longest=int((st.ranges[:, 1] - st.ranges[:, 0]).max()), ran=ops.last_bin_mode["mode"], L=L)
+                longest=int((st.ranges[:, 1] - st.ranges[:, 0]).max()), ran=ops.last_bin_mode["mode"], L=L,
+                coarse=ops.last_bin_mode["coarse"])
 
 
 def _same_binning(a, b):
@@ -501,7 +502,7 @@ def test_binning_modes_are_bit_identical(monkeypatch):
     same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632 and L-class
     tiles <= 20,480 instances); direct hands a step whose longest tile exceeds its shared-memory capacity to onesweep."""
     seen, lens = set(), []
-    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 60000, 64), ("init", 120000, 32)):
+    for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 25000, 160), ("init", 60000, 64), ("init", 120000, 32)):
         g = make_gaussians(2, N, kind, seed=17).numpy()
         cv, cvp, _ = make_cameras(2, 2, seed=17)
         res = {m: _bin_result(monkeypatch, m, g, cv, cvp, S) for m in ("onesweep", "hybrid", "direct", "auto")}
@@ -512,9 +513,19 @@ def test_binning_modes_are_bit_identical(monkeypatch):
         assert res["direct"]["ran"] == ("direct" if longest <= 20480 else "onesweep"), (longest, res["direct"]["ran"])
         if kind == "trained":
             assert res["auto"]["ran"] == "direct"
-        seen.add("M" if longest <= 5632 else ("L" if longest <= 20480 else "handover"))
+        seen.add("M" if longest <= 5632 else ("X" if longest <= 9216 else ("L" if longest <= 20480 else "handover")))
         lens.append(longest)
-    assert seen == {"M", "L", "handover"}, (seen, lens)  # every size class and the hand-over were exercised
+        # the coarse grouping of the direct path (pairs grouped by 8x8-tile super-tile before the scatter): forced on
+        # (LGM_COARSE_RATIO=1: whenever there is an entry) and off (0); the default takes it from 6 instances per entry
+        if longest <= 20480:
+            monkeypatch.setenv("LGM_COARSE_RATIO", "1")
+            c1 = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
+            monkeypatch.setenv("LGM_COARSE_RATIO", "0")
+            c0 = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
+            monkeypatch.delenv("LGM_COARSE_RATIO")
+            assert c1["coarse"] and not c0["coarse"], (kind, N, c1["coarse"], c0["coarse"])
+            assert _same_binning(res["onesweep"], c1) and _same_binning(res["onesweep"], c0), f"{kind} N={N}: coarse grouping differs"
+    assert seen >= {"M", "L", "handover"}, (seen, lens)  # the size classes and the hand-over were exercised
 
 
 def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
