@@ -25,7 +25,7 @@ constexpr int kBlock2 = 128;      // 4 warps x (8x8 pixels)
 // 4.96 / 5.25 / 6.43 ms (larger batches cost resident CTAs: 48 B of shared memory per staged Gaussian)
 constexpr int kFwdBatch2 = 256;
 constexpr int kBwdBatch2 = 384;
-constexpr int kMaxBatch2 = 2048;
+constexpr int kFwdOcc2 = 10, kBwdOcc2 = 8;  // resident CTAs per SM the kernels are compiled for (launch bounds)
 // A pixel that has stopped (or lies outside the image) is parked at row 1e18: its dy is astronomically large, so the
 // Gaussian's exponent is hugely negative (conics are >= ~1e-7), alpha underflows to 0 and the reference's own
 // "alpha < 1/255 -> skip" test rejects the pair — no `done` flag in the inner loop.  (A non-positive-definite conic gives
@@ -80,6 +80,32 @@ __device__ __forceinline__ float2 exp_fast2(float2 x)
     return r;
 }
 
+// Staging buffer as four arrays (conflict-free 16-byte stores: a 48-byte record stride would serialise every STS.128
+// four ways), 52 B per staged Gaussian: p0[], p1[], rgbd[] as the fields of Staged, mask[] = the patch mask on its own.
+constexpr int kStagedBytes2 = 3 * 16 + 4;
+// BATCH is a compile-time constant so that the three other arrays are immediate offsets from one base register.
+template <int BATCH>
+struct Staging2 {
+    float4* p0;
+    float4* const p1;
+    float4* const rgbd;
+    uint32_t* const mask;
+    __device__ __forceinline__ Staging2(unsigned char* base)
+        : p0(reinterpret_cast<float4*>(base)), p1(p0 + BATCH), rgbd(p0 + 2 * BATCH), mask(reinterpret_cast<uint32_t*>(p0 + 3 * BATCH)) {}
+    template <bool DEPTH>
+    __device__ __forceinline__ void stage(int k, uint32_t g, uint32_t view_base, const float* __restrict__ scene_g,
+                                          const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
+                                          const float* __restrict__ depth, float tile_x0, float tile_y0) const
+    {
+        Staged r;
+        stage_one<64, DEPTH>(r, g, view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+        p0[k] = r.p0;
+        p1[k] = r.p1;
+        rgbd[k] = r.rgbd;
+        mask[k] = __float_as_uint(r.p1.w);
+    }
+};
+
 // this lane's pixels: column x, rows y0 and y0 + 4 of the warp's 8x8 patch
 __device__ __forceinline__ void pixels_of_lane(int tile_x, int tile_y, int& px, int& py0)
 {
@@ -88,17 +114,18 @@ __device__ __forceinline__ void pixels_of_lane(int tile_x, int tile_y, int& px, 
     py0 = tile_y * kTile + (warp >> 1) * 8 + (lane >> 3);
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(kBlock2, 8)
+template <bool DEPTH, int MINB, int BATCH>
+__global__ void __launch_bounds__(kBlock2, MINB)
 composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                       const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                       const float* __restrict__ depth, const uint32_t* __restrict__ vals,
-                      const uint2* __restrict__ ranges, const float* __restrict__ bg, int clamp_image, int batch,
+                      const uint2* __restrict__ ranges, const float* __restrict__ bg, int clamp_image,
                       float* __restrict__ image, float* __restrict__ alpha_img, float* __restrict__ depth_img,
                       uint32_t* __restrict__ n_contrib)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
+    const Staging2<BATCH> sb(smem_raw);
+    constexpr int batch = BATCH;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gt = blockIdx.x;
@@ -127,17 +154,17 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         if (__syncthreads_count(LGM_BOTH_PARKED) == kBlock2) break;  // also the barrier that protects the staging buffer
         const int nb = min(batch, todo - r0);
         for (int k = threadIdx.x; k < nb; k += kBlock2)
-            stage_one<64, DEPTH>(s_rec[k], vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+            sb.template stage<DEPTH>(k, vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             if (__all_sync(0xffffffffu, LGM_BOTH_PARKED)) break;  // every pixel of the warp's patch is saturated (or outside)
             const int jl = base + lane;
-            unsigned m = __ballot_sync(0xffffffffu, jl < nb && ((__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u));
+            unsigned m = __ballot_sync(0xffffffffu, jl < nb && ((sb.mask[jl] >> warp) & 1u));
             while (m != 0u) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
-                const float4 p0 = s_rec[j].p0;
-                const float4 p1 = s_rec[j].p1;
+                const float4 p0 = sb.p0[j];
+                const float4 p1 = sb.p1[j];
                 const float dx = LGM_SUB(p0.x, pfx);
                 const float2 dy = add2(bc(p0.y), npfy);
                 const float2 power = pair_power2(p0.z, p0.w, p1.x, dx, dy);
@@ -153,7 +180,7 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                 npfy.x = stop0 ? -kParked : npfy.x;
                 npfy.y = stop1 ? -kParked : npfy.y;
                 if (!__any_sync(0xffffffffu, comp0 || comp1)) continue;
-                const float4 cd = s_rec[j].rgbd;
+                const float4 cd = sb.rgbd[j];
                 const float2 ae = make_float2(comp0 ? a.x : 0.0f, comp1 ? a.y : 0.0f);
                 C0 = fma2(mul2(bc(cd.x), ae), T, C0);
                 C1 = fma2(mul2(bc(cd.y), ae), T, C1);
@@ -196,18 +223,19 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     }
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(kBlock2, 6)
+template <bool DEPTH, int MINB, int BATCH>
+__global__ void __launch_bounds__(kBlock2, MINB)
 composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
                       const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
                       const float* __restrict__ depth, const uint32_t* __restrict__ vals,
                       const uint2* __restrict__ ranges, const float* __restrict__ bg,
                       const float* __restrict__ alpha_img, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
-                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows, int batch)
+                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Staged* s_rec = reinterpret_cast<Staged*>(smem_raw);
+    const Staging2<BATCH> sb(smem_raw);
+    constexpr int batch = BATCH;
     __shared__ uint32_t s_max[kBlock2 / 32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -271,8 +299,8 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         const int nb = min(batch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
         for (int k = threadIdx.x; k < nb; k += kBlock2)
-            stage_one<64, DEPTH>(s_rec[k], vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity,
-                                 depth, tile_x0, tile_y0);
+            sb.template stage<DEPTH>(k, vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
+                                     tile_x0, tile_y0);
         __syncthreads();
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
@@ -280,15 +308,15 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
             bool cand = false;
             if (jl < nb) {
                 const uint32_t pos_l = (uint32_t)(todo - 1 - (r0 + jl));
-                cand = ((__float_as_uint(s_rec[jl].p1.w) >> warp) & 1u) && pos_l < wmax;
+                cand = ((sb.mask[jl] >> warp) & 1u) && pos_l < wmax;
             }
             unsigned m = __ballot_sync(0xffffffffu, cand);
             while (m != 0u) {
                 const int j = base + __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t pos = (uint32_t)(todo - 1 - (r0 + j));
-                const float4 p0 = s_rec[j].p0;
-                const float4 p1 = s_rec[j].p1;
+                const float4 p0 = sb.p0[j];
+                const float4 p1 = sb.p1[j];
                 const float dx = LGM_SUB(p0.x, pfx);
                 const float2 dy = add2(bc(p0.y), npfy);
                 const float2 power = pair_power2(p0.z, p0.w, p1.x, dx, dy);  // the forward's pinned decisions
@@ -303,7 +331,7 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                 // alpha = 0 and G = 0, which leaves its running state untouched and makes its ten terms exact zeros.  One
                 // scalar per pixel carries A.5's "colour behind" recursions (see composite.cu):
                 //   U <- U + a (c . dC + depth dD + dA - U),  dL/dalpha = (c . dC + depth dD + dA - U) T + bg-term,  T <- T / (1 - a)
-                const float4 cd = s_rec[j].rgbd;
+                const float4 cd = sb.rgbd[j];
                 const float2 ae = make_float2(valid0 ? a.x : 0.0f, valid1 ? a.y : 0.0f);
                 const float2 Gv = make_float2(valid0 ? G.x : 0.0f, valid1 ? G.y : 0.0f);
                 const float2 om = add2(bc(1.0f), neg2(ae));
@@ -350,14 +378,34 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     }
 }
 
-int batch2_or_default(Tuning which, int dflt)
+template <bool DEPTH, int MINB, int BATCH>
+cudaError_t run2_fwd(cudaStream_t stream, unsigned blocks, const RenderParams& prm, const float* gaussians,
+                     const int32_t* view_scene, const float2* xy, const float4* conic_opacity, const float* depth,
+                     const uint32_t* vals, const uint2* ranges, const float* bg, int clamp_image, float* image, float* alpha,
+                     float* depth_img, uint32_t* n_contrib)
 {
-    const int v = tuning(which);
-    return (v >= 32 && v <= kMaxBatch2 && v % 32 == 0) ? v : dflt;
+    composite2_fwd_kernel<DEPTH, MINB, BATCH><<<blocks, kBlock2, BATCH * kStagedBytes2, stream>>>(
+        prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, clamp_image, image, alpha, depth_img, n_contrib);
+    return cudaGetLastError();
+}
+
+template <bool DEPTH, int MINB, int BATCH>
+cudaError_t run2_bwd(cudaStream_t stream, unsigned blocks, const RenderParams& prm, const float* gaussians,
+                     const int32_t* view_scene, const float2* xy, const float4* conic_opacity, const float* depth,
+                     const uint32_t* vals, const uint2* ranges, const float* bg, const float* alpha, const uint32_t* n_contrib,
+                     const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth, float* grad_rows)
+{
+    composite2_bwd_kernel<DEPTH, MINB, BATCH><<<blocks, kBlock2, BATCH * kStagedBytes2, stream>>>(
+        prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth,
+        grad_rows);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
+// Launch shapes.  The staging batch and the resident CTAs per SM (launch bounds) are template parameters; lgm_set_tuning
+// "fwd_batch" / "bwd_batch" (256 | 384; 20 KB fit the default shared-memory limit) and "c2_occ" (100 x forward + backward
+// CTAs per SM) select among the instantiations.
 cudaError_t launch_composite2_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const int32_t* view_scene, const float2* xy, const float4* conic_opacity,
                                   const float* depth, const uint32_t* vals, const uint2* ranges, const float* bg,
@@ -365,21 +413,15 @@ cudaError_t launch_composite2_fwd(cudaStream_t stream, const RenderParams& prm, 
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int batch = batch2_or_default(kTuneFwdBatch, kFwdBatch2);
-    const int smem = batch * (int)sizeof(Staged);
-    static std::atomic<uint64_t> opted_d{0}, opted_n{0};
-    if (depth_img) {
-        if (cudaError_t e = opt_in_dynamic_smem(composite2_fwd_kernel<true>, kMaxBatch2 * sizeof(Staged), opted_d)) return e;
-        composite2_fwd_kernel<true><<<(unsigned)blocks, kBlock2, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                                ranges, bg, clamp_image, batch, image, alpha, depth_img,
-                                                                                n_contrib);
-    } else {
-        if (cudaError_t e = opt_in_dynamic_smem(composite2_fwd_kernel<false>, kMaxBatch2 * sizeof(Staged), opted_n)) return e;
-        composite2_fwd_kernel<false><<<(unsigned)blocks, kBlock2, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                                 ranges, bg, clamp_image, batch, image, alpha, depth_img,
-                                                                                 n_contrib);
-    }
-    return cudaGetLastError();
+    const int batch = tuning(kTuneFwdBatch) == 384 ? 384 : kFwdBatch2;
+    const int occ = tuning(kTuneC2Occ) >= 0 ? tuning(kTuneC2Occ) / 100 : kFwdOcc2;
+#define LGM_F(D, M, B) run2_fwd<D, M, B>(stream, (unsigned)blocks, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, \
+                                         clamp_image, image, alpha, depth_img, n_contrib)
+#define LGM_FB(D, M) (batch == 384 ? LGM_F(D, M, 384) : LGM_F(D, M, 256))
+    if (depth_img) return occ == 12 ? LGM_FB(true, 12) : (occ == 8 ? LGM_FB(true, 8) : LGM_FB(true, 10));
+    return occ == 12 ? LGM_FB(false, 12) : (occ == 8 ? LGM_FB(false, 8) : LGM_FB(false, 10));
+#undef LGM_FB
+#undef LGM_F
 }
 
 cudaError_t launch_composite2_bwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
@@ -390,21 +432,15 @@ cudaError_t launch_composite2_bwd(cudaStream_t stream, const RenderParams& prm, 
 {
     const size_t blocks = (size_t)prm.n_views * prm.n_tiles;
     if (blocks == 0) return cudaSuccess;
-    const int batch = batch2_or_default(kTuneBwdBatch, kBwdBatch2);
-    const int smem = batch * (int)sizeof(Staged);
-    static std::atomic<uint64_t> opted_d{0}, opted_n{0};
-    if (dL_ddepth) {
-        if (cudaError_t e = opt_in_dynamic_smem(composite2_bwd_kernel<true>, kMaxBatch2 * sizeof(Staged), opted_d)) return e;
-        composite2_bwd_kernel<true><<<(unsigned)blocks, kBlock2, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                                ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-                                                                                dL_ddepth, grad_rows, batch);
-    } else {
-        if (cudaError_t e = opt_in_dynamic_smem(composite2_bwd_kernel<false>, kMaxBatch2 * sizeof(Staged), opted_n)) return e;
-        composite2_bwd_kernel<false><<<(unsigned)blocks, kBlock2, smem, stream>>>(prm, gaussians, view_scene, xy, conic_opacity, depth, vals,
-                                                                                 ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha,
-                                                                                 dL_ddepth, grad_rows, batch);
-    }
-    return cudaGetLastError();
+    const int batch = tuning(kTuneBwdBatch) == 256 ? 256 : kBwdBatch2;
+    const int occ = tuning(kTuneC2Occ) >= 0 ? tuning(kTuneC2Occ) % 100 : kBwdOcc2;
+#define LGM_B(D, M, B) run2_bwd<D, M, B>(stream, (unsigned)blocks, prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, \
+                                         alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth, grad_rows)
+#define LGM_BB(D, M) (batch == 256 ? LGM_B(D, M, 256) : LGM_B(D, M, 384))
+    if (dL_ddepth) return occ == 10 ? LGM_BB(true, 10) : (occ == 6 ? LGM_BB(true, 6) : LGM_BB(true, 8));
+    return occ == 10 ? LGM_BB(false, 10) : (occ == 6 ? LGM_BB(false, 6) : LGM_BB(false, 8));
+#undef LGM_BB
+#undef LGM_B
 }
 
 }  // namespace lgm
