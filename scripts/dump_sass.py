@@ -17,9 +17,16 @@ KEEP = {  # demangled-name substring -> file tag
     "scan_block_sums_kernel": "scan_block_sums_kernel", "emit_kernel": "emit_kernel", "histogram_kernel": "histogram_kernel",
     "onesweep_kernel<512, 8, 2, false>": "onesweep_kernel", "tile_ranges_kernel": "tile_ranges_kernel",
     "tile_enumerate_kernel<false>": "tile_count_kernel", "tile_enumerate_kernel<true>": "tile_scatter_kernel",
-    "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel": "tile_bucket_sort_kernel",
-    "composite_fwd_kernel<32>": "composite_fwd_kernel", "composite_bwd_kernel<32, false>": "composite_bwd_kernel",
+    "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel<512, 5632, 11, 3>": "tile_bucket_sort_kernel",
+    "coarse_scatter_kernel": "coarse_scatter_kernel", "tile_scatter_entries_kernel": "tile_scatter_entries_kernel",
+    # the shipped compositing kernels (two pixels per lane, packed fp32): the instantiations LGM's training step runs
+    # (depth image computed in the forward as the reference does; no depth gradient in the backward)
+    "composite2_fwd_kernel<true, 10, 256>": "composite2_fwd_kernel", "composite2_fwd_kernel<false, 10, 256>": "composite2_fwd_kernel_nodepth",
+    "composite2_bwd_kernel<false, 8, 384>": "composite2_bwd_kernel", "composite2_bwd_kernel<true, 8, 384>": "composite2_bwd_kernel_depth",
+    # the one-pixel-per-lane kernels kept for comparison (LGM_PATCH_LANES=32)
+    "composite_fwd_kernel<32, true>": "composite1_fwd_kernel", "composite_bwd_kernel<32, false>": "composite1_bwd_kernel",
     "sh_forward_kernel": "sh_forward_kernel", "sh_backward_kernel": "sh_backward_kernel", "mse_loss_grad_kernel": "mse_loss_grad_kernel",
+    "activate_fwd_kernel": "activate_fwd_kernel", "rot_column_sums_kernel": "rot_column_sums_kernel",
 }
 
 
@@ -47,8 +54,9 @@ def main():
                 hist_lines.append(f"== {tag}  ({d[:100]})  {total} SASS instructions\n   " +
                                   "  ".join(f"{k}:{v}" for k, v in ops.most_common(24)) + "\n")
     with open(os.path.join(ROOT, "profiles", f"{prefix}_sass_opcode_histograms.txt"), "w") as f:
-        f.write("Static SASS opcode counts per kernel (cuobjdump -sass, sm_100a).  No UTC*MMA / HMMA / UTMALDG: the path has no\n"
-                "dense contraction and its staging is an indexed gather (see DESIGN.md §4).\n\n" + "\n".join(hist_lines))
+        f.write("Static SASS opcode counts per kernel (cuobjdump -sass, sm_100a).  The compositing kernels use the sm_100 packed fp32\n"
+                "instructions FFMA2 / FMUL2 / FADD2 (fma/mul/add.rn.f32x2).  No UTC*MMA / HMMA: the path has no dense contraction;\n"
+                "no UTMALDG / UBLKCP: its staging is an indexed gather (see DESIGN.md §4).\n\n" + "\n".join(hist_lines))
     missing = set(KEEP.values()) - done
     print("written:", sorted(done))
     if missing:
