@@ -99,8 +99,8 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L, uint64_t E)
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
 thread_local bool g_last_coarse = false;
 
-std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
-const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ"};
+std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ", "sort_bulk"};
 std::atomic<int> g_sm_count[lgm::kMaxDevices];
 
 }  // namespace

@@ -223,6 +223,35 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     }
 }
 
+// group_reduce_10<32> (composite_common.cuh) with the additions of its first two levels packed (FADD2): the same sums on
+// the same lanes.
+template <bool DEPTH>
+__device__ __forceinline__ void warp_reduce_10_packed(const float (&a)[8], const float (&b)[2], int lane, float& A, float& Bv)
+{
+    const unsigned full = 0xffffffffu;
+    const bool h1 = lane & 16, h2 = lane & 8, h3 = lane & 4;
+    float2 k01 = make_float2(h1 ? a[4] : a[0], h1 ? a[5] : a[1]), k23 = make_float2(h1 ? a[6] : a[2], h1 ? a[7] : a[3]);
+    const float s0 = h1 ? a[0] : a[4], s1 = h1 ? a[1] : a[5], s2 = h1 ? a[2] : a[6], s3 = h1 ? a[3] : a[7];
+    float bk = DEPTH ? (h1 ? b[1] : b[0]) : b[0];
+    const float bs = DEPTH ? (h1 ? b[0] : b[1]) : b[0];
+    k01 = add2(k01, make_float2(__shfl_xor_sync(full, s0, 16), __shfl_xor_sync(full, s1, 16)));
+    k23 = add2(k23, make_float2(__shfl_xor_sync(full, s2, 16), __shfl_xor_sync(full, s3, 16)));
+    bk += __shfl_xor_sync(full, bs, 16);  // DEPTH = false: a plain butterfly, all lanes end with sum b[0]
+    float2 m = h2 ? k23 : k01;
+    const float2 t = h2 ? k01 : k23;
+    m = add2(m, make_float2(__shfl_xor_sync(full, t.x, 8), __shfl_xor_sync(full, t.y, 8)));
+    bk += __shfl_xor_sync(full, bk, 8);
+    A = h3 ? m.y : m.x;
+    const float u = h3 ? m.x : m.y;
+    A += __shfl_xor_sync(full, u, 4);
+    bk += __shfl_xor_sync(full, bk, 4);
+    A += __shfl_xor_sync(full, A, 2);
+    bk += __shfl_xor_sync(full, bk, 2);
+    A += __shfl_xor_sync(full, A, 1);
+    bk += __shfl_xor_sync(full, bk, 1);
+    Bv = bk;
+}
+
 template <bool DEPTH, int MINB, int BATCH>
 __global__ void __launch_bounds__(kBlock2, MINB)
 composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
@@ -369,7 +398,7 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                     vb[1] = 0.0f;
                 }
                 float A, Bv;
-                group_reduce_10<32, DEPTH>(va, vb, lane, A, Bv);
+                warp_reduce_10_packed<DEPTH>(va, vb, lane, A, Bv);
                 // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
                 float* row = grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow;
                 if (a_sender || b_sender) atomicAdd(row + (a_sender ? a_slot : b_slot), a_sender ? A : Bv);

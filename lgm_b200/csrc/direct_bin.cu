@@ -39,7 +39,39 @@ constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 // global load / store phases overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians have most of their
 // instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
 constexpr int kSortThreadsX = 1024, kSortCapX = 9216, kLgBucketsX = 12;
-constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
+// (+ 16 B: the bulk copy of a segment starts at a 16-byte boundary, up to one pair before the segment, and ends at one)
+constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + 16 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
+
+// ---- 1-D bulk copy (TMA, cp.async.bulk) + mbarrier: the segment of a tile is contiguous in `pairs` ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 constexpr uint32_t kCoopAreaD = 12;  // as binning.cu: larger footprints are enumerated by the whole warp
 
 // Calls f(tile index inside the view, value, depth bits) once per (Gaussian, touched tile) for the Gaussian `idx` of
@@ -470,7 +502,7 @@ tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ en
 
 // D4.  Persistent CTAs pull tiles from a work list: list[item * list_step] for item < *n_list_ptr, items handed out
 // through *cursor.
-template <int T, int CAP, int LG_MAXB, int MIN_BLOCKS>
+template <int T, int CAP, int LG_MAXB, int MIN_BLOCKS, bool BULK>
 __global__ void __launch_bounds__(T, MIN_BLOCKS)
 tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ list,
                         int list_step, const uint32_t* __restrict__ n_list_ptr, uint32_t* __restrict__ cursor,
@@ -478,15 +510,18 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
 {
     constexpr int kSortCap = CAP, kMaxBuckets = 1 << LG_MAXB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* A = reinterpret_cast<uint64_t*>(smem_raw);                                // [kSortCap] depth << 32 | value
-    uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSortCap * 8);      // [kSortCap] bucket-grouped indices
-    uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 10);    // [kMaxBuckets + 1]
+    uint64_t* A_raw = reinterpret_cast<uint64_t*>(smem_raw);                                 // [kSortCap + 2] depth << 32 | value
+    uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kSortCap * 8 + 16);      // [kSortCap] bucket-grouped indices
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 10 + 16);    // [kMaxBuckets + 1]
+    __shared__ __align__(8) uint64_t s_mbar;
     uint32_t* s_red = bucket + kMaxBuckets + 1;                                          // [64]: min and max per warp
     __shared__ uint32_t s_item;
     constexpr int kWarps = T / 32;
     static_assert(CAP < 65536 && (kWarps & (kWarps - 1)) == 0 && kWarps <= 32, "16-bit indices, power-of-two warps");
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t n_list = *n_list_ptr;
+    if (BULK && t == 0) mbar_init(&s_mbar, 1u);
+    uint32_t parity = 0;
 
     while (true) {
         if (t == 0) s_item = atomicAdd(cursor, 1u);
@@ -497,6 +532,11 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
         const uint2 range = ranges[tile];
         const int n = (int)(range.y - range.x);
         const uint2* src = pairs + range.x;
+        // a stored pair (value, depth bits) read as one little-endian 64-bit word IS the key depth << 32 | value: staging is a
+        // plain copy of a contiguous segment -> one 1-D bulk copy (TMA) instead of a load / store loop.  The copy engine
+        // wants 16-byte alignment: it starts one pair early when the segment starts at an odd index
+        const uint32_t lead = BULK ? (range.x & 1u) : 0u;
+        uint64_t* A = A_raw + lead;
         if (n > kSortCap) {  // cannot happen: api.cu only takes this path when the longest tile fits
             __syncthreads();
             continue;
@@ -509,11 +549,27 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
 
         // sweep 0: stage, min / max of the depth bits
         uint32_t dmin = 0xffffffffu, dmax = 0u;
-        for (int i = t; i < n; i += T) {
-            const uint2 p = src[i];
-            A[i] = ((uint64_t)p.y << 32) | p.x;
-            dmin = min(dmin, p.y);
-            dmax = max(dmax, p.y);
+        if (BULK) {
+            if (t == 0) {
+                const uint32_t bytes = (((uint32_t)n + lead + 1u) & ~1u) * 8u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by ordinary loads / stores
+                mbar_expect_tx(&s_mbar, bytes);
+                bulk_load(A_raw, src - lead, bytes, &s_mbar);
+            }
+            mbar_wait(&s_mbar, parity);
+            parity ^= 1u;
+            for (int i = t; i < n; i += T) {
+                const uint32_t d = (uint32_t)(A[i] >> 32);
+                dmin = min(dmin, d);
+                dmax = max(dmax, d);
+            }
+        } else {
+            for (int i = t; i < n; i += T) {
+                const uint2 p = src[i];
+                A[i] = ((uint64_t)p.y << 32) | p.x;
+                dmin = min(dmin, p.y);
+                dmax = max(dmax, p.y);
+            }
         }
         dmin = __reduce_min_sync(0xffffffffu, dmin);
         dmax = __reduce_max_sync(0xffffffffu, dmax);
@@ -675,15 +731,20 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
     const DirectScratch d = direct_scratch(prm, scratch);
-    auto* sort_m = tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3>;
-    auto* sort_x = tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2>;
-    auto* sort_l = tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1>;
+    // staging by one 1-D bulk copy (TMA) per tile, or by a load / store loop (lgm_set_tuning "sort_bulk" 0)
+    const bool bulk = tuning(kTuneSortBulk) != 0;
+    auto* sort_m = bulk ? tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, true>
+                        : tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, false>;
+    auto* sort_x = bulk ? tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, true>
+                        : tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, false>;
+    auto* sort_l = bulk ? tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, true>
+                        : tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, false>;
     constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_x = sort_smem(kSortCapX, kLgBucketsX),
                      smem_l = sort_smem(kSortCapL, kLgBucketsL);
-    static std::atomic<uint64_t> opted_m{0}, opted_x{0}, opted_l{0};
-    if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted_m)) return e;
-    if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted_x)) return e;
-    if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted_l)) return e;
+    static std::atomic<uint64_t> opted[2][3];
+    if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted[bulk][0])) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted[bulk][1])) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted[bulk][2])) return e;
     const int n_sm = device_sm_count();
     cudaError_t err;
     if (entries) {

@@ -17,7 +17,7 @@ KEEP = {  # demangled-name substring -> file tag
     "scan_block_sums_kernel": "scan_block_sums_kernel", "emit_kernel": "emit_kernel", "histogram_kernel": "histogram_kernel",
     "onesweep_kernel<512, 8, 2, false>": "onesweep_kernel", "tile_ranges_kernel": "tile_ranges_kernel",
     "tile_enumerate_kernel<false>": "tile_count_kernel", "tile_enumerate_kernel<true>": "tile_scatter_kernel",
-    "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel<512, 5632, 11, 3>": "tile_bucket_sort_kernel",
+    "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel<512, 5632, 11, 3, true>": "tile_bucket_sort_kernel",
     "coarse_scatter_kernel": "coarse_scatter_kernel", "tile_scatter_entries_kernel": "tile_scatter_entries_kernel",
     # the shipped compositing kernels (two pixels per lane, packed fp32): the instantiations LGM's training step runs
     # (depth image computed in the forward as the reference does; no depth gradient in the backward)

@@ -3,7 +3,7 @@
 counters file bench.py reads (profiles/<tag>_counters.json).
 
     ncu -i gpurun_out/r02_prof.ncu-rep --page raw --csv > /tmp/raw.csv
-    python scripts/ncu_table.py /tmp/raw.csv profiles/r02_counters.json zero123g/trained
+    python scripts/ncu_table.py /tmp/raw.csv[,/tmp/more.csv] profiles/r02_counters.json zero123g/trained
 """
 import csv
 import json
@@ -24,11 +24,17 @@ UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "
 
 
 def main():
-    rows = list(csv.reader(open(sys.argv[1])))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
     out = []
-    for r in rows[2:]:
+    for path in sys.argv[1].split(","):
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        parse_rows(rows[2:], idx, units, out)
+    report(out)
+
+
+def parse_rows(rows, idx, units, out):
+    for r in rows:
         name = r[idx["Kernel Name"]]
         short = name.split("(")[0].replace("void ", "").replace("lgm::", "").replace("<unnamed>::", "").replace("unnamed>::", "").strip()
         d = {"kernel": short, "grid": r[idx["launch__grid_size"]], "block": r[idx["launch__block_size"]]}
@@ -46,6 +52,9 @@ def main():
                   for h, i in idx.items() if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and r[i]}
         d["top_stalls"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:4])
         out.append(d)
+
+
+def report(out):
     print("| kernel | time | regs | warps active | issue active | DRAM % | DRAM read / write | L1/TEX % | warp instr | top stalls (warps per issue cycle) |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     for d in out:
