@@ -99,8 +99,8 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L, uint64_t E)
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
 thread_local bool g_last_coarse = false;
 
-std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
-const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ", "sort_bulk"};
+std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ", "sort_bulk", "sparse_lanes"};
 std::atomic<int> g_sm_count[lgm::kMaxDevices];
 
 }  // namespace
@@ -134,7 +134,7 @@ int lgm_set_tuning(const char* name, int32_t value)
             g_tuning[i].store(value, std::memory_order_relaxed);
             return LGM_OK;
         }
-    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global, coarse_ratio)");
+    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global, coarse_ratio, c2_occ, sort_bulk, sparse_lanes)");
 }
 
 int lgm_direct_bin_tile_cap(void) { return lgm::direct_bin_tile_cap(); }

@@ -31,7 +31,7 @@ inline cudaError_t opt_in_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<
 }
 
 // ---- tuning / test hooks (lgm_set_tuning in include/lgm_b200.h; process-wide, read at launch time; api.cu) ----
-enum Tuning { kTuneFwdBatch = 0, kTunePatchLanes, kTuneBwdBatch, kTuneSortVariant, kTuneEnumGlobal, kTuneCoarseRatio, kTuneC2Occ, kTuneSortBulk, kTuneCount };
+enum Tuning { kTuneFwdBatch = 0, kTunePatchLanes, kTuneBwdBatch, kTuneSortVariant, kTuneEnumGlobal, kTuneCoarseRatio, kTuneC2Occ, kTuneSortBulk, kTuneSparseLanes, kTuneCount };
 int tuning(Tuning which);  // < 0: not set, the kernel's built-in default applies
 
 struct RenderParams {

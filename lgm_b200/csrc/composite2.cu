@@ -25,12 +25,26 @@ constexpr int kBlock2 = 128;      // 4 warps x (8x8 pixels)
 // 4.96 / 5.25 / 6.43 ms (larger batches cost resident CTAs: 48 B of shared memory per staged Gaussian)
 constexpr int kFwdBatch2 = 256;
 constexpr int kBwdBatch2 = 384;
+constexpr int kSparseLanes2 = 14;  // backward: hits with at most this many contributing lanes use direct vector reductions
+// (measured, headline step: 0 / 2 / 4 / 8 / 12 / 16 / 24 / 32 -> bwd 4.41 / 4.22 / 4.10 / 3.93 / 3.83 / 3.83 / 4.37 / 6.14 ms)
 constexpr int kFwdOcc2 = 10, kBwdOcc2 = 8;  // resident CTAs per SM the kernels are compiled for (launch bounds)
 // A pixel that has stopped (or lies outside the image) is parked at row 1e18: its dy is astronomically large, so the
 // Gaussian's exponent is hugely negative (conics are >= ~1e-7), alpha underflows to 0 and the reference's own
 // "alpha < 1/255 -> skip" test rejects the pair — no `done` flag in the inner loop.  (A non-positive-definite conic gives
 // power > 0 or -inf: skipped as well.)
 constexpr float kParked = 1e18f;
+
+#ifdef LGM_STATS
+// Developer build only (scripts/composite_stats.py, -DLGM_STATS): per-hit statistics of the compositing kernels.
+// [0] fwd candidates  [1] fwd hits (some pixel composites)  [2] fwd composited pixels  [3] fwd staged instances
+// [8] bwd candidates  [9] bwd hits  [10] bwd valid pixels  [11] bwd staged instances
+// [16 + b] bwd hits whose number of lanes with a valid pixel falls in bucket b: 1, 2, 3-4, 5-8, 9-16, 17-32
+__device__ unsigned long long g_stats[32];
+// the value is evaluated by every lane (it may contain warp votes)
+#define LGM_STAT(i, v) do { const unsigned long long sv_ = (v); if (lane == 0) st[i] += sv_; } while (0)
+#else
+#define LGM_STAT(i, v) do { } while (0)
+#endif
 
 // ---- packed fp32 (PTX ISA 8.6, sm_100+): both halves are .rn operations, never contracted or re-associated ----
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
@@ -148,6 +162,9 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
 
     float2 T = bc(1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), Wt = bc(0.f), D = bc(0.f);
     uint32_t last0 = 0, last1 = 0;
+#ifdef LGM_STATS
+    unsigned long long st[4] = {0, 0, 0, 0};
+#endif
 #define LGM_BOTH_PARKED (npfy.x < -0.5f * kParked && npfy.y < -0.5f * kParked)
 
     for (int r0 = 0; r0 < todo; r0 += batch) {
@@ -156,6 +173,7 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         for (int k = threadIdx.x; k < nb; k += kBlock2)
             sb.template stage<DEPTH>(k, vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
         __syncthreads();
+        if (warp == 0) LGM_STAT(3, nb);
         for (int base = 0; base < nb; base += 32) {
             if (__all_sync(0xffffffffu, LGM_BOTH_PARKED)) break;  // every pixel of the warp's patch is saturated (or outside)
             const int jl = base + lane;
@@ -179,7 +197,12 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                 const bool comp0 = cand0 && !stop0, comp1 = cand1 && !stop1;
                 npfy.x = stop0 ? -kParked : npfy.x;
                 npfy.y = stop1 ? -kParked : npfy.y;
+                LGM_STAT(0, 1);
                 if (!__any_sync(0xffffffffu, comp0 || comp1)) continue;
+#ifdef LGM_STATS
+                LGM_STAT(1, 1);
+                LGM_STAT(2, __popc(__ballot_sync(0xffffffffu, comp0)) + __popc(__ballot_sync(0xffffffffu, comp1)));
+#endif
                 const float4 cd = sb.rgbd[j];
                 const float2 ae = make_float2(comp0 ? a.x : 0.0f, comp1 ? a.y : 0.0f);
                 C0 = fma2(mul2(bc(cd.x), ae), T, C0);
@@ -195,6 +218,10 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         }
     }
 #undef LGM_BOTH_PARKED
+#ifdef LGM_STATS
+    if (lane == 0)
+        for (int i = 0; i < 4; i++) atomicAdd(&g_stats[i], st[i]);
+#endif
     const size_t hw = (size_t)prm.H * prm.W;
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
     const float2 o0 = fma2(T, bc(b0), C0), o1 = fma2(T, bc(b1), C1), o2 = fma2(T, bc(b2), C2);
@@ -252,6 +279,16 @@ __device__ __forceinline__ void warp_reduce_10_packed(const float (&a)[8], const
     Bv = bk;
 }
 
+// Vector reductions into a 16-byte aligned gradient row (sm_90+: REDG.E.ADD.F32x4 / .F32x2), fire and forget.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 template <bool DEPTH, int MINB, int BATCH>
 __global__ void __launch_bounds__(kBlock2, MINB)
 composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const int32_t* __restrict__ view_scene,
@@ -260,7 +297,7 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                       const uint2* __restrict__ ranges, const float* __restrict__ bg,
                       const float* __restrict__ alpha_img, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dimage, const float* __restrict__ dL_dalpha_img,
-                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows)
+                      const float* __restrict__ dL_ddepth_img, float* __restrict__ grad_rows, int sparse_lanes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Staging2<BATCH> sb(smem_raw);
@@ -316,6 +353,9 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     for (int w = 0; w < kBlock2 / 32; w++) bmax = max(bmax, s_max[w]);
     const int todo = (int)min(range.y - range.x, bmax);
 
+#ifdef LGM_STATS
+    unsigned long long st[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     float2 U = bc(0.f);  // (colour, depth, alpha) accumulated behind the current Gaussian, dotted with (dC, dD, dA)
     // which of the ten reduced sums this lane sends to the gradient row (group_reduce_10<32>): lanes 0, 4, .., 28 hold the
     // eight "a" sums (slots 0..7), lanes 1 and 17 the two "b" sums (slots 8, 9)
@@ -331,6 +371,7 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
             sb.template stage<DEPTH>(k, vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
                                      tile_x0, tile_y0);
         __syncthreads();
+        if (warp == 0) LGM_STAT(3, nb);
         for (int base = 0; base < nb; base += 32) {
             const int jl = base + lane;
             // positions >= wmax were never reached by this warp's patch in the forward
@@ -354,7 +395,17 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                 const float2 a = make_float2(fminf(kAlphaMax, ar.x), fminf(kAlphaMax, ar.y));
                 const bool valid0 = (pos < lc0) && !(power.x > 0.0f) && !(a.x < kAlphaMin);
                 const bool valid1 = (pos < lc1) && !(power.y > 0.0f) && !(a.y < kAlphaMin);
-                if (!__any_sync(0xffffffffu, valid0 || valid1)) continue;
+                LGM_STAT(0, 1);
+                const unsigned vm = __ballot_sync(0xffffffffu, valid0 || valid1);  // lanes with a contributing pixel
+                if (vm == 0u) continue;
+#ifdef LGM_STATS
+                {
+                    const int nl = __popc(vm);
+                    LGM_STAT(1, 1);
+                    LGM_STAT(2, __popc(__ballot_sync(0xffffffffu, valid0)) + __popc(__ballot_sync(0xffffffffu, valid1)));
+                    LGM_STAT(8 + (nl <= 1 ? 0 : nl <= 2 ? 1 : nl <= 4 ? 2 : nl <= 8 ? 3 : nl <= 16 ? 4 : 5), 1);
+                }
+#endif
 
                 // Evaluated for both pixels of every lane, no divergent region: a pixel that does not contribute runs with
                 // alpha = 0 and G = 0, which leaves its running state untouched and makes its ten terms exact zeros.  One
@@ -397,14 +448,30 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                 } else {
                     vb[1] = 0.0f;
                 }
+                float* row = grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow;
+                if (__popc(vm) <= sparse_lanes) {
+                    // A hit that only a few lanes contribute to (a Gaussian clipping the patch: 18 % of the hits of the
+                    // headline step have one or two such lanes): those lanes send their own terms with three vector
+                    // reductions instead of the whole warp running the 14-shuffle reduction for them.
+                    if (valid0 || valid1) {
+                        red_add_v4(row, va[0], va[1], va[2], va[3]);
+                        red_add_v4(row + 4, va[4], va[5], va[6], va[7]);
+                        if (DEPTH) red_add_v2(row + 8, vb[0], vb[1]);
+                        else atomicAdd(row + 8, vb[0]);
+                    }
+                    continue;
+                }
                 float A, Bv;
                 warp_reduce_10_packed<DEPTH>(va, vb, lane, A, Bv);
                 // ten lanes hold the ten sums: fire-and-forget fp32 reductions (RED) into the Gaussian's gradient row
-                float* row = grad_rows + (size_t)__float_as_uint(p1.z) * kGradRow;
                 if (a_sender || b_sender) atomicAdd(row + (a_sender ? a_slot : b_slot), a_sender ? A : Bv);
             }
         }
     }
+#ifdef LGM_STATS
+    if (lane == 0)
+        for (int i = 0; i < 16; i++) atomicAdd(&g_stats[8 + i], st[i]);
+#endif
 }
 
 template <bool DEPTH, int MINB, int BATCH>
@@ -424,9 +491,11 @@ cudaError_t run2_bwd(cudaStream_t stream, unsigned blocks, const RenderParams& p
                      const uint32_t* vals, const uint2* ranges, const float* bg, const float* alpha, const uint32_t* n_contrib,
                      const float* dL_dimage, const float* dL_dalpha, const float* dL_ddepth, float* grad_rows)
 {
+    // lgm_set_tuning "sparse_lanes": hits with at most this many contributing lanes skip the warp reduction (0 = never)
+    const int sparse_lanes = tuning(kTuneSparseLanes) >= 0 ? tuning(kTuneSparseLanes) : kSparseLanes2;
     composite2_bwd_kernel<DEPTH, MINB, BATCH><<<blocks, kBlock2, BATCH * kStagedBytes2, stream>>>(
         prm, gaussians, view_scene, xy, conic_opacity, depth, vals, ranges, bg, alpha, n_contrib, dL_dimage, dL_dalpha, dL_ddepth,
-        grad_rows);
+        grad_rows, sparse_lanes);
     return cudaGetLastError();
 }
 
@@ -472,4 +541,21 @@ cudaError_t launch_composite2_bwd(cudaStream_t stream, const RenderParams& prm, 
 #undef LGM_B
 }
 
+#ifdef LGM_STATS
+cudaError_t debug_stats(unsigned long long* host_out, int reset)
+{
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && host_out) e = cudaMemcpyFromSymbol(host_out, g_stats, sizeof(g_stats));
+    if (e == cudaSuccess && reset) {
+        const unsigned long long z[32] = {};
+        e = cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+    }
+    return e;
+}
+#endif
+
 }  // namespace lgm
+
+#ifdef LGM_STATS
+extern "C" int lgm_debug_stats(unsigned long long* host_out, int reset) { return (int)lgm::debug_stats(host_out, reset); }
+#endif

@@ -68,11 +68,22 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
 }
 
 // Which of the tile's patches can this Gaussian reach with alpha >= 1/255 ?
-// alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. 0.5 d^T Q d <= tau = ln(255 o) with
-// Q = [[cx, cy], [cy, cz]]: an ellipse around the centre with axis-aligned half extents
-//   hx = sqrt(2 tau cz / det Q),  hy = sqrt(2 tau cx / det Q)          (+ safety margins for fp32 rounding).
+// alpha = min(0.99, o * exp(power)) >= 1/255 requires power >= -ln(255 o), i.e. q(d) = d^T Q d <= 2 tau, tau = ln(255 o),
+// with Q = [[cx, cy], [cy, cz]] and d = centre - pixel: an ellipse around the centre.
 // Computed ONCE per staged Gaussian by its staging thread; each patch then only tests its bit.
 // 255 o <= 1: never visible (mask 0).  Q not positive definite (or NaN): the region is unbounded, all patches.
+//
+// LANES >= 32 (the 8-pixel-wide patches of the default kernels): the EXACT test — the minimum of q over the rectangle
+// spanned by the patch's pixel centres against 2 tau.  q is convex with its minimum at d = 0, so over a box it is
+// attained on the faces that separate the box from the origin: with (X, Y) = the box point closest to 0 per coordinate,
+//   min q = min( min_dy q(X, dy),  min_dx q(dx, Y) ),  each a clamped 1-D minimisation (dy* = clamp(-cy X / cz), ...).
+// Measured on the headline step (scripts/composite_stats.py): with the axis-aligned extents of the ellipse alone 28 % of
+// the evaluated (patch, Gaussian) candidates had no pixel above the threshold — the Gaussians are anisotropic and
+// randomly oriented, so the ellipse's bounding box is loose.
+// Narrower patches (the cross-check variants LGM_PATCH_LANES = 16 / 8) keep the bounding-box test
+//   hx = sqrt(2 tau cz / det Q),  hy = sqrt(2 tau cx / det Q).
+// Safety margins for fp32 rounding (of this test, of the kernels' pinned `power`, of ex2.approx / __logf): the threshold
+// is scaled and padded, the rectangle grown by kCullPix.
 template <int LANES>
 __device__ __forceinline__ uint32_t patch_mask(float px, float py, const float4 co, float tile_x0, float tile_y0)
 {
@@ -83,6 +94,33 @@ __device__ __forceinline__ uint32_t patch_mask(float px, float py, const float4 
     const float det = co.x * co.z - co.y * co.y;
     if (!(det > 0.0f) || !(co.x > 0.0f) || !(co.z > 0.0f)) return kAll;
     const float t2 = 2.0f * __logf(k) * kCullScale + kCullPad;
+    if (LANES >= 32) {
+        const float gx = px - tile_x0, gy = py - tile_y0;  // centre relative to the tile origin
+        const float kx = -__fdividef(co.y, co.x), ky = -__fdividef(co.y, co.z), cy2 = co.y + co.y;
+        // fp32 rounding of q (here and in the kernels' `power`): its three terms are each <= cx dx^2 + cz dy^2 in magnitude
+        // and cancel for elongated ellipses — a pad proportional to their bound over the tile
+        const float ax = fabsf(gx) + (float)kTile, ay = fabsf(gy) + (float)kTile;
+        const float t2p = fmaf(4e-6f, fmaf(co.x * ax, ax, co.z * ay * ay), t2);
+        uint32_t m = 0;
+#pragma unroll
+        for (int r = 0; r < PT::NROWS; r++) {
+            // d = centre - pixel over the patch's pixel centres [r PH, r PH + PH - 1] (grown by kCullPix)
+            const float y_lo = gy - (float)(r * PT::PH + PT::PH - 1) - kCullPix, y_hi = gy - (float)(r * PT::PH) + kCullPix;
+            const float Y = fminf(fmaxf(0.0f, y_lo), y_hi);
+            const float czY2 = co.z * Y * Y, cy2Y = cy2 * Y;
+#pragma unroll
+            for (int c = 0; c < PT::NCOLS; c++) {
+                const float x_lo = gx - (float)(c * PT::PW + PT::PW - 1) - kCullPix, x_hi = gx - (float)(c * PT::PW) + kCullPix;
+                const float X = fminf(fmaxf(0.0f, x_lo), x_hi);
+                const float dy = fminf(fmaxf(X * ky, y_lo), y_hi);          // minimiser on the face dx = X
+                const float q1 = fmaf(fmaf(co.z, dy, cy2 * X), dy, co.x * X * X);
+                const float dx = fminf(fmaxf(Y * kx, x_lo), x_hi);          // minimiser on the face dy = Y
+                const float q2 = fmaf(fmaf(co.x, dx, cy2Y), dx, czY2);
+                m |= (!(q1 > t2p) || !(q2 > t2p)) ? (1u << (PT::NCOLS * r + c)) : 0u;  // NaN compares false -> keep
+            }
+        }
+        return m;
+    }
     const float inv = __fdividef(t2, det);
     const float hx = sqrtf(co.z * inv) * kCullScale + kCullPix, hy = sqrtf(co.x * inv) * kCullScale + kCullPix;
     const float lo_x = px - hx - tile_x0, hi_x = px + hx - tile_x0;  // extent relative to the tile origin
