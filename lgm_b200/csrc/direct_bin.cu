@@ -34,6 +34,10 @@ namespace {
 // per SM — the trained-scene case.  L: up to 20,480 instances, 1024 threads, 216 KB, one CTA per SM — untrained
 // Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
 constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
+// S: tiles of up to 2,048 instances, 256 threads, 25 KB, 6 CTAs per SM.  A trained scene's tiles hold ~750 instances on
+// average: with 512 threads most of a CTA idles through the barriers, bucket scans and the two-iteration sweeps of such a
+// tile (the fixed cost per tile is paid by every warp).
+constexpr int kSortThreadsS = 256, kSortCapS = 2048, kLgBucketsS = 10;
 constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 // X: the class between them — tiles of up to 9,216 instances, 1024 threads, 109 KB: TWO CTAs per SM, so that one CTA's
 // global load / store phases overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians have most of their
@@ -321,12 +325,13 @@ cudaError_t launch_tile_enumerate(cudaStream_t stream, const RenderParams& prm, 
 
 // head[] words of the direct path's scratch
 enum Head { kHeadM = 0, kHeadMCursor = 1, kHeadLongest = 2, kHeadL = 3, kHeadLCursor = 4, kHeadX = 5, kHeadXCursor = 6,
-            kHeadItems = 7, kHeadItemCursor = 8, kHeadItemOverflow = 9 };
+            kHeadItems = 7, kHeadItemCursor = 8, kHeadItemOverflow = 9, kHeadS = 10, kHeadSCursor = 11 };
 
 // D2.  One CTA per view: the view's first slot is the sum of the totals of the views before it, the tiles of the view
 // are scanned in chunks of 256.  Writes ranges[] (empty tiles stay (0,0)), appends the non-empty tiles to the work lists
 // (warp-aggregated) and records the longest tile.  Tiles of the M class (<= kSortCapM) fill `list` from the front, those
-// of the L class (> kSortCapX) from the back, the X class in between fills `list_x`.
+// of the L class (> kSortCapX) from the back; the X class in between fills `list_x` from the front, the S class
+// (<= kSortCapS) from the back.
 // Coarse grouping (super_counts != null): the same for the entries — super_offsets[] = first entry of every (view,
 // super-tile) group in the grouped entry list, one work item (group, chunk) per kCoarseChunk entries of a group, and
 // the total number of entries (the last view's CTA writes it to *entries_out).
@@ -353,8 +358,17 @@ tile_ranges_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __r
         carry += tot;
         if (i < n_tiles) ranges[gt] = n ? make_uint2(start, start + n) : make_uint2(0u, 0u);
         longest = max(longest, n);
-        const bool is_m = n != 0u && n <= (uint32_t)kSortCapM, is_l = n > (uint32_t)kSortCapX;
+        const bool is_s = n != 0u && n <= (uint32_t)kSortCapS;
+        const bool is_m = n > (uint32_t)kSortCapS && n <= (uint32_t)kSortCapM, is_l = n > (uint32_t)kSortCapX;
         const bool is_x = n > (uint32_t)kSortCapM && !is_l;
+        const unsigned ms = __ballot_sync(0xffffffffu, is_s);
+        if (ms) {
+            const int leader = __ffs(ms) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&head[kHeadS], (uint32_t)__popc(ms));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_s) list_x[n_ranges - 1u - (base + __popc(ms & ((1u << lane) - 1u)))] = gt;
+        }
         const unsigned m = __ballot_sync(0xffffffffu, is_m);
         if (m) {
             const int leader = __ffs(m) - 1;
@@ -799,9 +813,12 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
                         : tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, false>;
     auto* sort_l = bulk ? tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, true>
                         : tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, false>;
+    auto* sort_s = bulk ? tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, true>
+                        : tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, false>;
     constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_x = sort_smem(kSortCapX, kLgBucketsX),
-                     smem_l = sort_smem(kSortCapL, kLgBucketsL);
-    static std::atomic<uint64_t> opted[2][3];
+                     smem_l = sort_smem(kSortCapL, kLgBucketsL), smem_s = sort_smem(kSortCapS, kLgBucketsS);
+    static std::atomic<uint64_t> opted[2][4];
+    if (cudaError_t e = opt_in_dynamic_smem(sort_s, smem_s, opted[bulk][3])) return e;
     if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted[bulk][0])) return e;
     if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted[bulk][1])) return e;
     if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted[bulk][2])) return e;
@@ -833,9 +850,15 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
                                                         d.head + kHeadXCursor, vals_sorted, keys_sorted);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
-    sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head + kHeadM,
-                                                    d.head + kHeadMCursor, vals_sorted, keys_sorted);
+    if (longest_tile > (uint32_t)kSortCapS) {
+        const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
+        sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head + kHeadM,
+                                                        d.head + kHeadMCursor, vals_sorted, keys_sorted);
+        if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    }
+    const uint32_t n_cta = (uint32_t)min((unsigned)(6 * n_sm), n_ranges);
+    sort_s<<<n_cta, kSortThreadsS, smem_s, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list_x + (n_ranges - 1), -1,
+                                                    d.head + kHeadS, d.head + kHeadSCursor, vals_sorted, keys_sorted);
     return cudaGetLastError();
 }
 

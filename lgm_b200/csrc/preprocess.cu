@@ -108,6 +108,7 @@ cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, 
 
 // ---- K7: preprocess backward.  One thread per Gaussian loops over the views of its scene and accumulates in
 // registers, so the sum over views needs no atomics and is deterministic. ----
+constexpr int kViewChunk = 32;
 __global__ void __launch_bounds__(kBlock, 3)
 preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussians, const float* __restrict__ view_mats,
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ scene_view_offsets,
@@ -116,7 +117,7 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                       const float* __restrict__ cov3d, float* __restrict__ dL_dcov3d)
 {
     __shared__ __align__(16) float s_g[kBlock * 14];
-    __shared__ float s_m[32];
+    __shared__ float s_m[kViewChunk * 32];  // view and projection matrices of up to kViewChunk views
     const int scene = blockIdx.y;
     const int base = blockIdx.x * kBlock;
     const int n = min(kBlock, prm.P - base);
@@ -146,23 +147,37 @@ preprocess_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         }
     }
     const int v0 = scene_view_offsets[scene], v1 = scene_view_offsets[scene + 1];
-    for (int v = v0; v < v1; v++) {
+    // The matrices of kViewChunk views are staged at once, so that the view loop itself runs without block barriers: the
+    // warps drift apart and one warp's row loads overlap the others' arithmetic.  The radius of the next view is fetched
+    // one iteration ahead (the row loads depend on it).
+    for (int c0 = v0; c0 < v1; c0 += kViewChunk) {
+        const int nc = min(kViewChunk, v1 - c0);
         __syncthreads();
-        if (threadIdx.x < 16) s_m[threadIdx.x] = view_mats[v * 16 + threadIdx.x];
-        else if (threadIdx.x < 32) s_m[threadIdx.x] = proj_mats[v * 16 + threadIdx.x - 16];
+        for (int i = threadIdx.x; i < nc * 32; i += kBlock) {
+            const int v = c0 + (i >> 5), k = i & 31;
+            s_m[i] = k < 16 ? view_mats[v * 16 + k] : proj_mats[v * 16 + k - 16];
+        }
         __syncthreads();
         if (!active) continue;
-        const size_t gi = (size_t)v * prm.P + base + threadIdx.x;
-        if (!(radii[gi] > 0)) continue;
-        const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
-        const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
-        // r0 = (Sx, Sy, Sxx, Sxy)  r1 = (Syy, S0 = dL/dopacity, col.r, col.g)  r2 = (col.b, depth, -, -): moment form
-        preprocess_point_bwd_view(pos, cov6, s_m, s_m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, r0.x, r0.y, r0.z, r0.w, r1.x, r2.y,
-                                  d, g6, /*moments=*/true, (float)prm.W, (float)prm.H, opacity);
-        d[3] += r1.y;
-        d[11] += r1.z;
-        d[12] += r1.w;
-        d[13] += r2.x;
+        const size_t g0 = (size_t)c0 * prm.P + base + threadIdx.x;
+        int rad = radii[g0];
+        for (int j = 0; j < nc; j++) {
+            const size_t gi = g0 + (size_t)j * prm.P;
+            const int rad_next = j + 1 < nc ? radii[gi + prm.P] : 0;
+            if (rad > 0) {
+                const float4* row = reinterpret_cast<const float4*>(grad_rows + gi * kGradRow);
+                const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
+                // r0 = (Sx, Sy, Sxx, Sxy)  r1 = (Syy, S0 = dL/dopacity, col.r, col.g)  r2 = (col.b, depth, -, -): moment form
+                const float* m = s_m + j * 32;
+                preprocess_point_bwd_view(pos, cov6, m, m + 16, prm.tanx, prm.tany, prm.fx, prm.fy, r0.x, r0.y, r0.z, r0.w, r1.x,
+                                          r2.y, d, g6, /*moments=*/true, (float)prm.W, (float)prm.H, opacity);
+                d[3] += r1.y;
+                d[11] += r1.z;
+                d[12] += r1.w;
+                d[13] += r2.x;
+            }
+            rad = rad_next;
+        }
     }
     if (active) {
         if (cov3d) {
