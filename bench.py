@@ -499,16 +499,17 @@ def run_native(args):
                          "algorithmic_bytes": int(sort_bytes), "ms": t_sort,
                          "per_pass": {"bytes": int(24 * Lr), "ms": t_sort / (npass + 8.0 / 24.0)}}
         # ---- roofline of the HBM-bound group: K1 preprocess + binning, as IMPLEMENTED ----
-        # bytes the implemented algorithm must move: K1 44 + 36 per (view, Gaussian); direct binning:
+        # bytes the implemented algorithm must move: K1 44 + 36 per (view, Gaussian) + the 48-byte gradient row
+        # it zeroes for the backward; direct binning:
         # count 12 and scatter 16 per (view, Gaussian) + 8 per instance written, per-tile sort 8 read + 4 written per
         # instance, 20 per tile; onesweep path: emit 20 per pair + 12 per instance, sort (24 n_pass + 8) per instance,
         # ranges 8 per instance + 8 per tile.
         P_ = N
         bin_mode = ops.last_bin_mode["mode"]
         if bin_mode == "direct":
-            impl_bytes = n_local * (80 + 12 + 16) * P_ + 20 * Lr + 20 * n_local * n_tiles
+            impl_bytes = n_local * (80 + 48 + 12 + 16) * P_ + 20 * Lr + 20 * n_local * n_tiles
         else:
-            impl_bytes = n_local * (80 + 20) * P_ + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
+            impl_bytes = n_local * (80 + 48 + 20) * P_ + 12 * Lr + sort_bytes + 8 * Lr + 8 * n_local * n_tiles
         t_grp = stages.get("geom", 0.0) + stages.get("bin_count", 0.0) + stages.get("bin", 0.0)
         ach_grp = impl_bytes / (t_grp * 1e-3) / 1e9 if t_grp > 0 else None
         survey_bytes = n_local * (80 * P_ + 20 * P_) + 12 * Lr + (6 * 24 + 8) * Lr + 8 * Lr + 8 * n_local * n_tiles
@@ -517,7 +518,7 @@ def run_native(args):
                     "achieved": ach_grp, "peak": peak, "unit": "GB/s", "frac": ach_grp / peak if ach_grp else None,
                     "traffic": grp_traffic, "traffic_source": counters_src if grp_traffic else None,
                     "peak_source": peak_src, "algorithmic_bytes": int(impl_bytes), "ms": t_grp,
-                    "definition": "bytes the implemented algorithm must move (108 B per (view, Gaussian) + 20 B per instance + 20 B "
+                    "definition": "bytes the implemented algorithm must move (156 B per (view, Gaussian), 48 of them the gradient row K1 zeroes, + 20 B per instance + 20 B "
                                   "per tile on the direct path) / CUDA-event time of the geom + bin_count + bin stages",
                     "survey_8d": {"algorithmic_bytes": int(survey_bytes), "frac": survey_bytes / (t_grp * 1e-3) / 1e9 / peak if t_grp > 0 else None,
                                   "note": "SURVEY.md 8d's figure (100 B per (view, Gaussian) + 172 B per instance) counts a 6-pass LSD radix "

@@ -63,8 +63,9 @@ typedef struct lgm_render_params {
 
 /* 2: moment-form gradient rows (lgm_backward_geom takes conic_opacity), want_sorted_keys, direct binning.
  * 3: enqueue-only binning (lgm_forward_count, lgm_step_counts; lgm_forward_bin takes longest_tile / bin_mode),
- *    lgm_set_tuning instead of environment variables, activations with the reference's normalisation axis. */
-#define LGM_ABI_VERSION 3
+ *    lgm_set_tuning instead of environment variables, activations with the reference's normalisation axis.
+ * 4: lgm_forward_geom_rows (K1 zeroes the gradient rows), tuning "sparse_lanes". */
+#define LGM_ABI_VERSION 4
 int lgm_abi_version(void);
 const char* lgm_last_error_string(void);
 
@@ -112,6 +113,14 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
                            const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
                            float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
                            uint64_t* total_instances, const float* cov3d);
+
+/* The same, and K1 also zeroes the step's gradient rows: grad_rows f32 [n_views * P, LGM_GRAD_ROW] (16-byte aligned), the
+ * buffer lgm_backward(_composite) accumulates into — K1 is bound by instruction issue, so the 48 B per pair ride along
+ * instead of a separate fill of ~1 GB per step.  NULL = lgm_forward_geom_cov3d (the caller zeroes the rows). */
+int lgm_forward_geom_rows(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                          const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                          float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                          uint64_t* total_instances, const float* cov3d, float* grad_rows);
 
 /* Binning, first half (direct path D1 + D2): per-tile instance counts and their scan.  After it `ranges`
  * uint2[n_views * tiles] holds every tile's [start, end) in the final instance list (empty tiles (0,0)) and

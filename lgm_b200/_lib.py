@@ -21,7 +21,7 @@ class LgmError(RuntimeError):
 
 
 _lib = None
-ABI_VERSION = 3  # include/lgm_b200.h LGM_ABI_VERSION
+ABI_VERSION = 4  # include/lgm_b200.h LGM_ABI_VERSION
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _pp = ctypes.POINTER(RenderParams)
 
@@ -33,6 +33,7 @@ _SIGNATURES = {
     "lgm_bin_workspace_bytes": (ctypes.c_int, [_pp, _i64, _i64, ctypes.POINTER(_sz)]),
     "lgm_forward_geom": (ctypes.c_int, [_vp, _pp] + [_vp] * 12),
     "lgm_forward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 13),
+    "lgm_forward_geom_rows": (ctypes.c_int, [_vp, _pp] + [_vp] * 14),
     "lgm_backward_geom_cov3d": (ctypes.c_int, [_vp, _pp] + [_vp] * 8 + [_i32, _vp, _vp]),
     "lgm_set_tuning": (ctypes.c_int, [ctypes.c_char_p, _i32]),
     "lgm_count_workspace_bytes": (ctypes.c_int, [_pp, ctypes.POINTER(_sz)]),

@@ -168,6 +168,15 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
                            float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
                            uint64_t* total_instances, const float* cov3d)
 {
+    return lgm_forward_geom_rows(stream, prm, gaussians, view_mats, proj_mats, view_scene, depth, radii, xy, conic_opacity,
+                                 tiles_touched, block_sums, block_offsets, total_instances, cov3d, nullptr);
+}
+
+int lgm_forward_geom_rows(void* stream, const lgm_render_params* prm, const float* gaussians, const float* view_mats,
+                          const float* proj_mats, const int32_t* view_scene, float* depth, int32_t* radii, float* xy,
+                          float* conic_opacity, uint32_t* tiles_touched, uint32_t* block_sums, uint32_t* block_offsets,
+                          uint64_t* total_instances, const float* cov3d, float* grad_rows)
+{
     lgm::RenderParams p;
     if (int rc = make_params(prm, p)) return rc;
     LGM_NOTNULL(total_instances);
@@ -181,7 +190,7 @@ int lgm_forward_geom_cov3d(void* stream, const lgm_render_params* prm, const flo
     LGM_NOTNULL(block_sums); LGM_NOTNULL(block_offsets);
     LGM_CUDA(lgm::launch_preprocess_fwd(s, p, gaussians, view_mats, proj_mats, view_scene, depth, radii,
                                         reinterpret_cast<float2*>(xy), reinterpret_cast<float4*>(conic_opacity),
-                                        tiles_touched, block_sums, cov3d),
+                                        tiles_touched, block_sums, cov3d, grad_rows),
              "forward_geom: preprocess");
     LGM_CUDA(lgm::launch_scan_block_sums(s, block_sums, (uint32_t)p.n_views, (uint32_t)((p.P + lgm::kBlock - 1) / lgm::kBlock),
                                          block_offsets, reinterpret_cast<unsigned long long*>(total_instances)),

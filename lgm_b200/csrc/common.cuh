@@ -54,7 +54,8 @@ constexpr int kBlock = 256;  // threads per block of the per-Gaussian kernels an
 cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* view_scene,
                                   float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
-                                  uint32_t* tiles_touched, uint32_t* block_sums, const float* cov3d = nullptr);
+                                  uint32_t* tiles_touched, uint32_t* block_sums, const float* cov3d = nullptr,
+                                  float* zero_rows = nullptr);
 cudaError_t launch_mark_visible(cudaStream_t stream, int P, const float* means, const float* view_mat, uint8_t* visible);
 // direct_bin.cu: count -> scan -> scatter -> per-tile shared-memory sort (no global radix sort); a step whose longest
 // tile exceeds direct_bin_tile_cap() must use the onesweep path

@@ -30,7 +30,7 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
                       const float* __restrict__ proj_mats, const int32_t* __restrict__ view_scene,
                       float* __restrict__ depth, int32_t* __restrict__ radii, float2* __restrict__ xy,
                       float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched,
-                      uint32_t* __restrict__ block_sums, const float* __restrict__ cov3d)
+                      uint32_t* __restrict__ block_sums, const float* __restrict__ cov3d, float4* __restrict__ zero_rows)
 {
     __shared__ __align__(16) float s_g[kBlock * 14];
     __shared__ float s_mv[16], s_mp[16];
@@ -58,6 +58,14 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         conic_opacity[gi] = make_float4(o.cx, o.cy, o.cz, o.radius > 0 ? g[3] : 0.f);
         if (tiles_touched) tiles_touched[gi] = o.tiles;
         tiles = o.tiles;
+        if (zero_rows) {
+            // the backward's gradient row of this (view, Gaussian) pair, zeroed here: the kernel is bound by instruction
+            // issue (correctly rounded divisions), so the 48 B of stores ride along instead of a separate 1 GB fill
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            zero_rows[3 * gi] = z;
+            zero_rows[3 * gi + 1] = z;
+            zero_rows[3 * gi + 2] = z;
+        }
     }
     // block sum of tiles_touched -> one partial per (view, Gaussian block); scanned by scan_block_sums_kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,12 +85,14 @@ preprocess_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
 cudaError_t launch_preprocess_fwd(cudaStream_t stream, const RenderParams& prm, const float* gaussians,
                                   const float* view_mats, const float* proj_mats, const int32_t* view_scene,
                                   float* depth, int32_t* radii, float2* xy, float4* conic_opacity,
-                                  uint32_t* tiles_touched, uint32_t* block_sums, const float* cov3d)
+                                  uint32_t* tiles_touched, uint32_t* block_sums, const float* cov3d, float* zero_rows)
 {
+    static_assert(kGradRow == 12, "three 16-byte vectors per gradient row");
     if (prm.P == 0 || prm.n_views == 0) return cudaSuccess;
     dim3 grid((prm.P + kBlock - 1) / kBlock, prm.n_views);
     preprocess_fwd_kernel<<<grid, kBlock, 0, stream>>>(prm, gaussians, view_mats, proj_mats, view_scene, depth, radii, xy,
-                                                       conic_opacity, tiles_touched, block_sums, cov3d);
+                                                       conic_opacity, tiles_touched, block_sums, cov3d,
+                                                       reinterpret_cast<float4*>(zero_rows));
     return cudaGetLastError();
 }
 

@@ -87,8 +87,8 @@ class ForwardState:
 def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offsets, bg, cfg: ViewConfig,
                   prepare_backward=False, cov3d=None):
     """All views in one set of launches.  Returns (image [VW,3,H,W], alpha [VW,1,H,W], depth [VW,1,H,W], state).
-    prepare_backward: also allocate and zero the backward's gradient rows now — the fill then runs on the GPU while
-    the host waits for the instance count, instead of at the head of the backward.
+    prepare_backward: also allocate the backward's gradient rows now and let K1 zero them (lgm_forward_geom_rows) — no
+    separate fill of 48 B per (view, Gaussian) pair at the head of the backward.
     cov3d [B,P,6]: upstream's cov3D_precomp — replaces the covariance built from the scale / rotation columns."""
     L = _lib.lib()
     _check_cuda_f32(gaussians, "gaussians", (14,))
@@ -120,10 +120,12 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         _check_cuda_f32(cov3d, "cov3d", (6,))
         if cov3d.numel() != B * P * 6:
             raise _lib.LgmError(f"cov3d must hold n_scenes * P * 6 values, got {tuple(cov3d.shape)}")
-    _timed("geom", lambda: _lib.check(L.lgm_forward_geom_cov3d(
+    # the backward's gradient rows: K1 zeroes the row of every (view, Gaussian) pair it processes (no separate fill)
+    st.grad_rows = torch.empty(npair, _lib.GRAD_ROW, dtype=torch.float32, device=dev) if (prepare_backward and npair) else None
+    _timed("geom", lambda: _lib.check(L.lgm_forward_geom_rows(
         s, prm, _lib.ptr(gaussians), _lib.ptr(view_mats), _lib.ptr(proj_mats), _lib.ptr(view_scene), _lib.ptr(st.depth),
         _lib.ptr(st.radii), _lib.ptr(st.xy), _lib.ptr(st.conic_opacity), _lib.ptr(st.tiles_touched), _lib.ptr(block_sums),
-        _lib.ptr(block_offsets), _lib.ptr(counts), _lib.ptr(cov3d)), "lgm_forward_geom"))
+        _lib.ptr(block_offsets), _lib.ptr(counts), _lib.ptr(cov3d), _lib.ptr(st.grad_rows)), "lgm_forward_geom"))
     launch_counter["kernels"] += 2 if npair else 0
     # first half of the binning (per-tile counts and their scan = the final ranges of the direct path): it does not
     # need the instance count, so it runs before the step's readback and leaves the longest tile next to the count
@@ -138,7 +140,6 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
             _lib.ptr(counts)), "lgm_forward_count"))
         launch_counter["kernels"] += 2
     # work that does not depend on the instance count is queued before the host waits for it
-    st.grad_rows = torch.zeros(max(npair, 1), _lib.GRAD_ROW, dtype=torch.float32, device=dev) if prepare_backward else None
     image = torch.empty(VW, 3, H, W, dtype=torch.float32, device=dev)
     alpha = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev)
     depth_img = torch.empty(VW, 1, H, W, dtype=torch.float32, device=dev) if cfg.want_depth else None

@@ -50,7 +50,7 @@ def test_struct_layout_matches_header():
 
 def test_size_queries_and_errors(lib):
     from lgm_b200 import _lib
-    assert lib.lgm_abi_version() == 3
+    assert lib.lgm_abi_version() == 4
     assert lib.lgm_tiles_per_view(320, 320) == 400 and lib.lgm_tiles_per_view(512, 512) == 1024
     assert lib.lgm_tiles_per_view(17, 33) == 2 * 3
     assert lib.lgm_num_block_sums(98304, 208) == 208 * 384 and lib.lgm_num_block_sums(257, 3) == 6
