@@ -21,16 +21,18 @@
 // D4 is a bucket sort: keys are mapped monotonically to ~n/2 buckets by (depth - min) * nb / (range + 1), counted and
 // grouped with shared-memory atomics (two sweeps), and each element finds its final slot by counting the smaller keys
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
-// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Two size classes (M: <= 5,632 instances,
-// 3 CTAs per SM; L: <= 20,480, one 1024-thread CTA per SM).  A longer tile cannot be staged in shared memory: the caller
-// (api.cu) reads the longest tile back and uses the onesweep path for such a step.
+// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Four size classes (S: <= 2,048 instances, 256
+// threads, 6 CTAs per SM; M: <= 5,632, 512 threads, 3 CTAs; X: <= 9,216, 1024 threads, 2 CTAs; L: <= 20,480, one 1024-thread
+// CTA per SM).  A tile whose keys pile up in one bucket (depth ties) is ordered by a bitonic network instead of the rank
+// loop (kTieLimit).  A longer tile cannot be staged in shared memory: the caller (api.cu) reads the longest tile back and
+// uses the onesweep path for such a step.
 #include "common.cuh"
 #include "splat_math.cuh"
 
 namespace lgm {
 namespace {
 
-// Two size classes of the per-tile sort.  M: tiles of up to 5,632 instances, 512 threads, 63 KB of shared memory, 3 CTAs
+// Size classes of the per-tile sort.  M: tiles of up to 5,632 instances, 512 threads, 63 KB of shared memory, 3 CTAs
 // per SM — the trained-scene case.  L: up to 20,480 instances, 1024 threads, 216 KB, one CTA per SM — untrained
 // Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
 constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
@@ -44,6 +46,9 @@ constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 // instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
 constexpr int kSortThreadsX = 1024, kSortCapX = 9216, kLgBucketsX = 12;
 // (+ 16 B: the bulk copy of a segment starts at a 16-byte boundary, up to one pair before the segment, and ends at one)
+// bucket occupancy beyond which a tile is ordered by the sorting network instead of the rank loop (lgm_set_tuning
+// "tie_limit" is not provided: the value only bounds the worst case, 256^2 compares per bucket)
+constexpr uint32_t kTieLimit = 256;
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + 16 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 
 // ---- 1-D bulk copy (TMA, cp.async.bulk) + mbarrier: the segment of a tile is contiguous in `pairs` ----
@@ -665,16 +670,53 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
         for (int i = t; i < n; i += T) atomicAdd(&bucket[LGM_BUCKET((uint32_t)(A[i] >> 32))], 1u);
         __syncthreads();
 
-        // exclusive scan of the nb sizes (each thread owns nb / T consecutive buckets, or one when nb < T)
+        // exclusive scan of the nb sizes (each thread owns nb / T consecutive buckets, or one when nb < T); the fullest
+        // bucket is found on the way
+        uint32_t fullest = 0;
         {
             const int per = nb >= T ? nb / T : 1;
             const int b0 = t * per;
             uint32_t sum = 0;
             if (b0 < nb)
-                for (int j = 0; j < per; j++) sum += bucket[b0 + j];
+                for (int j = 0; j < per; j++) {
+                    const uint32_t c = bucket[b0 + j];
+                    sum += c;
+                    fullest = max(fullest, c);
+                }
             const uint32_t incl = warp_incl_scan(sum, lane);
-            if (lane == 31) s_red[warp] = incl;
+            fullest = __reduce_max_sync(0xffffffffu, fullest);
+            if (lane == 31) { s_red[warp] = incl; s_red[kWarps + warp] = fullest; }
             __syncthreads();
+            fullest = __reduce_max_sync(0xffffffffu, s_red[kWarps + (lane & (kWarps - 1))]);
+            if (fullest > kTieLimit) {
+                // Depth ties (a plane at constant view depth, duplicated points, positions clamped to the same value) put
+                // many keys into one bucket, and the rank loop of sweep 3 is quadratic in the bucket size.  Such a tile is
+                // ordered by a sorting network instead: bitonic merges in their all-ascending form (first step of a merge
+                // pairs i with i ^ (k - 1)), which needs no padding — a partner beyond n is a virtual +infinity that no
+                // comparator moves.  n log^2 n / 4 comparators whatever the keys are.
+                __syncthreads();
+                for (uint32_t k = 2; (k >> 1) < (uint32_t)n; k <<= 1) {
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        const uint32_t flip = (j == (k >> 1)) ? (k - 1u) : j;
+                        for (uint32_t i = t; i < (uint32_t)n; i += T) {
+                            const uint32_t p = i ^ flip;
+                            if (p > i && p < (uint32_t)n) {
+                                const uint64_t a = A[i], b = A[p];
+                                if (b < a) { A[i] = b; A[p] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                const uint64_t hi_t = (uint64_t)tile << 32;
+                for (int i = t; i < n; i += T) {
+                    const uint64_t key = A[i];
+                    vals_sorted[range.x + i] = (uint32_t)key;
+                    if (keys_sorted) keys_sorted[range.x + i] = hi_t | (key >> 32);
+                }
+                __syncthreads();  // shared memory is reused by the next tile
+                continue;
+            }
             const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? s_red[lane] : 0u);  // warp < kWarps <= 32
             uint32_t run = base + incl - sum;
             if (b0 < nb)

@@ -565,6 +565,16 @@ def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
     monkeypatch.setenv("LGM_ENUM_GLOBAL", "1")
     c = _bin_result(monkeypatch, "direct", g3, cv, cvp, 64)
     assert c["ran"] == b["ran"] and _same_binning(a, c)
+    monkeypatch.delenv("LGM_ENUM_GLOBAL")
+    # (e) thousands of exact duplicates: whole tiles share ONE depth, so all their keys fall into one bucket of the tile
+    # sort — ordered by the sorting network (direct_bin.cu kTieLimit) instead of the quadratic rank loop; 1,200 / 7,000 /
+    # 15,000 copies exercise the S, X and L size classes
+    for copies in (1200, 7000, 15000):
+        g4 = make_gaussians(1, 2000, "trained", seed=8)
+        g4 = torch.cat([g4, g4[:, :1].repeat(1, copies, 1)], dim=1).contiguous().numpy()
+        a, b = _bin_result(monkeypatch, "onesweep", g4, cv, cvp, 96), _bin_result(monkeypatch, "direct", g4, cv, cvp, 96)
+        assert b["ran"] == "direct" and a["longest"] >= copies, (b["ran"], a["longest"])
+        assert _same_binning(a, b)
 
 
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
