@@ -188,6 +188,7 @@ int lgm_forward_geom_rows(void* stream, const lgm_render_params* prm, const floa
     LGM_NOTNULL(gaussians); LGM_NOTNULL(view_mats); LGM_NOTNULL(proj_mats); LGM_NOTNULL(view_scene);
     LGM_NOTNULL(depth); LGM_NOTNULL(radii); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity);
     LGM_NOTNULL(block_sums); LGM_NOTNULL(block_offsets);
+    if (reinterpret_cast<uintptr_t>(grad_rows) & 15u) return fail(LGM_ERR_BAD_VALUE, "grad_rows must be 16-byte aligned");
     LGM_CUDA(lgm::launch_preprocess_fwd(s, p, gaussians, view_mats, proj_mats, view_scene, depth, radii,
                                         reinterpret_cast<float2*>(xy), reinterpret_cast<float4*>(conic_opacity),
                                         tiles_touched, block_sums, cov3d, grad_rows),
@@ -346,6 +347,8 @@ int lgm_backward_composite(void* stream, const lgm_render_params* prm, const flo
     LGM_NOTNULL(gaussians); LGM_NOTNULL(view_scene); LGM_NOTNULL(xy); LGM_NOTNULL(conic_opacity); LGM_NOTNULL(depth);
     LGM_NOTNULL(ranges); LGM_NOTNULL(bg); LGM_NOTNULL(alpha); LGM_NOTNULL(n_contrib); LGM_NOTNULL(dL_dimage); LGM_NOTNULL(dL_dalpha);
     LGM_NOTNULL(grad_rows);  // dL_ddepth may be NULL: no gradient w.r.t. the depth image
+    // the rows are accumulated with 16-byte vector reductions and read with 16-byte loads
+    if (reinterpret_cast<uintptr_t>(grad_rows) & 15u) return fail(LGM_ERR_BAD_VALUE, "grad_rows must be 16-byte aligned");
     LGM_CUDA(lgm::launch_composite_bwd((cudaStream_t)stream, p, gaussians, view_scene, reinterpret_cast<const float2*>(xy),
                                        reinterpret_cast<const float4*>(conic_opacity), depth, vals_sorted,
                                        reinterpret_cast<const uint2*>(ranges), bg, alpha, n_contrib, dL_dimage, dL_dalpha,

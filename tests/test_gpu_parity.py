@@ -664,6 +664,46 @@ def test_composite_variants_agree(monkeypatch):
             assert ((a - b).abs() / scale).max().item() <= 2e-5, f"gradients differ at LGM_PATCH_LANES={lanes}"
 
 
+def test_sparse_and_dense_reduction_paths_agree(monkeypatch):
+    """The backward sends a hit's ten sums either through the warp reduction (dense hits) or with vector reductions from
+    the contributing lanes themselves (sparse hits; composite2.cu kSparseLanes2, LGM_SPARSE_LANES).  Always the tree (0),
+    the shipped mix (unset) and never the tree (32) must give the same gradient rows up to fp32 summation order — with
+    and without a depth gradient (two / one word in the last vector), on small splats (mostly sparse hits) and on large
+    saturating ones (mostly dense hits)."""
+    from lgm_b200 import ops
+    B, V, N, S = 2, 3, 6000, 72
+    g0 = make_gaussians(B, N, "trained", seed=31)
+    g0[:, :, 4:7] *= 2.0
+    g0[1] = make_gaussians(1, N, "init", seed=32)[0]
+    cv, cvp, _ = make_cameras(B, V, seed=31)
+    t = tan_half(49.1)
+    d_img, d_alpha, d_depth = make_upstream_grads(B, V, S, S, seed=31, with_depth=True)
+    g, vm, pm, bg, img, al, dp, st = _cuda_forward(g0.numpy(), cv, cvp, [0.1, 0.2, 0.3], S, S, t, t)
+    res = {}
+    for lanes in ("0", None, "32"):
+        if lanes is None:
+            monkeypatch.delenv("LGM_SPARSE_LANES", raising=False)
+        else:
+            monkeypatch.setenv("LGM_SPARSE_LANES", lanes)
+        from lgm_b200 import _lib
+        _lib.apply_env_tuning()
+        outs = []
+        for dd in (d_depth, None):
+            dg, rows = ops.backward_views(g, vm, pm, bg, st, al, (d_img * 1e4).reshape(B * V, 3, S, S).to(DEV).contiguous(),
+                                          (d_alpha * 1e4).reshape(B * V, 1, S, S).to(DEV).contiguous(),
+                                          None if dd is None else (dd * 1e4).reshape(B * V, 1, S, S).to(DEV).contiguous())
+            outs += [dg.clone(), rows.clone()]
+        res[lanes] = outs
+    monkeypatch.delenv("LGM_SPARSE_LANES", raising=False)
+    _lib.apply_env_tuning()
+    assert float(res["0"][1].abs().max()) > 0
+    for lanes in (None, "32"):
+        for a, b in zip(res["0"], res[lanes]):
+            scale = a.abs().amax(dim=tuple(range(a.dim() - 1)), keepdim=True).clamp_min(1e-20)
+            assert ((a - b).abs() / scale).max().item() <= 2e-5, f"gradients differ at LGM_SPARSE_LANES={lanes}"
+        assert torch.equal(res["0"][1][:, 10:], res[lanes][1][:, 10:])  # the two padding words stay zero
+
+
 def test_fused_mse_loss_matches_torch():
     """lgm_b200.mse_image_alpha_loss = F.mse_loss(image) + F.mse_loss(alpha) of /root/reference/core/models.py:153: value
     and gradients, odd element counts (scalar tail), a non-unit incoming gradient, explicit weights."""
