@@ -1,6 +1,7 @@
 #!/bin/bash
 # ncu passes over one short bench run (B200_PROFILING.md recipe): launch list with durations, then a full capture of
 # the path's kernels of one step.  Each ncu run follows a plain run of the same command that exited 0.
+# The full capture skips the three warm-up steps (NCU_SKIP kernels of the path; 10 per step of the headline workload).
 # TAG names the outputs (gpurun_out/${TAG}_launches.csv, ${TAG}_prof.ncu-rep); BENCH_ARGS selects the workload.
 set -u
 mkdir -p gpurun_out
@@ -12,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 echo "launch list rc=$?"
 if [ "${FULLCAP:-1}" = "1" ]; then
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-lgm}" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-12} -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-composite|preprocess|tile_|scan_block|coarse_scatter|emit|onesweep|histogram}" -s ${NCU_SKIP:-30} -c ${NCU_COUNT:-10} -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/${TAG}_ncu_full.log
 fi
 ls -la gpurun_out/ | grep ${TAG}
