@@ -23,8 +23,8 @@
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
 // for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Four size classes (S: <= 2,048 instances, 256
 // threads, 6 CTAs per SM; M: <= 5,632, 512 threads, 3 CTAs; X: <= 9,216, 1024 threads, 2 CTAs; L: <= 20,480, one 1024-thread
-// CTA per SM).  A tile whose keys pile up in one bucket (depth ties) is ordered by a bitonic network instead of the rank
-// loop (kTieLimit).  A longer tile cannot be staged in shared memory: the caller (api.cu) reads the longest tile back and
+// CTA per SM).  A tile whose keys pile up in few buckets (depth ties) is ordered by a bitonic network instead of the rank
+// loop, when the loop would make more compares than the network.  A longer tile cannot be staged in shared memory: the caller (api.cu) reads the longest tile back and
 // uses the onesweep path for such a step.
 #include "common.cuh"
 #include "splat_math.cuh"
@@ -46,9 +46,6 @@ constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 // instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
 constexpr int kSortThreadsX = 1024, kSortCapX = 9216, kLgBucketsX = 12;
 // (+ 16 B: the bulk copy of a segment starts at a 16-byte boundary, up to one pair before the segment, and ends at one)
-// bucket occupancy beyond which a tile is ordered by the sorting network instead of the rank loop (lgm_set_tuning
-// "tie_limit" is not provided: the value only bounds the worst case, 256^2 compares per bucket)
-constexpr uint32_t kTieLimit = 256;
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + 16 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 
 // ---- 1-D bulk copy (TMA, cp.async.bulk) + mbarrier: the segment of a tile is contiguous in `pairs` ----
@@ -670,9 +667,9 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
         for (int i = t; i < n; i += T) atomicAdd(&bucket[LGM_BUCKET((uint32_t)(A[i] >> 32))], 1u);
         __syncthreads();
 
-        // exclusive scan of the nb sizes (each thread owns nb / T consecutive buckets, or one when nb < T); the fullest
-        // bucket is found on the way
-        uint32_t fullest = 0;
+        // exclusive scan of the nb sizes (each thread owns nb / T consecutive buckets, or one when nb < T); the sum of the
+        // squared sizes — the number of compares the rank loop of sweep 3 will make — is formed on the way
+        uint32_t rank_work = 0;  // <= n^2 < 2^32
         {
             const int per = nb >= T ? nb / T : 1;
             const int b0 = t * per;
@@ -681,14 +678,17 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
                 for (int j = 0; j < per; j++) {
                     const uint32_t c = bucket[b0 + j];
                     sum += c;
-                    fullest = max(fullest, c);
+                    rank_work += c * c;
                 }
             const uint32_t incl = warp_incl_scan(sum, lane);
-            fullest = __reduce_max_sync(0xffffffffu, fullest);
-            if (lane == 31) { s_red[warp] = incl; s_red[kWarps + warp] = fullest; }
+            rank_work = __reduce_add_sync(0xffffffffu, rank_work);
+            if (lane == 31) { s_red[warp] = incl; s_red[kWarps + warp] = rank_work; }
             __syncthreads();
-            fullest = __reduce_max_sync(0xffffffffu, s_red[kWarps + (lane & (kWarps - 1))]);
-            if (fullest > kTieLimit) {
+            rank_work = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_red[kWarps + lane] : 0u);
+            // comparators of the sorting network below: n / 2 per stage, L (L + 1) / 2 stages, L = ceil(log2 n); one of
+            // them costs about twice a compare of the rank loop
+            const uint32_t lg_n = 32u - (uint32_t)__clz((unsigned)max(n - 1, 1));
+            if (rank_work > (uint32_t)n * (lg_n * (lg_n + 1u) / 2u)) {
                 // Depth ties (a plane at constant view depth, duplicated points, positions clamped to the same value) put
                 // many keys into one bucket, and the rank loop of sweep 3 is quadratic in the bucket size.  Such a tile is
                 // ordered by a sorting network instead: bitonic merges in their all-ascending form (first step of a merge

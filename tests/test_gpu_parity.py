@@ -567,7 +567,7 @@ def test_direct_binning_depth_ties_and_long_tiles(monkeypatch):
     assert c["ran"] == b["ran"] and _same_binning(a, c)
     monkeypatch.delenv("LGM_ENUM_GLOBAL")
     # (e) thousands of exact duplicates: whole tiles share ONE depth, so all their keys fall into one bucket of the tile
-    # sort — ordered by the sorting network (direct_bin.cu kTieLimit) instead of the quadratic rank loop; 1,200 / 7,000 /
+    # sort — ordered by the sorting network (direct_bin.cu: when the rank loop would make more compares) instead of the quadratic rank loop; 1,200 / 7,000 /
     # 15,000 copies exercise the S, X and L size classes
     for copies in (1200, 7000, 15000):
         g4 = make_gaussians(1, 2000, "trained", seed=8)
