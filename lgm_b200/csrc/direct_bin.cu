@@ -22,7 +22,7 @@
 // grouped with shared-memory atomics (two sweeps), and each element finds its final slot by counting the smaller keys
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
 // for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Four size classes (S: <= 2,048 instances, 256
-// threads, 6 CTAs per SM; M: <= 5,632, 512 threads, 3 CTAs; X: <= 9,216, 1024 threads, 2 CTAs; L: <= 20,480, one 1024-thread
+// threads, 6 CTAs per SM; M: <= 5,632, 512 threads, 3 CTAs; X: <= 11,776, 1024 threads, 2 CTAs; L: <= 20,480, one 1024-thread
 // CTA per SM).  A tile whose keys pile up in few buckets (depth ties) is ordered by a bitonic network instead of the rank
 // loop, when the loop would make more compares than the network.  A longer tile cannot be staged in shared memory: the caller (api.cu) reads the longest tile back and
 // uses the onesweep path for such a step.
@@ -41,10 +41,10 @@ constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
 // tile (the fixed cost per tile is paid by every warp).
 constexpr int kSortThreadsS = 256, kSortCapS = 2048, kLgBucketsS = 10;
 constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
-// X: the class between them — tiles of up to 9,216 instances, 1024 threads, 109 KB: TWO CTAs per SM, so that one CTA's
+// X: the class between them — tiles of up to 11,776 instances, 1024 threads, 111 KB in the grouped-keys form: TWO CTAs per SM, so that one CTA's
 // global load / store phases overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians have most of their
 // instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
-constexpr int kSortThreadsX = 1024, kSortCapX = 9216, kLgBucketsX = 12;
+constexpr int kSortThreadsX = 1024, kSortCapX = 11776, kLgBucketsX = 12;
 // (+ 16 B: the bulk copy of a segment starts at a 16-byte boundary, up to one pair before the segment, and ends at one)
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + 16 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 
@@ -752,6 +752,193 @@ tile_bucket_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict
     }
 }
 
+// D4, second form ("grouped keys").  The first form stages the segment (A), groups 16-bit INDICES by bucket and ranks
+// every element against A[order[q]] — three random shared-memory gathers per compare chain, and the kernel is bound by
+// the bandwidth of the shared-memory pipe under bank conflicts (ncu: L1 82 %).  Here the segment is not staged at all: the
+// three sweeps that need the keys in input order (min / max, bucket sizes, grouping) read them straight from global
+// memory — coalesced 8-byte loads of a segment that stays in L1 / L2 between the sweeps — and the grouping sweep scatters
+// the KEYS themselves into shared memory.  The rank sweep then reads its own key at its own index and scans its bucket,
+// which neighbouring lanes share or adjoin: nearly conflict-free.  8 B of shared memory per instance instead of 10.
+template <int T, int CAP, int LG_MAXB, int MIN_BLOCKS>
+__global__ void __launch_bounds__(T, MIN_BLOCKS)
+tile_group_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ list,
+                       int list_step, const uint32_t* __restrict__ n_list_ptr, uint32_t* __restrict__ cursor,
+                       uint32_t* __restrict__ vals_sorted, uint64_t* __restrict__ keys_sorted)
+{
+    constexpr int kSortCap = CAP, kMaxBuckets = 1 << LG_MAXB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* G = reinterpret_cast<uint64_t*>(smem_raw);                                  // [kSortCap] keys grouped by bucket
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kSortCap * 8);      // [kMaxBuckets + 1]
+    uint32_t* s_red = bucket + kMaxBuckets + 1;                                           // [64]
+    __shared__ uint32_t s_item, s_tile;
+    __shared__ uint2 s_range;
+    constexpr int kWarps = T / 32;
+    static_assert((kWarps & (kWarps - 1)) == 0 && kWarps <= 32, "power-of-two warps");
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t n_list = *n_list_ptr;
+
+    // Work items are fetched ONE TILE AHEAD: a tile starts with a chain of dependent global round trips (cursor atomic ->
+    // list entry -> range -> first touch of the segment, ~3 us) that only the other two or five CTAs of the SM could
+    // hide.  Thread 0 draws the next item while the current tile's first sweeps run, resolves its tile and range during
+    // the last sweeps, and asks L2 for the next segment (cp.async.bulk.prefetch.L2).
+    if (t == 0) {
+        const uint32_t item = atomicAdd(cursor, 1u);
+        s_item = item;
+        if (item < n_list) {
+            const uint32_t tl = list[(ptrdiff_t)item * list_step];
+            s_tile = tl;
+            s_range = ranges[tl];
+        }
+    }
+    __syncthreads();
+    while (true) {
+        const uint32_t item = s_item;
+        if (item >= n_list) break;
+        const uint32_t tile = s_tile;
+        const uint2 range = s_range;
+        uint32_t next_item = 0xffffffffu;
+        if (t == 0) next_item = atomicAdd(cursor, 1u);  // in flight during the first sweeps
+        const int n = (int)(range.y - range.x);
+        // a stored pair (value, depth bits) read as one little-endian 64-bit word IS the key depth << 32 | value
+        const uint64_t* __restrict__ src = reinterpret_cast<const uint64_t*>(pairs + range.x);
+        uint32_t next_tile = 0;
+        uint2 next_range = make_uint2(0u, 0u);
+        if (n > kSortCap) {  // cannot happen: api.cu only takes this path when the longest tile fits
+            __syncthreads();
+            if (t == 0) {
+                s_item = next_item;
+                if (next_item < n_list) { s_tile = list[(ptrdiff_t)next_item * list_step]; s_range = ranges[s_tile]; }
+            }
+            __syncthreads();
+            continue;
+        }
+        int lg_nb = 32 - __clz((unsigned)max(n - 1, 1)) - 1;
+        lg_nb = min(max(lg_nb, 5), LG_MAXB);
+        const int nb = 1 << lg_nb;
+
+        // sweep 0: min / max of the depth bits
+        uint32_t dmin = 0xffffffffu, dmax = 0u;
+        for (int i = t; i < n; i += T) {
+            const uint32_t d = (uint32_t)(src[i] >> 32);
+            dmin = min(dmin, d);
+            dmax = max(dmax, d);
+        }
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0) { s_red[warp] = dmin; s_red[kWarps + warp] = dmax; }
+        for (int i = t; i <= nb; i += T) bucket[i] = 0u;
+        __syncthreads();  // also orders the read of s_item above against the next iteration's write
+        dmin = __reduce_min_sync(0xffffffffu, s_red[lane & (kWarps - 1)]);
+        dmax = __reduce_max_sync(0xffffffffu, s_red[kWarps + (lane & (kWarps - 1))]);
+        const uint32_t span = dmax - dmin;
+        const bool direct = span < (uint32_t)nb;
+        const uint32_t mul = direct ? 0u : 0xffffffffu / (((span + 1u) >> lg_nb) + 1u);
+#define LGM_BUCKET(d) (direct ? ((d) - dmin) : __umulhi((d) - dmin, mul))
+
+        // sweep 1: bucket sizes (the barrier after it also protects s_red, which the scan reuses)
+        for (int i = t; i < n; i += T) atomicAdd(&bucket[LGM_BUCKET((uint32_t)(src[i] >> 32))], 1u);
+        __syncthreads();
+
+        // exclusive scan of the sizes + the compares the rank sweep will make (sum of the squared sizes)
+        uint32_t rank_work = 0;
+        {
+            const int per = nb >= T ? nb / T : 1;
+            const int b0 = t * per;
+            uint32_t sum = 0;
+            if (b0 < nb)
+                for (int j = 0; j < per; j++) {
+                    const uint32_t c = bucket[b0 + j];
+                    sum += c;
+                    rank_work += c * c;
+                }
+            const uint32_t incl = warp_incl_scan(sum, lane);
+            rank_work = __reduce_add_sync(0xffffffffu, rank_work);
+            if (lane == 31) { s_red[warp] = incl; s_red[kWarps + warp] = rank_work; }
+            __syncthreads();
+            rank_work = __reduce_add_sync(0xffffffffu, lane < kWarps ? s_red[kWarps + lane] : 0u);
+            const uint32_t lg_n = 32u - (uint32_t)__clz((unsigned)max(n - 1, 1));
+            if (rank_work > (uint32_t)n * (lg_n * (lg_n + 1u) / 2u)) {
+                // depth ties: the bitonic network of the first form, on a plain copy of the segment
+                for (int i = t; i < n; i += T) G[i] = src[i];
+                __syncthreads();
+                for (uint32_t k = 2; (k >> 1) < (uint32_t)n; k <<= 1) {
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        const uint32_t flip = (j == (k >> 1)) ? (k - 1u) : j;
+                        for (uint32_t i = t; i < (uint32_t)n; i += T) {
+                            const uint32_t p = i ^ flip;
+                            if (p > i && p < (uint32_t)n) {
+                                const uint64_t a = G[i], b = G[p];
+                                if (b < a) { G[i] = b; G[p] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                const uint64_t hi_t = (uint64_t)tile << 32;
+                for (int i = t; i < n; i += T) {
+                    const uint64_t key = G[i];
+                    vals_sorted[range.x + i] = (uint32_t)key;
+                    if (keys_sorted) keys_sorted[range.x + i] = hi_t | (key >> 32);
+                }
+                if (t == 0) {
+                    s_item = next_item;
+                    if (next_item < n_list) { s_tile = list[(ptrdiff_t)next_item * list_step]; s_range = ranges[s_tile]; }
+                }
+                __syncthreads();
+                continue;
+            }
+            const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? s_red[lane] : 0u);
+            uint32_t run = base + incl - sum;
+            if (b0 < nb)
+                for (int j = 0; j < per; j++) {
+                    const uint32_t c = bucket[b0 + j];
+                    bucket[b0 + j] = run;
+                    run += c;
+                }
+        }
+        __syncthreads();
+        // the next item's tile and range: two dependent loads, in flight during sweep 2
+        if (t == 0 && next_item < n_list) {
+            next_tile = list[(ptrdiff_t)next_item * list_step];
+            next_range = ranges[next_tile];
+        }
+
+        // sweep 2: the keys, grouped by bucket; bucket[b] runs from the bucket's start to its end
+        for (int i = t; i < n; i += T) {
+            const uint64_t key = src[i];
+            G[atomicAdd(&bucket[LGM_BUCKET((uint32_t)(key >> 32))], 1u)] = key;
+        }
+        __syncthreads();
+        if (t == 0 && next_item < n_list && next_range.y > next_range.x) {
+            // ask L2 for the next segment (16-byte granules around it)
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(pairs + next_range.x) & ~(uintptr_t)15;
+            const uintptr_t a1 = (reinterpret_cast<uintptr_t>(pairs + next_range.y) + 15) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+        }
+
+        // sweep 3: final slot = bucket start + number of smaller keys in the bucket
+        const uint64_t hi = (uint64_t)tile << 32;
+        for (int p = t; p < n; p += T) {
+            const uint64_t key = G[p];
+            const uint32_t b = LGM_BUCKET((uint32_t)(key >> 32));
+            const uint32_t s0 = b ? bucket[b - 1] : 0u, e0 = bucket[b];
+            uint32_t rank = 0;
+            for (uint32_t q = s0; q < e0; q++) rank += (G[q] < key) ? 1u : 0u;
+            const uint32_t out = range.x + s0 + rank;
+            vals_sorted[out] = (uint32_t)key;
+            if (keys_sorted) keys_sorted[out] = hi | (key >> 32);
+        }
+#undef LGM_BUCKET
+        if (t == 0) {
+            s_item = next_item;
+            s_tile = next_tile;
+            s_range = next_range;
+        }
+        __syncthreads();  // shared memory is reused by the next tile; the next item is published
+    }
+}
+constexpr size_t group_sort_smem(int cap, int lg_buckets) { return (size_t)cap * 8 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
+
 }  // namespace
 
 int direct_bin_tile_cap() { return kSortCapL; }
@@ -847,23 +1034,37 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
     const DirectScratch d = direct_scratch(prm, scratch);
-    // staging by one 1-D bulk copy (TMA) per tile, or by a load / store loop (lgm_set_tuning "sort_bulk" 0)
-    const bool bulk = tuning(kTuneSortBulk) != 0;
-    auto* sort_m = bulk ? tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, true>
-                        : tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, false>;
-    auto* sort_x = bulk ? tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, true>
-                        : tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, false>;
-    auto* sort_l = bulk ? tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, true>
-                        : tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, false>;
-    auto* sort_s = bulk ? tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, true>
-                        : tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, false>;
-    constexpr size_t smem_m = sort_smem(kSortCapM, kLgBucketsM), smem_x = sort_smem(kSortCapX, kLgBucketsX),
-                     smem_l = sort_smem(kSortCapL, kLgBucketsL), smem_s = sort_smem(kSortCapS, kLgBucketsS);
-    static std::atomic<uint64_t> opted[2][4];
-    if (cudaError_t e = opt_in_dynamic_smem(sort_s, smem_s, opted[bulk][3])) return e;
-    if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted[bulk][0])) return e;
-    if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted[bulk][1])) return e;
-    if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted[bulk][2])) return e;
+    // lgm_set_tuning "sort_bulk": 2 (default) = the grouped-keys form (reads the segment from global memory, no staging);
+    // 1 = first form, segment staged by one 1-D bulk copy (TMA) per tile; 0 = first form, staged by a load / store loop
+    const int form = tuning(kTuneSortBulk) >= 0 ? tuning(kTuneSortBulk) : 2;
+    const bool bulk = form != 0;
+    using SortFn = void (*)(const uint2*, const uint2*, const uint32_t*, int, const uint32_t*, uint32_t*, uint32_t*, uint64_t*);
+    SortFn sort_m, sort_x, sort_l, sort_s;
+    size_t smem_m, smem_x, smem_l, smem_s;
+    if (form >= 2) {
+        sort_m = tile_group_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 4>;
+        sort_x = tile_group_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2>;
+        sort_l = tile_group_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1>;
+        sort_s = tile_group_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 8>;
+        smem_m = group_sort_smem(kSortCapM, kLgBucketsM); smem_x = group_sort_smem(kSortCapX, kLgBucketsX);
+        smem_l = group_sort_smem(kSortCapL, kLgBucketsL); smem_s = group_sort_smem(kSortCapS, kLgBucketsS);
+    } else {
+        sort_m = bulk ? tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, true>
+                      : tile_bucket_sort_kernel<kSortThreadsM, kSortCapM, kLgBucketsM, 3, false>;
+        sort_x = bulk ? tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, true>
+                      : tile_bucket_sort_kernel<kSortThreadsX, kSortCapX, kLgBucketsX, 2, false>;
+        sort_l = bulk ? tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, true>
+                      : tile_bucket_sort_kernel<kSortThreadsL, kSortCapL, kLgBucketsL, 1, false>;
+        sort_s = bulk ? tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, true>
+                      : tile_bucket_sort_kernel<kSortThreadsS, kSortCapS, kLgBucketsS, 6, false>;
+        smem_m = sort_smem(kSortCapM, kLgBucketsM); smem_x = sort_smem(kSortCapX, kLgBucketsX);
+        smem_l = sort_smem(kSortCapL, kLgBucketsL); smem_s = sort_smem(kSortCapS, kLgBucketsS);
+    }
+    static std::atomic<uint64_t> opted[3][4];
+    if (cudaError_t e = opt_in_dynamic_smem(sort_m, smem_m, opted[form >= 2 ? 2 : form][0])) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_x, smem_x, opted[form >= 2 ? 2 : form][1])) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_l, smem_l, opted[form >= 2 ? 2 : form][2])) return e;
+    if (cudaError_t e = opt_in_dynamic_smem(sort_s, smem_s, opted[form >= 2 ? 2 : form][3])) return e;
     const int n_sm = device_sm_count();
     cudaError_t err;
     if (entries) {
@@ -893,12 +1094,12 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
     if (longest_tile > (uint32_t)kSortCapS) {
-        const uint32_t n_cta = (uint32_t)min((unsigned)(3 * n_sm), n_ranges);
+        const uint32_t n_cta = (uint32_t)min((unsigned)((form >= 2 ? 4 : 3) * n_sm), n_ranges);
         sort_m<<<n_cta, kSortThreadsM, smem_m, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list, 1, d.head + kHeadM,
                                                         d.head + kHeadMCursor, vals_sorted, keys_sorted);
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
     }
-    const uint32_t n_cta = (uint32_t)min((unsigned)(6 * n_sm), n_ranges);
+    const uint32_t n_cta = (uint32_t)min((unsigned)((form >= 2 ? 8 : 6) * n_sm), n_ranges);
     sort_s<<<n_cta, kSortThreadsS, smem_s, stream>>>(static_cast<const uint2*>(pairs), ranges, d.list_x + (n_ranges - 1), -1,
                                                     d.head + kHeadS, d.head + kHeadSCursor, vals_sorted, keys_sorted);
     return cudaGetLastError();

@@ -173,7 +173,7 @@ def forward_views(gaussians, view_mats, proj_mats, view_scene, scene_view_offset
         last_bin_mode["mode"] = BIN_MODES.get(mode, "none")
         if mode == 3:    # scatter (plain, or coarse grouping + fine scatter), tile sort (one to four size classes)
             last_bin_mode["coarse"] = bool(L.lgm_last_bin_coarse())
-            launch_counter["kernels"] += (2 if last_bin_mode["coarse"] else 1) + 1 + (longest > 2048) + (longest > 5632) + (longest > 9216)
+            launch_counter["kernels"] += (2 if last_bin_mode["coarse"] else 1) + 1 + (longest > 2048) + (longest > 5632) + (longest > 11776)
         elif mode == 2:  # emit, histogram, tile-bit passes, ranges, short + long tile sort
             launch_counter["kernels"] += 5 + tile_bit_passes(VW * n_tiles)
         else:            # emit, histogram, ranges + onesweep passes

@@ -499,7 +499,7 @@ def _same_binning(a, b):
 def test_binning_modes_are_bit_identical(monkeypatch):
     """The three binning paths of lgm_forward_bin — direct (count / scatter / per-tile shared-memory sort, direct_bin.cu),
     onesweep (one LSD sort of the 64-bit keys) and hybrid (onesweep on the tile bits + per-tile radix sort) — give the
-    same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632 and L-class
+    same sorted keys / values / ranges / image, light and heavy tiles alike (direct: M-class tiles <= 5,632, X-class <= 11,776 and L-class
     tiles <= 20,480 instances); direct hands a step whose longest tile exceeds its shared-memory capacity to onesweep."""
     seen, lens = set(), []
     for kind, N, S in (("trained", 20000, 128), ("init", 6000, 96), ("init", 25000, 160), ("init", 60000, 64), ("init", 120000, 32)):
@@ -513,7 +513,15 @@ def test_binning_modes_are_bit_identical(monkeypatch):
         assert res["direct"]["ran"] == ("direct" if longest <= 20480 else "onesweep"), (longest, res["direct"]["ran"])
         if kind == "trained":
             assert res["auto"]["ran"] == "direct"
-        seen.add("M" if longest <= 5632 else ("X" if longest <= 9216 else ("L" if longest <= 20480 else "handover")))
+        seen.add("M" if longest <= 5632 else ("X" if longest <= 11776 else ("L" if longest <= 20480 else "handover")))
+        # the three forms of the per-tile sort (direct_bin.cu): grouped keys read from global memory (default), segment
+        # staged by a bulk copy, segment staged by a load / store loop
+        if longest <= 20480:
+            for form in ("1", "0"):
+                monkeypatch.setenv("LGM_SORT_BULK", form)
+                f = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
+                assert f["ran"] == "direct" and _same_binning(res["onesweep"], f), f"{kind} N={N}: sort form {form} differs"
+            monkeypatch.delenv("LGM_SORT_BULK")
         lens.append(longest)
         # the coarse grouping of the direct path (pairs grouped by 8x8-tile super-tile before the scatter): forced on
         # (LGM_COARSE_RATIO=1: whenever there is an entry) and off (0); the default takes it from 6 instances per entry
