@@ -423,12 +423,15 @@ def run_native(args):
         for _ in range(2):
             step_resident()
         ops.stage_times_ms()
-        nrep = 3
+        nrep = 5
+        per_rep = []
         for _ in range(nrep):
             step_resident()
-        tms = ops.stage_times_ms()
+            per_rep.append({k: sum(v) for k, v in ops.stage_times_ms().items()})
         ops.enable_stage_timing(False)
-        stages = {k: sum(v) / nrep for k, v in tms.items()}
+        # median over the repetitions: one disturbed repetition (a straggling copy of the e2e legs, an allocator refill)
+        # must not move a stage
+        stages = {k: sorted(r.get(k, 0.0) for r in per_rep)[nrep // 2] for k in per_rep[0]}
         # instance count and tile statistics of this rank's block
         from lgm_b200.dist import shard_views
         vm, pm, _, scene, _ = shard_views(cv_dev, cvp_dev, cp_dev, rank, world)

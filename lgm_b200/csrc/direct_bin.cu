@@ -123,6 +123,36 @@ __device__ __forceinline__ void for_each_touched_tile(const RenderParams& prm, c
     }
 }
 
+// The same enumeration for a rect already held in a register: x0 | y0 << 8 | x1 << 16 | y1 << 24 (tile grids up to 255 x 255;
+// 0 = no footprint).  The count / scatter kernel loads the rects of its kEnumItems Gaussians up front — kEnumItems
+// independent loads in flight instead of a dependent radius -> centre -> rect chain per item (43 % of the scatter's stall
+// samples sat on those two loads) — and walks them twice without reloading.
+template <typename F>
+__device__ __forceinline__ void for_each_tile_of_rect(uint32_t packed, int gx, uint32_t val, uint32_t dbits, F&& f)
+{
+    const int x0 = packed & 0xffu, y0 = (packed >> 8) & 0xffu, x1 = (packed >> 16) & 0xffu, y1 = packed >> 24;
+    const uint32_t area = (uint32_t)((x1 - x0) * (y1 - y0));
+    const bool big = area > kCoopAreaD;
+    if (area != 0 && !big) {
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) f((uint32_t)(y * gx + x), val, dbits);
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t pk = __shfl_sync(0xffffffffu, packed, src);
+        const uint32_t sd = __shfl_sync(0xffffffffu, dbits, src), sv = __shfl_sync(0xffffffffu, val, src);
+        const uint32_t sx0 = pk & 0xffu, sy0 = (pk >> 8) & 0xffu, w = ((pk >> 16) & 0xffu) - sx0;
+        const uint32_t a = w * ((pk >> 24) - sy0);
+        for (uint32_t i = lane; i < a; i += 32) {
+            const uint32_t ry = i / w, rx = i - ry * w;
+            f((sy0 + ry) * (uint32_t)gx + sx0 + rx, sv, sd);
+        }
+    }
+}
+
 // D1 / D3.  A CTA owns kEnumItems x 256 consecutive Gaussians of one view and aggregates in shared memory first: with
 // ~170 non-empty tiles per view, every one of the 62 M instances of a step going to global memory on its own piles
 // ~1,750 same-address atomics on each counter (measured: 2.8 ms count + 3.8 ms scatter, 4 % issue utilisation).
@@ -245,6 +275,64 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     // recounting was measured slower: 0.63 vs 0.53 ms — the recount sweep also warms L1 with the rows the scatter reads)
     __syncthreads();
     for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
+    if (prm.gx <= 255 && prm.gy <= 255) {
+        // rects of this thread's Gaussians, loaded up front (independent loads) and kept packed in registers
+        int rad[kEnumItems];
+        uint32_t rect[kEnumItems];
+#pragma unroll
+        for (int k = 0; k < kEnumItems; k++) {
+            const int idx = first + k * kBlock;
+            rad[k] = idx < prm.P ? radii[(size_t)view * prm.P + idx] : 0;
+        }
+        float2 ctr[kEnumItems];
+#pragma unroll
+        for (int k = 0; k < kEnumItems; k++)
+            ctr[k] = rad[k] > 0 ? xy[(size_t)view * prm.P + first + k * kBlock] : make_float2(0.f, 0.f);
+        uint32_t dbits[kEnumItems];
+#pragma unroll
+        for (int k = 0; k < kEnumItems; k++) {
+            rect[k] = 0u;
+            dbits[k] = 0u;
+            if (rad[k] > 0) {
+                int x0, y0, x1, y1;
+                tile_rect(ctr[k].x, ctr[k].y, rad[k], prm.gx, prm.gy, x0, y0, x1, y1);
+                if ((x1 - x0) * (y1 - y0) != 0) {
+                    rect[k] = (uint32_t)x0 | (uint32_t)y0 << 8 | (uint32_t)x1 << 16 | (uint32_t)y1 << 24;
+                    if (SCATTER) dbits[k] = __float_as_uint(depth[(size_t)view * prm.P + first + k * kBlock]);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kEnumItems; k++)
+            for_each_tile_of_rect(rect[k], prm.gx, 0u, 0u, [&](uint32_t tl, uint32_t, uint32_t) { atomicAdd(&s_hist[tl], 1u); });
+        __syncthreads();
+        if (!SCATTER) {
+            uint32_t mine = 0;
+            for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
+                const uint32_t c = s_hist[i];
+                if (c) atomicAdd(&counts[tile_base + i], c);
+                mine += c;
+            }
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&view_totals[view], mine);
+        } else {
+            for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) {
+                const uint32_t c = s_hist[i];
+                if (c) s_base[i] = ranges[tile_base + i].x + atomicSub(&counts[tile_base + i], c) - c;
+                s_hist[i] = 0u;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kEnumItems; k++)
+                for_each_tile_of_rect(rect[k], prm.gx, (uint32_t)((size_t)view * prm.P + first + k * kBlock), dbits[k],
+                                      [&](uint32_t tl, uint32_t val, uint32_t db) {
+                                          pairs[s_base[tl] + atomicAdd(&s_hist[tl], 1u)] = make_uint2(val, db);
+                                      });
+        }
+        return;
+    }
+    // tile grids beyond 255 tiles in one direction: rects are re-derived in each pass
     __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < kEnumItems; k++)

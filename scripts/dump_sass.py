@@ -18,6 +18,7 @@ KEEP = {  # demangled-name substring -> file tag
     "onesweep_kernel<512, 8, 2, false>": "onesweep_kernel", "tile_ranges_kernel": "tile_ranges_kernel",
     "tile_enumerate_kernel<false>": "tile_count_kernel", "tile_enumerate_kernel<true>": "tile_scatter_kernel",
     "tile_ranges_scan_kernel": "tile_ranges_scan_kernel", "tile_bucket_sort_kernel<512, 5632, 11, 3, true>": "tile_bucket_sort_kernel",
+    "tile_group_sort_kernel<512, 5632, 11, 4>": "tile_group_sort_kernel",
     "coarse_scatter_kernel": "coarse_scatter_kernel", "tile_scatter_entries_kernel": "tile_scatter_entries_kernel",
     # the shipped compositing kernels (two pixels per lane, packed fp32): the instantiations LGM's training step runs
     # (depth image computed in the forward as the reference does; no depth gradient in the backward)
@@ -55,8 +56,10 @@ def main():
                                   "  ".join(f"{k}:{v}" for k, v in ops.most_common(24)) + "\n")
     with open(os.path.join(ROOT, "profiles", f"{prefix}_sass_opcode_histograms.txt"), "w") as f:
         f.write("Static SASS opcode counts per kernel (cuobjdump -sass, sm_100a).  The compositing kernels use the sm_100 packed fp32\n"
-                "instructions FFMA2 / FMUL2 / FADD2 (fma/mul/add.rn.f32x2).  No UTC*MMA / HMMA: the path has no dense contraction;\n"
-                "no UTMALDG / UBLKCP: its staging is an indexed gather (see DESIGN.md §4).\n\n" + "\n".join(hist_lines))
+                "instructions FFMA2 / FMUL2 / FADD2 (fma/mul/add.rn.f32x2) and, in the backward, the vector reduction REDG.E.ADD.F32x4;\n"
+                "the tile sorts use the bulk-copy engine (UBLKPF.L2 prefetch in the default form, UBLKCP + SYNCS staging in the\n"
+                "first form).  No UTC*MMA / HMMA: the path has no dense contraction; the compositing staging is an indexed gather\n"
+                "(see DESIGN.md §4).\n\n" + "\n".join(hist_lines))
     missing = set(KEEP.values()) - done
     print("written:", sorted(done))
     if missing:

@@ -63,7 +63,7 @@ def report(out):
             d.get("dram_read_bytes", 0) / 1e6, d.get("dram_write_bytes", 0) / 1e6, d.get("l1tex_pct", 0), d.get("warp_instructions", 0) / 1e9,
             ", ".join(f"{k} {v:.1f}" for k, v in d["top_stalls"].items())))
     if len(sys.argv) > 2:
-        grp = [d for d in out if any(k in d["kernel"] for k in ("preprocess_fwd", "scan_block", "tile_enumerate", "tile_ranges_scan", "tile_bucket_sort",
+        grp = [d for d in out if any(k in d["kernel"] for k in ("preprocess_fwd", "scan_block", "tile_enumerate", "tile_ranges_scan", "tile_bucket_sort", "tile_group_sort",
                                                                  "coarse_scatter", "tile_scatter_entries"))]
         wi = {}
         for d in out:
