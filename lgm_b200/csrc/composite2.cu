@@ -170,8 +170,21 @@ composite2_fwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
     for (int r0 = 0; r0 < todo; r0 += batch) {
         if (__syncthreads_count(LGM_BOTH_PARKED) == kBlock2) break;  // also the barrier that protects the staging buffer
         const int nb = min(batch, todo - r0);
-        for (int k = threadIdx.x; k < nb; k += kBlock2)
-            sb.template stage<DEPTH>(k, vals[range.x + r0 + k], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+        {
+            // the instance indices of this thread's slots first (independent loads), then the gathers they address
+            constexpr int kPer = BATCH / kBlock2;
+            uint32_t gi[kPer];
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const int k = threadIdx.x + u * kBlock2;
+                gi[u] = k < nb ? vals[range.x + r0 + k] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const int k = threadIdx.x + u * kBlock2;
+                if (k < nb) sb.template stage<DEPTH>(k, gi[u], view_base, scene_g, xy, conic_opacity, depth, tile_x0, tile_y0);
+            }
+        }
         __syncthreads();
         if (warp == 0) LGM_STAT(3, nb);
         for (int base = 0; base < nb; base += 32) {
@@ -367,6 +380,7 @@ composite2_bwd_kernel(const RenderParams prm, const float* __restrict__ gaussian
         __syncthreads();  // the staging buffer is free again
         const int nb = min(batch, todo - r0);
         // slot k holds list position todo-1-(r0+k): the walk is back to front
+        // (loading the thread's instance indices first, as the forward kernel does, measured slower here: 3.95 vs 3.81 ms)
         for (int k = threadIdx.x; k < nb; k += kBlock2)
             sb.template stage<DEPTH>(k, vals[range.x + (uint32_t)(todo - 1 - (r0 + k))], view_base, scene_g, xy, conic_opacity, depth,
                                      tile_x0, tile_y0);

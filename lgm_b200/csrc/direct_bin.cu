@@ -191,6 +191,32 @@ __device__ __forceinline__ uint32_t load_rect(const RenderParams& prm, const int
     return (uint32_t)((x1 - x0) * (y1 - y0));
 }
 
+// The packed rects (x0 | y0 << 8 | x1 << 16 | y1 << 24, 0 = no footprint; tile grids up to 255 x 255) of the kEnumItems
+// Gaussians first, first + 256, ... of `view`: all radii, then all centres — independent loads in flight.
+__device__ __forceinline__ void load_rects_packed(const RenderParams& prm, const int32_t* __restrict__ radii,
+                                                  const float2* __restrict__ xy, int view, int first, uint32_t (&rect)[kEnumItems])
+{
+    int rad[kEnumItems];
+    float2 ctr[kEnumItems];
+#pragma unroll
+    for (int k = 0; k < kEnumItems; k++) {
+        const int idx = first + k * kBlock;
+        rad[k] = idx < prm.P ? radii[(size_t)view * prm.P + idx] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kEnumItems; k++)
+        ctr[k] = rad[k] > 0 ? xy[(size_t)view * prm.P + first + k * kBlock] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kEnumItems; k++) {
+        rect[k] = 0u;
+        if (rad[k] > 0) {
+            int x0, y0, x1, y1;
+            tile_rect(ctr[k].x, ctr[k].y, rad[k], prm.gx, prm.gy, x0, y0, x1, y1);
+            if ((x1 - x0) * (y1 - y0) != 0) rect[k] = (uint32_t)x0 | (uint32_t)y0 << 8 | (uint32_t)x1 << 16 | (uint32_t)y1 << 24;
+        }
+    }
+}
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(kBlock)
 tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
@@ -210,14 +236,26 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     // instances per (view, Gaussian) pair — the instance total is on the device since the preprocess stage's scan
     const bool heavy = !SCATTER && super_counts &&
                        *total_instances >= coarse_gate * (unsigned long long)prm.n_views * (unsigned long long)prm.P;
+    // rects of this thread's Gaussians, loaded up front and kept packed in registers for every pass below
+    const bool small_grid = prm.gx <= 255 && prm.gy <= 255;
+    uint32_t rect[kEnumItems];
+    if (small_grid) load_rects_packed(prm, radii, xy, view, first, rect);
+    auto rect_of = [&](int k, int& x0, int& y0, int& x1, int& y1) -> uint32_t {
+        if (small_grid) {
+            x0 = rect[k] & 0xffu; y0 = (rect[k] >> 8) & 0xffu; x1 = (rect[k] >> 16) & 0xffu; y1 = rect[k] >> 24;
+            return rect[k];
+        }
+        const int idx = first + k * kBlock;
+        return load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1);
+    };
     if (heavy) {
         // entries per super-tile of this CTA's Gaussians (a Gaussian has one entry per super-tile its rect touches)
         for (int i = threadIdx.x; i < n_super; i += kBlock) s_base[i] = 0u;
         __syncthreads();
+#pragma unroll
         for (int k = 0; k < kEnumItems; k++) {
-            const int idx = first + k * kBlock;
             int x0, y0, x1, y1;
-            if (load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+            if (rect_of(k, x0, y0, x1, y1) == 0) continue;
             for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
                 for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) atomicAdd(&s_base[sy * nsx + sx], 1u);
         }
@@ -240,10 +278,10 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
         __syncthreads();
         for (int i = threadIdx.x; i < cells; i += kBlock) grid[i] = 0;
         __syncthreads();
+#pragma unroll
         for (int k = 0; k < kEnumItems; k++) {
-            const int idx = first + k * kBlock;
             int x0, y0, x1, y1;
-            if (load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+            if (rect_of(k, x0, y0, x1, y1) == 0) continue;
             atomicAdd(&grid[y0 * sx + x0], 1);
             atomicAdd(&grid[y0 * sx + x1], -1);
             atomicAdd(&grid[y1 * sx + x0], -1);
@@ -275,33 +313,11 @@ tile_enumerate_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     // recounting was measured slower: 0.63 vs 0.53 ms — the recount sweep also warms L1 with the rows the scatter reads)
     __syncthreads();
     for (int i = threadIdx.x; i < prm.n_tiles; i += kBlock) s_hist[i] = 0u;
-    if (prm.gx <= 255 && prm.gy <= 255) {
-        // rects of this thread's Gaussians, loaded up front (independent loads) and kept packed in registers
-        int rad[kEnumItems];
-        uint32_t rect[kEnumItems];
-#pragma unroll
-        for (int k = 0; k < kEnumItems; k++) {
-            const int idx = first + k * kBlock;
-            rad[k] = idx < prm.P ? radii[(size_t)view * prm.P + idx] : 0;
-        }
-        float2 ctr[kEnumItems];
-#pragma unroll
-        for (int k = 0; k < kEnumItems; k++)
-            ctr[k] = rad[k] > 0 ? xy[(size_t)view * prm.P + first + k * kBlock] : make_float2(0.f, 0.f);
+    if (small_grid) {
         uint32_t dbits[kEnumItems];
 #pragma unroll
-        for (int k = 0; k < kEnumItems; k++) {
-            rect[k] = 0u;
-            dbits[k] = 0u;
-            if (rad[k] > 0) {
-                int x0, y0, x1, y1;
-                tile_rect(ctr[k].x, ctr[k].y, rad[k], prm.gx, prm.gy, x0, y0, x1, y1);
-                if ((x1 - x0) * (y1 - y0) != 0) {
-                    rect[k] = (uint32_t)x0 | (uint32_t)y0 << 8 | (uint32_t)x1 << 16 | (uint32_t)y1 << 24;
-                    if (SCATTER) dbits[k] = __float_as_uint(depth[(size_t)view * prm.P + first + k * kBlock]);
-                }
-            }
-        }
+        for (int k = 0; k < kEnumItems; k++)
+            dbits[k] = (SCATTER && rect[k]) ? __float_as_uint(depth[(size_t)view * prm.P + first + k * kBlock]) : 0u;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kEnumItems; k++)
@@ -532,11 +548,16 @@ coarse_scatter_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
     const int view = blockIdx.y;
     const int first = blockIdx.x * (kBlock * kEnumItems) + threadIdx.x;
     for (int i = threadIdx.x; i < n_super; i += kBlock) s_cnt[i] = 0u;
+    // (the grouping is only used for tile grids up to 255 x 255: the rects are loaded up front and kept in registers)
+    uint32_t rect[kEnumItems], dbits[kEnumItems];
+    load_rects_packed(prm, radii, xy, view, first, rect);
+#pragma unroll
+    for (int k = 0; k < kEnumItems; k++) dbits[k] = rect[k] ? __float_as_uint(depth[(size_t)view * prm.P + first + k * kBlock]) : 0u;
     __syncthreads();
+#pragma unroll
     for (int k = 0; k < kEnumItems; k++) {
-        const int idx = first + k * kBlock;
-        int x0, y0, x1, y1;
-        if (load_rect(prm, radii, xy, (size_t)view * prm.P + idx, idx < prm.P, x0, y0, x1, y1) == 0) continue;
+        if (rect[k] == 0u) continue;
+        const int x0 = rect[k] & 0xffu, y0 = (rect[k] >> 8) & 0xffu, x1 = (rect[k] >> 16) & 0xffu, y1 = rect[k] >> 24;
         for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
             for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) atomicAdd(&s_cnt[sy * nsx + sx], 1u);
     }
@@ -548,19 +569,18 @@ coarse_scatter_kernel(const RenderParams prm, const int32_t* __restrict__ radii,
         s_cnt[i] = 0u;
     }
     __syncthreads();
+#pragma unroll
     for (int k = 0; k < kEnumItems; k++) {
-        const int idx = first + k * kBlock;
-        const size_t gi = (size_t)view * prm.P + idx;
-        int x0, y0, x1, y1;
-        if (load_rect(prm, radii, xy, gi, idx < prm.P, x0, y0, x1, y1) == 0) continue;
-        const uint32_t dbits = __float_as_uint(depth[gi]);
+        if (rect[k] == 0u) continue;
+        const size_t gi = (size_t)view * prm.P + first + k * kBlock;
+        const int x0 = rect[k] & 0xffu, y0 = (rect[k] >> 8) & 0xffu, x1 = (rect[k] >> 16) & 0xffu, y1 = rect[k] >> 24;
         for (int sy = y0 >> kSuperShift; sy <= (y1 - 1) >> kSuperShift; sy++)
             for (int sx = x0 >> kSuperShift; sx <= (x1 - 1) >> kSuperShift; sx++) {
                 const int s = sy * nsx + sx;
                 const int cx0 = max(x0, sx << kSuperShift), cx1 = min(x1, (sx + 1) << kSuperShift);
                 const int cy0 = max(y0, sy << kSuperShift), cy1 = min(y1, (sy + 1) << kSuperShift);
-                const uint32_t rect = (uint32_t)cx0 | (uint32_t)cy0 << 8 | (uint32_t)cx1 << 16 | (uint32_t)cy1 << 24;
-                entries[s_base[s] + atomicAdd(&s_cnt[s], 1u)] = make_uint4((uint32_t)gi, dbits, rect, (uint32_t)view);
+                const uint32_t r = (uint32_t)cx0 | (uint32_t)cy0 << 8 | (uint32_t)cx1 << 16 | (uint32_t)cy1 << 24;
+                entries[s_base[s] + atomicAdd(&s_cnt[s], 1u)] = make_uint4((uint32_t)gi, dbits[k], r, (uint32_t)view);
             }
     }
 }
@@ -991,7 +1011,9 @@ tile_group_sort_kernel(const uint2* __restrict__ pairs, const uint2* __restrict_
             next_range = ranges[next_tile];
         }
 
-        // sweep 2: the keys, grouped by bucket; bucket[b] runs from the bucket's start to its end
+        // sweep 2: the keys, grouped by bucket; bucket[b] runs from the bucket's start to its end.  (Keeping the arrival
+        // index the counting atomic returns, so that this sweep needs no second atomic, was measured slower: 2 more bytes of
+        // shared memory per instance cost a resident CTA, and the atomics are not what bounds the kernel.)
         for (int i = t; i < n; i += T) {
             const uint64_t key = src[i];
             G[atomicAdd(&bucket[LGM_BUCKET((uint32_t)(key >> 32))], 1u)] = key;
