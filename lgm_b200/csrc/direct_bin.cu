@@ -173,6 +173,7 @@ constexpr int kEnumMaxTiles = 6144;  // 2 x 4 B per tile of dynamic shared memor
 // hundreds of pairs.  The entry counts come for free with the tile counts (same enumeration).
 constexpr int kSuperShift = 3, kSuperTiles = 1 << kSuperShift;
 constexpr int kCoarseChunk = 2048;       // entries per work item of the fine scatter
+constexpr uint32_t kCoopFine = 24;       // fine scatter: rects (clipped to a super-tile, <= 64 tiles) above this are walked by the whole warp
 constexpr uint32_t kCoarseMaxSupers = 1024;  // per view (a 4096^2 image); beyond that the plain scatter is used
 
 __host__ __device__ inline int supers_x(const RenderParams& prm) { return (prm.gx + kSuperTiles - 1) >> kSuperShift; }
@@ -616,13 +617,25 @@ tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ en
         const uint32_t e0 = super_offsets[g] + it.y * kCoarseChunk;
         const uint32_t n = min((uint32_t)kCoarseChunk, super_counts[g] - it.y * kCoarseChunk);
         const uint32_t tile_base = (uint32_t)view * (uint32_t)prm.n_tiles;
-        // Two sweeps over the item's entries (L1-resident, 32 KB).  Count per fine tile with a 9 x 9 DIFFERENCE GRID: a rect
-        // adds +1 / -1 / -1 / +1 at its corners and the 2-D prefix sum is the per-tile count — four shared-memory atomics per
-        // entry instead of one per instance.
-        for (uint32_t i = threadIdx.x; i < n; i += kBlock) {
-            const uint4 e = __ldg(entries + e0 + i);
-            const int x0 = (int)(e.z & 255u) - sx0, y0 = (int)((e.z >> 8) & 255u) - sy0;
-            const int x1 = (int)((e.z >> 16) & 255u) - sx0, y1 = (int)(e.z >> 24) - sy0;
+        // This thread's entries of the item, loaded up front (independent 16-byte loads) and kept in registers for both
+        // sweeps — value, depth bits, rect: in the first version every entry of every sweep waited for its own load (24 % of
+        // the kernel's stall samples, source view of the ncu capture).
+        constexpr int kPer = kCoarseChunk / kBlock;
+        uint32_t ev[kPer], ed[kPer], er[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const uint32_t i = threadIdx.x + (uint32_t)u * kBlock;
+            uint4 e = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n) e = __ldg(entries + e0 + i);
+            ev[u] = e.x; ed[u] = e.y; er[u] = e.z;
+        }
+        // Count per fine tile with a 9 x 9 DIFFERENCE GRID: a rect adds +1 / -1 / -1 / +1 at its corners and the 2-D prefix
+        // sum is the per-tile count — four shared-memory atomics per entry instead of one per instance.
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            if (threadIdx.x + (uint32_t)u * kBlock >= n) continue;
+            const int x0 = (int)(er[u] & 255u) - sx0, y0 = (int)((er[u] >> 8) & 255u) - sy0;
+            const int x1 = (int)((er[u] >> 16) & 255u) - sx0, y1 = (int)(er[u] >> 24) - sy0;
             atomicAdd(&s_diff[y0 * kD + x0], 1);
             atomicAdd(&s_diff[y0 * kD + x1], -1);
             atomicAdd(&s_diff[y1 * kD + x0], -1);
@@ -649,21 +662,21 @@ tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ en
             }
         }
         __syncthreads();
-        // place: a warp walks 32 entries at a time; every entry's rect (<= 64 tiles, ~12 on average) is enumerated by its
-        // thread, or by the whole warp when it is large
-        for (uint32_t i0 = 0; i0 < n; i0 += kBlock) {
-            const uint32_t i = i0 + threadIdx.x;
-            uint4 e = make_uint4(0u, 0u, 0u, 0u);
-            if (i < n) e = __ldg(entries + e0 + i);
-            const int x0 = (int)(e.z & 255u) - sx0, y0 = (int)((e.z >> 8) & 255u) - sy0;
-            const int w = (int)((e.z >> 16) & 255u) - sx0 - x0, h = (int)(e.z >> 24) - sy0 - y0;
-            const uint32_t area = i < n ? (uint32_t)(w * h) : 0u;
-            const bool big = area > kCoopAreaD;
+        // place: every entry's rect (<= 64 tiles, ~12 on average) is enumerated by its thread, or by the whole warp when it
+        // is large (kCoopFine: the warp-wide walk costs ~10 x a thread's own walk per instance, so only rects that would
+        // stall the other lanes for long take it)
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const bool in_range = threadIdx.x + (uint32_t)u * kBlock < n;
+            const int x0 = (int)(er[u] & 255u) - sx0, y0 = (int)((er[u] >> 8) & 255u) - sy0;
+            const int w = (int)((er[u] >> 16) & 255u) - sx0 - x0, h = (int)(er[u] >> 24) - sy0 - y0;
+            const uint32_t area = in_range ? (uint32_t)(w * h) : 0u;
+            const bool big = area > kCoopFine;
             if (area != 0u && !big) {
                 for (int y = y0; y < y0 + h; y++)
                     for (int x = x0; x < x0 + w; x++) {
                         const int f = y * kSuperTiles + x;
-                        pairs[s_base[f] + atomicAdd(&s_cnt[f], 1u)] = make_uint2(e.x, e.y);
+                        pairs[s_base[f] + atomicAdd(&s_cnt[f], 1u)] = make_uint2(ev[u], ed[u]);
                     }
             }
             unsigned m = __ballot_sync(0xffffffffu, big);
@@ -671,11 +684,13 @@ tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ en
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t a = __shfl_sync(0xffffffffu, area, src);
-                const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-                const uint32_t bw = (uint32_t)__shfl_sync(0xffffffffu, w, src);
-                const uint32_t sv = __shfl_sync(0xffffffffu, e.x, src), sd = __shfl_sync(0xffffffffu, e.y, src);
+                const uint32_t pk = __shfl_sync(0xffffffffu, (uint32_t)x0 | (uint32_t)y0 << 8 | (uint32_t)w << 16, src);
+                const uint32_t sv = __shfl_sync(0xffffffffu, ev[u], src), sd = __shfl_sync(0xffffffffu, ed[u], src);
+                const int bx0 = pk & 255u, by0 = (pk >> 8) & 255u;
+                const uint32_t bw = pk >> 16;                       // 1..8
+                const uint32_t inv = (65536u + bw - 1u) / bw;       // q / bw == (q * inv) >> 16 for q < 64 (warp-uniform)
                 for (uint32_t q = lane; q < a; q += 32) {
-                    const uint32_t ry = q / bw, rx = q - ry * bw;
+                    const uint32_t ry = (q * inv) >> 16, rx = q - ry * bw;
                     const int f = (by0 + (int)ry) * kSuperTiles + bx0 + (int)rx;
                     pairs[s_base[f] + atomicAdd(&s_cnt[f], 1u)] = make_uint2(sv, sd);
                 }
