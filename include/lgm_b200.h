@@ -73,9 +73,11 @@ const char* lgm_last_error_string(void);
  * staged per block barrier by the compositing kernels, multiple of 32), "patch_lanes" (32 | 16 | 8), "sort_variant"
  * (launch shape of the onesweep sort), "enum_global" (1: binning enumeration without the per-CTA shared-memory stage),
  * "coarse_ratio" (instances per coarse entry from which the direct binning groups by super-tile first; 0 = never),
- * "c2_occ" (100 x forward + backward resident CTAs per SM of the compositing kernels), "sort_bulk" (0: tile sort staged
- * by a load / store loop instead of the bulk copy), "sparse_lanes" (backward compositing: hits with at most this many
- * lanes holding a contributing pixel send their terms with vector reductions instead of the warp reduction; 0 = never).
+ * "c2_occ" (100 x forward + backward resident CTAs per SM of the compositing kernels), "sort_bulk" (form of the per-tile
+ * sort of the direct path: 2 = keys read from global memory and grouped in shared memory, the default; 1 = segment staged by
+ * a bulk copy (TMA), indices grouped; 0 = the same staged by a load / store loop), "sparse_lanes" (backward compositing:
+ * hits with at most this many lanes holding a contributing pixel send their terms with vector reductions instead of the
+ * warp reduction; 0 = never).
  * value < 0 restores the default. */
 int lgm_set_tuning(const char* name, int32_t value);
 
