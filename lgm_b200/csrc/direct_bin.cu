@@ -21,30 +21,33 @@
 // D4 is a bucket sort: keys are mapped monotonically to ~n/2 buckets by (depth - min) * nb / (range + 1), counted and
 // grouped with shared-memory atomics (two sweeps), and each element finds its final slot by counting the smaller keys
 // in its own bucket (2 on average).  No ballots, no per-warp histograms: ~70 instructions per element against ~6 x 45
-// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  Four size classes (S: <= 2,048 instances, 256
-// threads, 6 CTAs per SM; M: <= 5,632, 512 threads, 3 CTAs; X: <= 11,776, 1024 threads, 2 CTAs; L: <= 20,480, one 1024-thread
-// CTA per SM).  A tile whose keys pile up in few buckets (depth ties) is ordered by a bitonic network instead of the rank
-// loop, when the loop would make more compares than the network.  A longer tile cannot be staged in shared memory: the caller (api.cu) reads the longest tile back and
-// uses the onesweep path for such a step.
+// for the LSD passes, and 20 B of HBM traffic per instance instead of 152.  A tile whose keys pile up in few buckets
+// (depth ties) is ordered by a bitonic network instead of the rank loop, when the loop would make more compares than the
+// network.  Two forms (lgm_set_tuning "sort_bulk"): tile_group_sort_kernel (default) reads the segment from global memory
+// and groups the KEYS in shared memory, 8 B per instance; tile_bucket_sort_kernel stages the segment (load / store loop or
+// one TMA bulk copy) and groups 16-bit indices, 10 B per instance.  Four size classes (S: <= 2,048 instances, 256 threads;
+// M: <= 5,632, 512 threads; X: <= 11,776, 1024 threads, two CTAs per SM in the default form; L: <= 20,480, one 1024-thread
+// CTA per SM).  A longer tile cannot be held in shared memory: the caller (api.cu) is told the longest tile and uses the
+// onesweep path for such a step.
 #include "common.cuh"
 #include "splat_math.cuh"
 
 namespace lgm {
 namespace {
 
-// Size classes of the per-tile sort.  M: tiles of up to 5,632 instances, 512 threads, 63 KB of shared memory, 3 CTAs
-// per SM — the trained-scene case.  L: up to 20,480 instances, 1024 threads, 216 KB, one CTA per SM — untrained
-// Gaussians, 1024^2 views of 1 M Gaussians.  (10 B per element: 64-bit key + 16-bit index; 4 B per bucket.)
-constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
-// S: tiles of up to 2,048 instances, 256 threads, 25 KB, 6 CTAs per SM.  A trained scene's tiles hold ~750 instances on
-// average: with 512 threads most of a CTA idles through the barriers, bucket scans and the two-iteration sweeps of such a
-// tile (the fixed cost per tile is paid by every warp).
+// Size classes of the per-tile sort (shared memory per CTA in the default / the staged form).
+// S: tiles of up to 2,048 instances, 256 threads, 21 / 25 KB, 8 / 6 CTAs per SM.  A trained scene's tiles hold ~750
+// instances on average: with 512 threads most of a CTA idles through the barriers, bucket scans and the two-iteration
+// sweeps of such a tile (the fixed cost per tile is paid by every warp).
 constexpr int kSortThreadsS = 256, kSortCapS = 2048, kLgBucketsS = 10;
-constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
-// X: the class between them — tiles of up to 11,776 instances, 1024 threads, 111 KB in the grouped-keys form: TWO CTAs per SM, so that one CTA's
-// global load / store phases overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians have most of their
-// instances in such tiles; with the L class alone they ran one CTA per SM at 50 % of the warp slots)
+// M: up to 5,632 instances, 512 threads, 54 / 64 KB, 4 / 3 CTAs per SM — where most instances of a trained scene live.
+constexpr int kSortThreadsM = 512, kSortCapM = 5632, kLgBucketsM = 11;
+// X: up to 11,776 instances, 1024 threads, 111 KB in the default form: TWO CTAs per SM, so that one CTA's global phases
+// overlap the other's shared-memory phases (1024^2 views of 1 M Gaussians and untrained Gaussians have most of their
+// instances in such tiles; 134 KB and one CTA per SM in the staged form).
 constexpr int kSortThreadsX = 1024, kSortCapX = 11776, kLgBucketsX = 12;
+// L: up to 20,480 instances, 1024 threads, 180 / 216 KB, one CTA per SM; launched first.
+constexpr int kSortThreadsL = 1024, kSortCapL = 20480, kLgBucketsL = 12;
 // (+ 16 B: the bulk copy of a segment starts at a 16-byte boundary, up to one pair before the segment, and ends at one)
 constexpr size_t sort_smem(int cap, int lg_buckets) { return (size_t)cap * 10 + 16 + (size_t)((1 << lg_buckets) + 1) * 4 + 64 * 4; }
 
