@@ -77,7 +77,8 @@ const char* lgm_last_error_string(void);
  * sort of the direct path: 2 = keys read from global memory and grouped in shared memory, the default; 1 = segment staged by
  * a bulk copy (TMA), indices grouped; 0 = the same staged by a load / store loop), "sparse_lanes" (backward compositing:
  * hits with at most this many lanes holding a contributing pixel send their terms with vector reductions instead of the
- * warp reduction; 0 = never).
+ * warp reduction; 0 = never), "fine_tile_major" (scatter of the heavy steps: 1 = every fine tile sweeps the super-tile's
+ * entries, 0 = every entry walks its tiles; default: by the step's instances per entry).
  * value < 0 restores the default. */
 int lgm_set_tuning(const char* name, int32_t value);
 

@@ -86,7 +86,7 @@ def lib():
 # Tuning / test hooks of the library (lgm_set_tuning) and the environment variables that drive them from Python.  The
 # C library itself never reads the environment; apply_env_tuning() is called by ops at the head of every render.
 _TUNING_ENV = {"fwd_batch": "LGM_FWD_BATCH", "bwd_batch": "LGM_BWD_BATCH", "patch_lanes": "LGM_PATCH_LANES",
-               "sort_variant": "LGM_SORT_VARIANT", "enum_global": "LGM_ENUM_GLOBAL", "coarse_ratio": "LGM_COARSE_RATIO", "c2_occ": "LGM_C2_OCC", "sort_bulk": "LGM_SORT_BULK", "sparse_lanes": "LGM_SPARSE_LANES"}
+               "sort_variant": "LGM_SORT_VARIANT", "enum_global": "LGM_ENUM_GLOBAL", "coarse_ratio": "LGM_COARSE_RATIO", "c2_occ": "LGM_C2_OCC", "sort_bulk": "LGM_SORT_BULK", "sparse_lanes": "LGM_SPARSE_LANES", "fine_tile_major": "LGM_FINE_TILE_MAJOR"}
 _tuning_applied = {}
 BIN_MODE_IDS = {"auto": 0, "onesweep": 1, "hybrid": 2, "direct": 3}
 

@@ -99,8 +99,8 @@ BinWorkspace bin_layout(const lgm::RenderParams& p, uint32_t L, uint64_t E)
 thread_local int g_last_bin_mode = LGM_BIN_NONE;
 thread_local bool g_last_coarse = false;
 
-std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
-const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ", "sort_bulk", "sparse_lanes"};
+std::atomic<int> g_tuning[lgm::kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
+const char* const kTuningNames[lgm::kTuneCount] = {"fwd_batch", "patch_lanes", "bwd_batch", "sort_variant", "enum_global", "coarse_ratio", "c2_occ", "sort_bulk", "sparse_lanes", "fine_tile_major"};
 std::atomic<int> g_sm_count[lgm::kMaxDevices];
 
 }  // namespace
@@ -134,7 +134,7 @@ int lgm_set_tuning(const char* name, int32_t value)
             g_tuning[i].store(value, std::memory_order_relaxed);
             return LGM_OK;
         }
-    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global, coarse_ratio, c2_occ, sort_bulk, sparse_lanes)");
+    return fail(LGM_ERR_BAD_VALUE, "lgm_set_tuning: unknown name (fwd_batch, bwd_batch, patch_lanes, sort_variant, enum_global, coarse_ratio, c2_occ, sort_bulk, sparse_lanes, fine_tile_major)");
 }
 
 int lgm_direct_bin_tile_cap(void) { return lgm::direct_bin_tile_cap(); }
@@ -277,7 +277,8 @@ int lgm_forward_bin(void* stream, const lgm_render_params* prm, const int32_t* r
         g_last_coarse = entries != nullptr;
         LGM_CUDA(lgm::launch_direct_bin_sort(s, p, radii, reinterpret_cast<const float2*>(xy), depth,
                                              reinterpret_cast<const uint2*>(ranges), keys_tmp, vals_sorted,
-                                             want_sorted_keys ? keys_sorted : nullptr, count_workspace, (uint32_t)longest_tile, entries),
+                                             want_sorted_keys ? keys_sorted : nullptr, count_workspace, (uint32_t)longest_tile, entries,
+                                             coarse_entries > 0 ? (uint32_t)((uint64_t)L / (uint64_t)coarse_entries) : 0u),
                  "forward_bin: direct sort");
         g_last_bin_mode = LGM_BIN_DIRECT;
         return LGM_OK;

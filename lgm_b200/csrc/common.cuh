@@ -31,7 +31,7 @@ inline cudaError_t opt_in_dynamic_smem(Kernel kernel, size_t bytes, std::atomic<
 }
 
 // ---- tuning / test hooks (lgm_set_tuning in include/lgm_b200.h; process-wide, read at launch time; api.cu) ----
-enum Tuning { kTuneFwdBatch = 0, kTunePatchLanes, kTuneBwdBatch, kTuneSortVariant, kTuneEnumGlobal, kTuneCoarseRatio, kTuneC2Occ, kTuneSortBulk, kTuneSparseLanes, kTuneCount };
+enum Tuning { kTuneFwdBatch = 0, kTunePatchLanes, kTuneBwdBatch, kTuneSortVariant, kTuneEnumGlobal, kTuneCoarseRatio, kTuneC2Occ, kTuneSortBulk, kTuneSparseLanes, kTuneFineTileMajor, kTuneCount };
 int tuning(Tuning which);  // < 0: not set, the kernel's built-in default applies
 
 struct RenderParams {
@@ -67,7 +67,8 @@ cudaError_t launch_direct_bin_count(cudaStream_t stream, const RenderParams& prm
 bool direct_bin_use_coarse(const RenderParams& prm, uint64_t n_instances, uint64_t coarse_entries);
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
-                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile, void* entries);
+                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile, void* entries,
+                                   uint32_t instances_per_entry = 0);
 // loss.cu: MSE(image) + MSE(alpha) and its gradient in one pass (core/models.py:153)
 cudaError_t launch_mse_loss_grad(cudaStream_t stream, const float* image, const float* gt_image, float* d_image, size_t n_img,
                                  float w_img, const float* alpha, const float* gt_alpha, float* d_alpha, size_t n_alpha,

@@ -176,6 +176,10 @@ constexpr int kEnumMaxTiles = 6144;  // 2 x 4 B per tile of dynamic shared memor
 // hundreds of pairs.  The entry counts come for free with the tile counts (same enumeration).
 constexpr int kSuperShift = 3, kSuperTiles = 1 << kSuperShift;
 constexpr int kCoarseChunk = 2048;       // entries per work item of the fine scatter
+// fine scatter: from this many instances per entry on, the placement is tile-major (cost ~ 64 tests per entry, coalesced
+// stores, no atomics) instead of entry-major (cost ~ instances).  Measured: untrained Gaussians (~25 per entry) bin 12.8 ->
+// 10.6 ms tile-major; 1 M Gaussians at 1024^2 (9 per entry) 7.2 -> 9.5 ms.
+constexpr uint32_t kTileMajorRatio = 16;
 constexpr uint32_t kCoopFine = 24;       // fine scatter: rects (clipped to a super-tile, <= 64 tiles) above this are walked by the whole warp
 constexpr uint32_t kCoarseMaxSupers = 1024;  // per view (a 4096^2 image); beyond that the plain scatter is used
 
@@ -596,10 +600,11 @@ __global__ void __launch_bounds__(kBlock, 4)
 tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ entries, const uint32_t* __restrict__ super_offsets,
                             const uint32_t* __restrict__ super_counts, const uint2* __restrict__ items,
                             const uint32_t* __restrict__ head, uint32_t* __restrict__ item_cursor, uint32_t* __restrict__ counts,
-                            const uint2* __restrict__ ranges, uint2* __restrict__ pairs)
+                            const uint2* __restrict__ ranges, uint2* __restrict__ pairs, int tile_major)
 {
     constexpr int kFine = kSuperTiles * kSuperTiles, kD = kSuperTiles + 1;
     __shared__ uint32_t s_cnt[kFine], s_base[kFine];
+    __shared__ uint32_t s_ev[kCoarseChunk], s_ed[kCoarseChunk], s_er[kCoarseChunk];  // tile_major: the item's entries
     __shared__ int s_diff[kD * kD];
     __shared__ uint32_t s_item;
     const int nsx = supers_x(prm), n_super = nsx * supers_y(prm);
@@ -665,6 +670,44 @@ tile_scatter_entries_kernel(const RenderParams prm, const uint4* __restrict__ en
             }
         }
         __syncthreads();
+        if (tile_major) {
+            // TILE-MAJOR placement: a warp owns eight of the 64 fine tiles; for each it sweeps the item's entries (staged in
+            // shared memory), and the lanes whose rect contains the tile write their pair at consecutive slots of the tile's
+            // run (ballot + popc): no shared-memory atomics, and every store of a warp lands in one run — full 32-byte
+            // sectors instead of one sector per 8-byte pair (the entry-major walk wrote 461 M sectors for 499 M pairs and
+            // kept L2 at 60 % of its throughput).
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const uint32_t i = threadIdx.x + (uint32_t)u * kBlock;
+                if (i < n) {
+                    s_ev[i] = ev[u];
+                    s_ed[i] = ed[u];
+                    // rect relative to the super-tile, one byte per coordinate: x0 | y0 << 8 | x1 << 16 | y1 << 24
+                    s_er[i] = er[u] - ((uint32_t)sx0 | (uint32_t)sy0 << 8 | (uint32_t)sx0 << 16 | (uint32_t)sy0 << 24);
+                }
+            }
+            __syncthreads();
+            const int warp = threadIdx.x >> 5;
+            const uint32_t lt_mask = (1u << lane) - 1u;
+            for (int f = warp; f < kFine; f += kBlock / 32) {
+                const int fx = f & (kSuperTiles - 1), fy = f >> kSuperShift;
+                if (s_diff[fy * kD + fx] == 0) continue;  // no instance of this item in the tile
+                uint32_t out = s_base[f];
+                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    bool inside = false;
+                    if (i < n) {
+                        const uint32_t r = s_er[i];
+                        inside = (uint32_t)fx >= (r & 255u) && (uint32_t)fx < ((r >> 16) & 255u) &&
+                                 (uint32_t)fy >= ((r >> 8) & 255u) && (uint32_t)fy < (r >> 24);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, inside);
+                    if (inside) pairs[out + __popc(m & lt_mask)] = make_uint2(s_ev[i], s_ed[i]);
+                    out += __popc(m);
+                }
+            }
+            continue;  // (the loop head synchronises before shared memory is reused)
+        }
         // place: every entry's rect (<= 64 tiles, ~12 on average) is enumerated by its thread, or by the whole warp when it
         // is large (kCoopFine: the warp-wide walk costs ~10 x a thread's own walk per instance, so only rects that would
         // stall the other lanes for long take it)
@@ -1158,7 +1201,8 @@ bool direct_bin_use_coarse(const RenderParams& prm, uint64_t n_instances, uint64
 // (entry buffer of coarse_entries x 16 B), then the fine scatter from the grouped entries.
 cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm, const int32_t* radii, const float2* xy,
                                    const float* depth, const uint2* ranges, void* pairs, uint32_t* vals_sorted,
-                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile, void* entries)
+                                   uint64_t* keys_sorted, void* scratch, uint32_t longest_tile, void* entries,
+                                   uint32_t instances_per_entry)
 {
     const uint32_t n_ranges = (uint32_t)prm.n_views * (uint32_t)prm.n_tiles;
     const DirectScratch d = direct_scratch(prm, scratch);
@@ -1202,7 +1246,9 @@ cudaError_t launch_direct_bin_sort(cudaStream_t stream, const RenderParams& prm,
         if ((err = cudaGetLastError()) != cudaSuccess) return err;
         tile_scatter_entries_kernel<<<4 * n_sm, kBlock, 0, stream>>>(prm, static_cast<const uint4*>(entries), d.super_offsets,
                                                                      d.super_counts, d.items, d.head, d.head + kHeadItemCursor, d.counts,
-                                                                     ranges, static_cast<uint2*>(pairs));
+                                                                     ranges, static_cast<uint2*>(pairs),
+                                                                     tuning(kTuneFineTileMajor) >= 0 ? tuning(kTuneFineTileMajor)
+                                                                                                     : (instances_per_entry >= kTileMajorRatio));
         err = cudaGetLastError();
     } else {
         err = launch_tile_enumerate<true>(stream, prm, radii, xy, depth, d.counts, d.view_totals, ranges, static_cast<uint2*>(pairs));

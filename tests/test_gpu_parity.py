@@ -528,6 +528,12 @@ def test_binning_modes_are_bit_identical(monkeypatch):
         if longest <= 20480:
             monkeypatch.setenv("LGM_COARSE_RATIO", "1")
             c1 = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
+            # both placements of the fine scatter: every entry walks its tiles / every tile sweeps the entries
+            for tm in ("0", "1"):
+                monkeypatch.setenv("LGM_FINE_TILE_MAJOR", tm)
+                ct = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
+                assert ct["coarse"] and _same_binning(res["onesweep"], ct), f"{kind} N={N}: fine scatter placement {tm} differs"
+            monkeypatch.delenv("LGM_FINE_TILE_MAJOR")
             monkeypatch.setenv("LGM_COARSE_RATIO", "0")
             c0 = _bin_result(monkeypatch, "direct", g, cv, cvp, S)
             monkeypatch.delenv("LGM_COARSE_RATIO")
